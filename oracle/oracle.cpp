@@ -1,0 +1,754 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.
+// CPU restatement of the plonkit prove path, used as the parity checker for the CUDA library and as the
+// timed "restated CPU baseline" (bench.py cpu_baseline / --impl reference).  Never linked into, imported by
+// or called from the product (plonkit_b200/); the product fails loudly if its CUDA library is missing.
+//
+// PARITY PIN: tests/test_oracle.py checks that orc_prove / orc_setup_commitments reproduce the reference's own
+// golden files byte-for-byte (test/circuits/simple/proof.bin and vk.bin, asserted by src/tests.rs:30-73).
+//
+// What is restated, and from where (the arithmetic lives in bellman_ce 0.3.2 @5809cc16, Cargo.lock:109-111,
+// which is NOT under /root/reference; the in-tree anchors are cited per function):
+//   * prove(): call sites src/plonk.rs:140,152-159; algebra = SURVEY.md App. A, which follows the in-tree
+//     Solidity verifier contrib/template.sol:445-758 (identities) and :267-307 (transcript).
+//   * setup polynomials / verification key: src/plonk.rs:104,122-124; layout SURVEY.md App. A.2/A.3, B.3.
+//   * radix-2 NTT (serial_fft / parallel_fft) and dense Pippenger (dense_multiexp): bellman's published
+//     algorithms (domain.rs / multiexp.rs [ext]); window c = ceil(ln(chunk_len)), c = 3 below 32 elements.
+//   * SRS generation Crs::crs_42: src/plonk.rs:41,47 (tau = 42).
+//   * EC inverse FFT Crs::from_powers: src/plonk.rs:179-185.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "bn254.hpp"
+#include "keccak.hpp"
+
+using namespace orc;
+
+// ---------------------------------------------------------------- threading (stands in for bellman's Worker)
+template <class F> static void parallel_chunks(size_t n, int threads, F f) {
+    if (threads < 1) threads = 1;
+    if (n == 0) return;
+    size_t chunk = (n + threads - 1) / threads;  // Worker::get_chunk_size [ext]
+    if (threads == 1 || n < 64) { f(0, n, 0); return; }
+    std::vector<std::thread> th;
+    int tid = 0;
+    for (size_t b = 0; b < n; b += chunk, ++tid) {
+        size_t e = std::min(n, b + chunk);
+        th.emplace_back([=] { f(b, e, tid); });
+    }
+    for (auto& t : th) t.join();
+}
+
+static int log2_floor(size_t x) { int l = 0; while ((size_t(1) << (l + 1)) <= x) ++l; return l; }
+
+// ---------------------------------------------------------------- domains
+static Fr root_of_unity_2_28() {
+    // g = 7^((r-1)/2^28)
+    u64 e[4];
+    u64 one[4] = {1, 0, 0, 0};
+    sub4(e, Params<FrTag>::P, one);
+    // shift right by 28
+    for (int i = 0; i < 4; ++i) e[i] = (e[i] >> 28) | (i < 3 ? (e[i + 1] << 36) : 0);
+    return Fr::from_u64(7).pow(e, 4);
+}
+static Fr omega_for(int log_n) {
+    Fr g = root_of_unity_2_28();
+    for (int i = 0; i < 28 - log_n; ++i) g = g.sqr();
+    return g;
+}
+
+// ---------------------------------------------------------------- radix-2 NTT (bellman domain.rs serial_fft/parallel_fft [ext])
+static inline uint32_t bitrev32(uint32_t x, int bits) {
+    uint32_t r = 0;
+    for (int i = 0; i < bits; ++i) { r = (r << 1) | (x & 1); x >>= 1; }
+    return r;
+}
+static void serial_fft(Fr* a, size_t n, const Fr& omega, int log_n) {
+    for (size_t k = 0; k < n; ++k) {
+        size_t rk = bitrev32((uint32_t)k, log_n);
+        if (k < rk) std::swap(a[k], a[rk]);
+    }
+    size_t m = 1;
+    for (int s = 0; s < log_n; ++s) {
+        u64 e = n / (2 * m);
+        Fr w_m = omega.pow_u64(e);
+        for (size_t k = 0; k < n; k += 2 * m) {
+            Fr w = Fr::one();
+            for (size_t j = 0; j < m; ++j) {
+                Fr t = a[k + j + m] * w;
+                a[k + j + m] = a[k + j] - t;
+                a[k + j] = a[k + j] + t;
+                w *= w_m;
+            }
+        }
+        m *= 2;
+    }
+}
+static void parallel_fft(Fr* a, size_t n, const Fr& omega, int log_n, int log_cpus) {
+    size_t num_cpus = size_t(1) << log_cpus;
+    int log_new_n = log_n - log_cpus;
+    size_t new_n = size_t(1) << log_new_n;
+    std::vector<std::vector<Fr>> tmp(num_cpus, std::vector<Fr>(new_n, Fr::zero()));
+    Fr new_omega = omega.pow_u64(num_cpus);
+    std::vector<std::thread> th;
+    for (size_t j = 0; j < num_cpus; ++j) {
+        th.emplace_back([&, j] {
+            Fr omega_j = omega.pow_u64(j);
+            Fr omega_step = omega.pow_u64((u64)j << log_new_n);
+            Fr elt = Fr::one();
+            std::vector<Fr>& t = tmp[j];
+            for (size_t i = 0; i < new_n; ++i) {
+                for (size_t s = 0; s < num_cpus; ++s) {
+                    size_t idx = (i + (s << log_new_n)) % n;
+                    t[i] += a[idx] * elt;
+                    elt *= omega_step;
+                }
+                elt *= omega_j;
+            }
+            serial_fft(t.data(), new_n, new_omega, log_new_n);
+        });
+    }
+    for (auto& t : th) t.join();
+    size_t mask = num_cpus - 1;
+    parallel_chunks(n, (int)num_cpus, [&](size_t b, size_t e, int) {
+        for (size_t idx = b; idx < e; ++idx) a[idx] = tmp[idx & mask][idx >> log_cpus];
+    });
+}
+static void best_fft(Fr* a, size_t n, const Fr& omega, int log_n, int threads) {
+    int log_cpus = log2_floor(threads < 1 ? 1 : threads);
+    if (log_n <= log_cpus || log_cpus == 0) serial_fft(a, n, omega, log_n);
+    else parallel_fft(a, n, omega, log_n, log_cpus);
+}
+static void distribute_powers(Fr* a, size_t n, const Fr& g, int threads) {
+    parallel_chunks(n, threads, [&](size_t b, size_t e, int) {
+        Fr x = g.pow_u64(b);
+        for (size_t i = b; i < e; ++i) { a[i] *= x; x *= g; }
+    });
+}
+static void scale_all(Fr* a, size_t n, const Fr& s, int threads) {
+    parallel_chunks(n, threads, [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) a[i] *= s; });
+}
+static void fft(std::vector<Fr>& a, int threads) {
+    int log_n = log2_floor(a.size());
+    best_fft(a.data(), a.size(), omega_for(log_n), log_n, threads);
+}
+static void ifft(std::vector<Fr>& a, int threads) {
+    int log_n = log2_floor(a.size());
+    best_fft(a.data(), a.size(), omega_for(log_n).inverse(), log_n, threads);
+    scale_all(a.data(), a.size(), Fr::from_u64(a.size()).inverse(), threads);
+}
+static const u64 COSET_GEN = 7;  // Fr::multiplicative_generator()
+static void coset_fft(std::vector<Fr>& a, int threads) {
+    distribute_powers(a.data(), a.size(), Fr::from_u64(COSET_GEN), threads);
+    fft(a, threads);
+}
+static void icoset_fft(std::vector<Fr>& a, int threads) {
+    ifft(a, threads);
+    distribute_powers(a.data(), a.size(), Fr::from_u64(COSET_GEN).inverse(), threads);
+}
+
+// ---------------------------------------------------------------- dense Pippenger (bellman multiexp.rs dense_multiexp [ext])
+struct Repr { u64 v[4]; };
+static G1 dense_multiexp_inner(const G1Affine* bases, const Repr* exps, size_t n, unsigned skip, unsigned c,
+                               bool handle_trivial, int threads) {
+    G1 region = G1::infinity();
+    std::mutex mu;
+    parallel_chunks(n, threads, [&](size_t b, size_t e, int) {
+        std::vector<G1> buckets((size_t(1) << c) - 1, G1::infinity());
+        G1 acc = G1::infinity();
+        for (size_t i = b; i < e; ++i) {
+            const u64* x = exps[i].v;
+            if ((x[0] | x[1] | x[2] | x[3]) == 0) continue;
+            if (x[0] == 1 && (x[1] | x[2] | x[3]) == 0) {
+                if (handle_trivial) acc = acc.add_mixed(bases[i]);
+                continue;
+            }
+            // (exp >> skip) % 2^c
+            unsigned limb = skip / 64, off = skip % 64;
+            u64 w = limb < 4 ? x[limb] >> off : 0;
+            if (off && limb + 1 < 4) w |= x[limb + 1] << (64 - off);
+            w &= (u64(1) << c) - 1;
+            if (w != 0) buckets[w - 1] = buckets[w - 1].add_mixed(bases[i]);
+        }
+        G1 running = G1::infinity();
+        for (size_t k = buckets.size(); k-- > 0;) {
+            running = running.add(buckets[k]);
+            acc = acc.add(running);
+        }
+        std::lock_guard<std::mutex> lk(mu);
+        region = region.add(acc);
+    });
+    skip += c;
+    if (skip >= 254) return region;  // Fr::NUM_BITS
+    G1 next = dense_multiexp_inner(bases, exps, n, skip, c, false, threads);
+    for (unsigned i = 0; i < c; ++i) next = next.dbl();
+    return next.add(region);
+}
+static G1 dense_multiexp(const G1Affine* bases, const Repr* exps, size_t n, int threads) {
+    if (n == 0) return G1::infinity();
+    unsigned c;
+    if (n < 32) c = 3;
+    else {
+        size_t chunk = (n + threads - 1) / threads;
+        c = (unsigned)std::ceil(std::log((double)chunk));
+        if (c < 1) c = 1;
+    }
+    return dense_multiexp_inner(bases, exps, n, 0, c, true, threads);
+}
+static G1Affine commit(const std::vector<Fr>& coeffs, const G1Affine* srs, int threads) {
+    size_t n = coeffs.size();
+    std::vector<Repr> reprs(n);
+    parallel_chunks(n, threads, [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) coeffs[i].to_canonical(reprs[i].v); });
+    return dense_multiexp(srs, reprs.data(), n, threads).to_affine();
+}
+
+// ---------------------------------------------------------------- byte encodings (big-endian canonical)
+static void be32(const u64 c[4], uint8_t* out) {
+    for (int i = 0; i < 32; ++i) out[i] = (uint8_t)(c[(31 - i) / 8] >> (8 * ((31 - i) % 8)));
+}
+static void write_fr_be(const Fr& x, uint8_t* out) { u64 c[4]; x.to_canonical(c); be32(c, out); }
+static void write_g1_be(const G1Affine& p, uint8_t* out) {
+    if (p.inf) { memset(out, 0, 64); out[0] = 0x40; return; }
+    u64 c[4];
+    p.x.to_canonical(c); be32(c, out);
+    p.y.to_canonical(c); be32(c, out + 32);
+}
+static void write_u64_be(u64 x, uint8_t* out) { for (int i = 0; i < 8; ++i) out[i] = (uint8_t)(x >> (8 * (7 - i))); }
+
+// ---------------------------------------------------------------- RollingKeccakTranscript (contrib/template.sol:267-307)
+struct Transcript {
+    uint8_t s0[32], s1[32];
+    uint32_t ctr;
+    Transcript() { memset(s0, 0, 32); memset(s1, 0, 32); ctr = 0; }
+    void update_u256(const uint8_t v[32]) {
+        uint8_t buf[4 + 96], n0[32], n1[32];
+        memset(buf, 0, 4);
+        memcpy(buf + 4, s0, 32); memcpy(buf + 36, s1, 32); memcpy(buf + 68, v, 32);
+        buf[3] = 0; keccak256(buf, 100, n0);
+        buf[3] = 1; keccak256(buf, 100, n1);
+        memcpy(s0, n0, 32); memcpy(s1, n1, 32);
+    }
+    void update_fr(const Fr& x) { uint8_t b[32]; write_fr_be(x, b); update_u256(b); }
+    void update_g1(const G1Affine& p) {
+        uint8_t b[64];
+        if (p.inf) memset(b, 0, 64);  // infinity hashes as (0, 0)  [probe: golden C_d, C_t3]
+        else { u64 c[4]; p.x.to_canonical(c); be32(c, b); p.y.to_canonical(c); be32(c, b + 32); }
+        update_u256(b); update_u256(b + 32);
+    }
+    Fr challenge() {
+        uint8_t buf[4 + 64 + 4], h[32];
+        buf[0] = buf[1] = buf[2] = 0; buf[3] = 2;
+        memcpy(buf + 4, s0, 32); memcpy(buf + 36, s1, 32);
+        buf[68] = (uint8_t)(ctr >> 24); buf[69] = (uint8_t)(ctr >> 16); buf[70] = (uint8_t)(ctr >> 8); buf[71] = (uint8_t)ctr;
+        ++ctr;
+        keccak256(buf, 72, h);
+        h[0] &= 0x1f;  // FR_MASK: keep the low 253 bits
+        u64 c[4] = {0, 0, 0, 0};
+        for (int i = 0; i < 32; ++i) c[(31 - i) / 8] |= (u64)h[i] << (8 * ((31 - i) % 8));
+        return Fr::from_canonical(c);
+    }
+};
+
+// ---------------------------------------------------------------- assembly (gate tables) shared with the tests
+extern "C" {
+struct orc_assembly {
+    uint64_t n;                 // N: domain size (power of two); rows 0..N-2 are gates, row N-1 unused
+    uint64_t num_inputs;        // public inputs = rows 0..num_inputs-1 (input gates, q_a = -1)
+    uint64_t nvars;             // number of variables incl. dummy variable 0 (value 0)
+    const uint32_t* wire_idx;   // [4][N] variable id per (column, row)
+    const uint64_t* var_values; // [nvars][4] canonical LE limbs (may be null for setup-only calls)
+    const uint64_t* selectors;  // [7][N][4] canonical LE: q_a,q_b,q_c,q_d,q_m,q_const,q_dnext
+};
+}
+
+static const u64 NON_RES[4] = {1, 5, 7, 10};  // k_i (vk.bin bytes 752-847; template.sol:845-853)
+
+static std::vector<Fr> load_frs(const uint64_t* src, size_t n, int threads) {
+    std::vector<Fr> v(n);
+    parallel_chunks(n, threads, [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) v[i] = Fr::from_canonical(src + 4 * i); });
+    return v;
+}
+
+// sigma_i values on H
+static void build_sigma(const orc_assembly& as, const std::vector<Fr>& omega_pows, std::vector<Fr> sigma[4]) {
+    size_t N = as.n;
+    Fr k[4];
+    for (int c = 0; c < 4; ++c) k[c] = Fr::from_u64(NON_RES[c]);
+    for (int c = 0; c < 4; ++c) {
+        sigma[c].resize(N);
+        for (size_t r = 0; r < N; ++r) sigma[c][r] = k[c] * omega_pows[r];
+    }
+    const uint64_t NONE = ~uint64_t(0);
+    std::vector<uint64_t> first(as.nvars, NONE), prev(as.nvars, NONE);
+    for (size_t r = 0; r < N; ++r)
+        for (int c = 0; c < 4; ++c) {
+            uint32_t var = as.wire_idx[(size_t)c * N + r];
+            if (var == 0) continue;
+            uint64_t pos = (uint64_t)c * N + r;
+            if (prev[var] != NONE) sigma[prev[var] / N][prev[var] % N] = k[c] * omega_pows[r];
+            else first[var] = pos;
+            prev[var] = pos;
+        }
+    for (size_t var = 1; var < as.nvars; ++var)
+        if (prev[var] != NONE) {
+            uint64_t f = first[var];
+            sigma[prev[var] / N][prev[var] % N] = k[f / N] * omega_pows[f % N];
+        }
+}
+
+static std::vector<Fr> powers(const Fr& g, size_t n) {
+    std::vector<Fr> p(n);
+    Fr x = Fr::one();
+    for (size_t i = 0; i < n; ++i) { p[i] = x; x *= g; }
+    return p;
+}
+
+static Fr eval_poly(const std::vector<Fr>& p, const Fr& x, int threads) {
+    std::vector<Fr> partial(threads < 1 ? 1 : threads, Fr::zero());
+    parallel_chunks(p.size(), threads, [&](size_t b, size_t e, int tid) {
+        Fr acc = Fr::zero();
+        for (size_t i = e; i-- > b;) acc = acc * x + p[i];
+        partial[tid] = acc * x.pow_u64(b);
+    });
+    Fr s = Fr::zero();
+    for (auto& v : partial) s += v;
+    return s;
+}
+
+// (p(X) - p(z)) / (X - z) by synthetic division (p(z) is discarded: remainder)
+static std::vector<Fr> divide_by_linear(const std::vector<Fr>& p, const Fr& z) {
+    size_t n = p.size();
+    std::vector<Fr> q(n, Fr::zero());
+    Fr carry = Fr::zero();
+    for (size_t i = n; i-- > 1;) {
+        carry = p[i] + carry * z;
+        q[i - 1] = carry;
+    }
+    return q;
+}
+
+// LDE of a coefficient vector (len N) onto the coset 7*H_{4N}, natural order
+static std::vector<Fr> lde4(const std::vector<Fr>& coeffs, int threads) {
+    std::vector<Fr> v(coeffs.size() * 4, Fr::zero());
+    std::copy(coeffs.begin(), coeffs.end(), v.begin());
+    coset_fft(v, threads);
+    return v;
+}
+
+struct SetupPolys {
+    std::vector<Fr> sel[7];    // monomial form
+    std::vector<Fr> sigma[4];  // monomial form
+    std::vector<Fr> sigma_vals[4];
+};
+static void make_setup(const orc_assembly& as, SetupPolys& sp, int threads) {
+    size_t N = as.n;
+    int log_n = log2_floor(N);
+    std::vector<Fr> om = powers(omega_for(log_n), N);
+    for (int s = 0; s < 7; ++s) {
+        sp.sel[s] = load_frs(as.selectors + (size_t)s * N * 4, N, threads);
+        ifft(sp.sel[s], threads);
+    }
+    build_sigma(as, om, sp.sigma_vals);
+    for (int c = 0; c < 4; ++c) { sp.sigma[c] = sp.sigma_vals[c]; ifft(sp.sigma[c], threads); }
+}
+
+extern "C" {
+
+void orc_init() { init_fields(); }
+
+// raw Montgomery constants, for checking against SURVEY App. C
+void orc_constants(uint64_t* out /* [2][3][4] : (R, R2, {INV,0,0,0}) for Fr then Fq */) {
+    init_fields();
+    memcpy(out, Params<FrTag>::R, 32); memcpy(out + 4, Params<FrTag>::R2, 32);
+    out[8] = Params<FrTag>::INV; out[9] = out[10] = out[11] = 0;
+    memcpy(out + 12, Params<FqTag>::R, 32); memcpy(out + 16, Params<FqTag>::R2, 32);
+    out[20] = Params<FqTag>::INV; out[21] = out[22] = out[23] = 0;
+}
+void orc_omega(int log_n, uint64_t out[4]) { init_fields(); omega_for(log_n).to_canonical(out); }
+
+void orc_keccak256(const uint8_t* in, uint64_t len, uint8_t out[32]) { keccak256(in, len, out); }
+
+// Fr helpers on canonical LE limbs (used by tests for cross-checks)
+void orc_fr_mul(const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n) {
+    init_fields();
+    for (uint64_t i = 0; i < n; ++i) (Fr::from_canonical(a + 4 * i) * Fr::from_canonical(b + 4 * i)).to_canonical(out + 4 * i);
+}
+void orc_fq_mul(const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n) {
+    init_fields();
+    for (uint64_t i = 0; i < n; ++i) (Fq::from_canonical(a + 4 * i) * Fq::from_canonical(b + 4 * i)).to_canonical(out + 4 * i);
+}
+void orc_fr_inv(const uint64_t* a, uint64_t* out, uint64_t n) {
+    init_fields();
+    for (uint64_t i = 0; i < n; ++i) Fr::from_canonical(a + 4 * i).inverse().to_canonical(out + 4 * i);
+}
+
+// (i)NTT over Fr, natural order in and out, canonical LE limbs.  coset != 0: coset_fft / icoset_fft with g = 7.
+void orc_ntt(uint64_t* data, int log_n, int inverse, int coset, int threads) {
+    init_fields();
+    size_t n = size_t(1) << log_n;
+    std::vector<Fr> a = load_frs(data, n, threads);
+    if (!inverse) { if (coset) coset_fft(a, threads); else fft(a, threads); }
+    else { if (coset) icoset_fft(a, threads); else ifft(a, threads); }
+    for (size_t i = 0; i < n; ++i) a[i].to_canonical(data + 4 * i);
+}
+// O(n^2) DFT, independent of the radix-2 code (small n only)
+void orc_naive_dft(const uint64_t* in, uint64_t* out, int log_n) {
+    init_fields();
+    size_t n = size_t(1) << log_n;
+    std::vector<Fr> a = load_frs(in, n, 1);
+    Fr w = omega_for(log_n);
+    for (size_t k = 0; k < n; ++k) {
+        Fr wk = w.pow_u64(k), x = Fr::one(), s = Fr::zero();
+        for (size_t j = 0; j < n; ++j) { s += a[j] * x; x *= wk; }
+        s.to_canonical(out + 4 * k);
+    }
+}
+// LDE x4 onto the coset 7*H_4N (natural order)
+void orc_lde4(const uint64_t* coeffs, int log_n, uint64_t* out, int threads) {
+    init_fields();
+    size_t n = size_t(1) << log_n;
+    std::vector<Fr> a = load_frs(coeffs, n, threads);
+    std::vector<Fr> v = lde4(a, threads);
+    for (size_t i = 0; i < 4 * n; ++i) v[i].to_canonical(out + 4 * i);
+}
+
+static std::vector<G1Affine> load_points(const uint64_t* xy, size_t n, int threads) {
+    std::vector<G1Affine> p(n);
+    parallel_chunks(n, threads, [&](size_t b, size_t e, int) {
+        for (size_t i = b; i < e; ++i) {
+            const uint64_t* s = xy + 8 * i;
+            bool inf = true;
+            for (int k = 0; k < 8; ++k) if (s[k]) inf = false;
+            if (inf) p[i] = G1Affine::infinity();
+            else { p[i].x = Fq::from_canonical(s); p[i].y = Fq::from_canonical(s + 4); p[i].inf = false; }
+        }
+    });
+    return p;
+}
+static void store_point(const G1Affine& a, uint64_t* out) {
+    if (a.inf) { memset(out, 0, 64); return; }
+    a.x.to_canonical(out); a.y.to_canonical(out + 4);
+}
+
+// MSM: scalars canonical LE [n][4]; bases affine canonical LE [n][8] ((0,0) = infinity); out [8] ((0,0) = infinity)
+void orc_msm(const uint64_t* scalars, const uint64_t* bases, uint64_t n, uint64_t* out, int threads) {
+    init_fields();
+    std::vector<G1Affine> b = load_points(bases, n, threads);
+    G1 r = dense_multiexp(b.data(), (const Repr*)scalars, n, threads);
+    store_point(r.to_affine(), out);
+}
+// naive sum of double-and-add products (independent check path; small n)
+void orc_msm_naive(const uint64_t* scalars, const uint64_t* bases, uint64_t n, uint64_t* out) {
+    init_fields();
+    std::vector<G1Affine> b = load_points(bases, n, 1);
+    G1 acc = G1::infinity();
+    for (uint64_t i = 0; i < n; ++i) acc = acc.add(G1::from_affine(b[i]).mul(scalars + 4 * i));
+    store_point(acc.to_affine(), out);
+}
+int orc_on_curve(const uint64_t* xy, uint64_t n) {
+    init_fields();
+    std::vector<G1Affine> b = load_points(xy, n, 1);
+    for (auto& p : b) if (!p.on_curve()) return 0;
+    return 1;
+}
+// out = k * P for canonical k
+void orc_g1_mul(const uint64_t* xy, const uint64_t* k, uint64_t* out) {
+    init_fields();
+    std::vector<G1Affine> b = load_points(xy, 1, 1);
+    store_point(G1::from_affine(b[0]).mul(k).to_affine(), out);
+}
+void orc_g1_add(const uint64_t* p, const uint64_t* q, uint64_t* out) {
+    init_fields();
+    std::vector<G1Affine> a = load_points(p, 1, 1), b = load_points(q, 1, 1);
+    store_point(G1::from_affine(a[0]).add(G1::from_affine(b[0])).to_affine(), out);
+}
+
+// Crs::crs_42 (src/plonk.rs:41,47): [tau^i] G, i < n, tau = 42 unless overridden
+void orc_srs_gen(uint64_t n, uint64_t tau, uint64_t* out, int threads) {
+    init_fields();
+    Fr t = Fr::from_u64(tau);
+    G1 g = G1::from_affine(G1Affine::generator());
+    std::vector<G1> pts(n);
+    parallel_chunks(n, threads, [&](size_t b, size_t e, int) {
+        u64 c[4];
+        t.pow_u64(b).to_canonical(c);
+        G1 p = g.mul(c);
+        u64 tc[4] = {tau, 0, 0, 0};
+        for (size_t i = b; i < e; ++i) { pts[i] = p; p = p.mul(tc); }
+    });
+    // batch normalisation
+    std::vector<Fq> z(n);
+    for (size_t i = 0; i < n; ++i) z[i] = pts[i].Z;
+    batch_inverse(z.data(), n);
+    parallel_chunks(n, threads, [&](size_t b, size_t e, int) {
+        for (size_t i = b; i < e; ++i) {
+            Fq zi2 = z[i].sqr();
+            G1Affine a; a.x = pts[i].X * zi2; a.y = pts[i].Y * zi2 * z[i]; a.inf = pts[i].is_inf();
+            store_point(a, out + 8 * i);
+        }
+    });
+}
+
+// Crs::from_powers (src/plonk.rs:179-185): EC inverse FFT of the first n monomial bases -> L_i(tau) G.
+// Radix-2 over Jacobian points; natural order in/out.
+void orc_ec_intt(const uint64_t* bases, int log_n, uint64_t* out, int threads) {
+    init_fields();
+    size_t n = size_t(1) << log_n;
+    std::vector<G1Affine> in = load_points(bases, n, threads);
+    std::vector<G1> a(n);
+    for (size_t i = 0; i < n; ++i) a[i] = G1::from_affine(in[i]);
+    for (size_t k = 0; k < n; ++k) { size_t rk = bitrev32((uint32_t)k, log_n); if (k < rk) std::swap(a[k], a[rk]); }
+    Fr omega_inv = omega_for(log_n).inverse();
+    size_t m = 1;
+    for (int s = 0; s < log_n; ++s) {
+        Fr w_m = omega_inv.pow_u64(n / (2 * m));
+        std::vector<Fr> w = powers(w_m, m);
+        std::vector<Repr> wc(m);
+        for (size_t j = 0; j < m; ++j) w[j].to_canonical(wc[j].v);
+        size_t groups = n / (2 * m);
+        parallel_chunks(groups, threads, [&](size_t gb, size_t ge, int) {
+            for (size_t g = gb; g < ge; ++g) {
+                size_t k = g * 2 * m;
+                for (size_t j = 0; j < m; ++j) {
+                    G1 t = j == 0 ? a[k + j + m] : a[k + j + m].mul(wc[j].v);
+                    G1 u = a[k + j];
+                    a[k + j] = u.add(t);
+                    a[k + j + m] = u.add(t.neg());
+                }
+            }
+        });
+        m *= 2;
+    }
+    u64 ninv[4];
+    Fr::from_u64(n).inverse().to_canonical(ninv);
+    parallel_chunks(n, threads, [&](size_t b, size_t e, int) {
+        for (size_t i = b; i < e; ++i) store_point(a[i].mul(ninv).to_affine(), out + 8 * i);
+    });
+}
+
+// setup polynomials -> 11 commitments (q_a,q_b,q_c,q_d,q_m,q_const,q_dnext, sigma_0..3): make_verification_key
+// (src/plonk.rs:122-124).  out: [11][8] canonical LE affine.  Also (optional) sigma values out [4][N][4].
+void orc_setup_commitments(const orc_assembly* as, const uint64_t* srs, uint64_t* out, uint64_t* sigma_vals_out, int threads) {
+    init_fields();
+    size_t N = as->n;
+    SetupPolys sp;
+    make_setup(*as, sp, threads);
+    std::vector<G1Affine> bases = load_points(srs, N, threads);
+    for (int s = 0; s < 7; ++s) store_point(commit(sp.sel[s], bases.data(), threads), out + 8 * s);
+    for (int c = 0; c < 4; ++c) store_point(commit(sp.sigma[c], bases.data(), threads), out + 8 * (7 + c));
+    if (sigma_vals_out)
+        for (int c = 0; c < 4; ++c)
+            for (size_t i = 0; i < N; ++i) sp.sigma_vals[c][i].to_canonical(sigma_vals_out + ((size_t)c * N + i) * 4);
+}
+
+// The prover (SetupForProver::prove with "keccak", monomial SRS; src/plonk.rs:132-176 -> prove_by_steps [ext]).
+// Writes proof.bin bytes to proof_out (capacity >= 16 + 32*num_inputs + 1096) and returns the
+// length, or a negative error code (-1: gate identity unsatisfied, -2: quotient not a polynomial).
+// challenges_out (optional): beta,gamma,alpha,zeta,v canonical LE [5][4].
+int64_t orc_prove(const orc_assembly* as, const uint64_t* srs, uint8_t* proof_out, uint64_t* challenges_out, int threads) {
+    init_fields();
+    const size_t N = as->n;
+    const int log_n = log2_floor(N);
+    const size_t NI = as->num_inputs;
+    const Fr omega = omega_for(log_n);
+    std::vector<Fr> om = powers(omega, N);
+    std::vector<G1Affine> bases = load_points(srs, N, threads);
+
+    // ---- setup polynomials (reference: prepare_setup_for_prover, src/plonk.rs:97-119; recomputed here per call)
+    SetupPolys sp;
+    make_setup(*as, sp, threads);
+
+    // ---- witness -> wire values
+    std::vector<Fr> vars = load_frs(as->var_values, as->nvars, threads);
+    std::vector<Fr> wv[4];
+    for (int c = 0; c < 4; ++c) {
+        wv[c].resize(N);
+        for (size_t r = 0; r < N; ++r) wv[c][r] = vars[as->wire_idx[(size_t)c * N + r]];
+    }
+    std::vector<Fr> selv[7];
+    for (int s = 0; s < 7; ++s) selv[s] = load_frs(as->selectors + (size_t)s * N * 4, N, threads);
+    std::vector<Fr> pi_vals(N, Fr::zero());
+    for (size_t i = 0; i < NI; ++i) pi_vals[i] = wv[0][i];
+    // is_satisfied_using_one_shot_check (src/plonk.rs:137)
+    for (size_t r = 0; r + 1 < N; ++r) {
+        Fr g = selv[0][r] * wv[0][r] + selv[1][r] * wv[1][r] + selv[2][r] * wv[2][r] + selv[3][r] * wv[3][r] +
+               selv[4][r] * wv[0][r] * wv[1][r] + selv[5][r] + selv[6][r] * wv[3][r + 1] + pi_vals[r];
+        if (!g.is_zero()) return -1;
+    }
+
+    Transcript tr;
+    for (size_t i = 0; i < NI; ++i) tr.update_fr(pi_vals[i]);
+
+    // ---- round 1: wire commitments
+    std::vector<Fr> w[4];
+    G1Affine Cw[4];
+    for (int c = 0; c < 4; ++c) {
+        w[c] = wv[c];
+        ifft(w[c], threads);
+        Cw[c] = commit(w[c], bases.data(), threads);
+        tr.update_g1(Cw[c]);
+    }
+    Fr beta = tr.challenge(), gamma = tr.challenge();
+
+    // ---- round 2: grand product
+    Fr kk[4];
+    for (int c = 0; c < 4; ++c) kk[c] = Fr::from_u64(NON_RES[c]);
+    std::vector<Fr> num(N), den(N);
+    parallel_chunks(N, threads, [&](size_t b, size_t e, int) {
+        for (size_t j = b; j < e; ++j) {
+            Fr nn = Fr::one(), dd = Fr::one();
+            for (int c = 0; c < 4; ++c) {
+                nn *= wv[c][j] + beta * kk[c] * om[j] + gamma;
+                dd *= wv[c][j] + beta * sp.sigma_vals[c][j] + gamma;
+            }
+            num[j] = nn; den[j] = dd;
+        }
+    });
+    batch_inverse(den.data(), N);
+    std::vector<Fr> zv(N);
+    zv[0] = Fr::one();
+    for (size_t j = 0; j + 1 < N; ++j) zv[j + 1] = zv[j] * num[j] * den[j];
+    std::vector<Fr> zp = zv;
+    ifft(zp, threads);
+    G1Affine Cz = commit(zp, bases.data(), threads);
+    tr.update_g1(Cz);
+    Fr alpha = tr.challenge();
+
+    // ---- round 3: quotient on the coset 7*H_4N
+    const size_t M = 4 * N;
+    std::vector<Fr> lw[4], lsel[7], lsig[4];
+    for (int c = 0; c < 4; ++c) lw[c] = lde4(w[c], threads);
+    for (int s = 0; s < 7; ++s) lsel[s] = lde4(sp.sel[s], threads);
+    for (int c = 0; c < 4; ++c) lsig[c] = lde4(sp.sigma[c], threads);
+    std::vector<Fr> lz = lde4(zp, threads);
+    std::vector<Fr> pi_poly = pi_vals;
+    ifft(pi_poly, threads);
+    std::vector<Fr> lpi = lde4(pi_poly, threads);
+    std::vector<Fr> l0c(N, Fr::from_u64(N).inverse());  // L_0(X) = (1/N) sum X^j
+    std::vector<Fr> ll0 = lde4(l0c, threads);
+    Fr omega4 = omega_for(log_n + 2);
+    Fr g7 = Fr::from_u64(COSET_GEN);
+    // 1/Z_H on the coset takes 4 values: x^N = 7^N * omega4^(J*N) = 7^N * i^(J mod 4)
+    Fr zh_inv[4];
+    {
+        Fr g7n = g7.pow_u64(N), w4n = omega4.pow_u64(N);
+        Fr x = g7n;
+        for (int i = 0; i < 4; ++i) { zh_inv[i] = (x - Fr::one()).inverse(); x *= w4n; }
+    }
+    std::vector<Fr> tq(M);
+    Fr alpha2 = alpha.sqr();
+    parallel_chunks(M, threads, [&](size_t b, size_t e, int) {
+        Fr x = g7 * omega4.pow_u64(b);
+        for (size_t J = b; J < e; ++J) {
+            size_t Jn = (J + 4) % M;  // X -> omega X on the 4N domain
+            const Fr &a = lw[0][J], &bb = lw[1][J], &c = lw[2][J], &d = lw[3][J];
+            Fr gate = lsel[0][J] * a + lsel[1][J] * bb + lsel[2][J] * c + lsel[3][J] * d + lsel[4][J] * a * bb + lsel[5][J] +
+                      lsel[6][J] * lw[3][Jn] + lpi[J];
+            Fr nn = lz[J], dd = lz[Jn];
+            for (int i = 0; i < 4; ++i) {
+                nn *= lw[i][J] + beta * kk[i] * x + gamma;
+                dd *= lw[i][J] + beta * lsig[i][J] + gamma;
+            }
+            Fr tot = gate + alpha * (nn - dd) + alpha2 * ll0[J] * (lz[J] - Fr::one());
+            tq[J] = tot * zh_inv[J % 4];
+            x *= omega4;
+        }
+    });
+    icoset_fft(tq, threads);
+    // deg t <= 4N - 5 ... top coefficients must vanish
+    for (size_t i = M - 3; i < M; ++i) if (!tq[i].is_zero()) return -2;
+    std::vector<Fr> tchunk[4];
+    G1Affine Ct[4];
+    for (int i = 0; i < 4; ++i) {
+        tchunk[i].assign(tq.begin() + i * N, tq.begin() + (i + 1) * N);
+        Ct[i] = commit(tchunk[i], bases.data(), threads);
+        tr.update_g1(Ct[i]);
+    }
+    Fr zeta = tr.challenge();
+
+    // ---- round 4: evaluations + linearisation
+    Fr zeta_omega = zeta * omega;
+    Fr wz[4], sz[3];
+    for (int c = 0; c < 4; ++c) wz[c] = eval_poly(w[c], zeta, threads);
+    Fr dzw = eval_poly(w[3], zeta_omega, threads);
+    for (int c = 0; c < 3; ++c) sz[c] = eval_poly(sp.sigma[c], zeta, threads);
+    Fr zzw = eval_poly(zp, zeta_omega, threads);
+    Fr tz = eval_poly(tq, zeta, threads);
+    Fr zeta_n = zeta.pow_u64(N);
+    Fr l0z = (zeta_n - Fr::one()) * (Fr::from_u64(N) * (zeta - Fr::one())).inverse();
+    Fr zfac = alpha2 * l0z, sfac = alpha * beta * zzw;
+    {
+        Fr p = alpha;
+        for (int i = 0; i < 4; ++i) p *= wz[i] + beta * kk[i] * zeta + gamma;
+        zfac += p;
+        for (int i = 0; i < 3; ++i) sfac *= wz[i] + beta * sz[i] + gamma;
+    }
+    std::vector<Fr> rp(N);
+    Fr ab = wz[0] * wz[1];
+    parallel_chunks(N, threads, [&](size_t b, size_t e, int) {
+        for (size_t i = b; i < e; ++i) {
+            rp[i] = sp.sel[5][i] + sp.sel[0][i] * wz[0] + sp.sel[1][i] * wz[1] + sp.sel[2][i] * wz[2] + sp.sel[3][i] * wz[3] +
+                    sp.sel[4][i] * ab + sp.sel[6][i] * dzw + zp[i] * zfac - sp.sigma[3][i] * sfac;
+        }
+    });
+    Fr rz = eval_poly(rp, zeta, threads);
+    for (int c = 0; c < 4; ++c) tr.update_fr(wz[c]);
+    tr.update_fr(dzw);
+    for (int c = 0; c < 3; ++c) tr.update_fr(sz[c]);
+    tr.update_fr(tz);
+    tr.update_fr(rz);
+    tr.update_fr(zzw);
+    Fr v = tr.challenge();
+
+    // ---- round 5: openings
+    std::vector<Fr> agg(N), agg2(N);
+    Fr vp[11];
+    vp[0] = Fr::one();
+    for (int i = 1; i <= 10; ++i) vp[i] = vp[i - 1] * v;
+    Fr zn2 = zeta_n.sqr(), zn3 = zn2 * zeta_n;
+    parallel_chunks(N, threads, [&](size_t b, size_t e, int) {
+        for (size_t i = b; i < e; ++i) {
+            agg[i] = tchunk[0][i] + zeta_n * tchunk[1][i] + zn2 * tchunk[2][i] + zn3 * tchunk[3][i] + vp[1] * rp[i] +
+                     vp[2] * w[0][i] + vp[3] * w[1][i] + vp[4] * w[2][i] + vp[5] * w[3][i] + vp[6] * sp.sigma[0][i] +
+                     vp[7] * sp.sigma[1][i] + vp[8] * sp.sigma[2][i];
+            agg2[i] = vp[9] * zp[i] + vp[10] * w[3][i];
+        }
+    });
+    std::vector<Fr> q1 = divide_by_linear(agg, zeta), q2 = divide_by_linear(agg2, zeta_omega);
+    G1Affine W1 = commit(q1, bases.data(), threads), W2 = commit(q2, bases.data(), threads);
+
+    if (challenges_out) {
+        beta.to_canonical(challenges_out); gamma.to_canonical(challenges_out + 4); alpha.to_canonical(challenges_out + 8);
+        zeta.to_canonical(challenges_out + 12); v.to_canonical(challenges_out + 16);
+    }
+
+    // ---- Proof::write
+    uint8_t* p = proof_out;
+    write_u64_be(N - 1, p); p += 8;
+    write_u64_be(NI, p); p += 8;
+    for (size_t i = 0; i < NI; ++i) { write_fr_be(pi_vals[i], p); p += 32; }
+    write_u64_be(4, p); p += 8;
+    for (int c = 0; c < 4; ++c) { write_g1_be(Cw[c], p); p += 64; }
+    write_g1_be(Cz, p); p += 64;
+    write_u64_be(4, p); p += 8;
+    for (int c = 0; c < 4; ++c) { write_g1_be(Ct[c], p); p += 64; }
+    write_u64_be(4, p); p += 8;
+    for (int c = 0; c < 4; ++c) { write_fr_be(wz[c], p); p += 32; }
+    write_u64_be(1, p); p += 8;
+    write_fr_be(dzw, p); p += 32;
+    write_fr_be(zzw, p); p += 32;
+    write_fr_be(tz, p); p += 32;
+    write_fr_be(rz, p); p += 32;
+    write_u64_be(3, p); p += 8;
+    for (int c = 0; c < 3; ++c) { write_fr_be(sz[c], p); p += 32; }
+    write_g1_be(W1, p); p += 64;
+    write_g1_be(W2, p); p += 64;
+    return (int64_t)(p - proof_out);
+}
+
+}  // extern "C"

@@ -1,0 +1,224 @@
+"""Host-side circuit model: R1CS / CircomCircuit and their synthesis into width-4 PLONK gate tables.
+
+Mirrors (names, argument meaning) the reference's host code for the step in front of the prove path:
+  * `R1CS`, `CircomCircuit`, `get_public_inputs`      — src/circom_circuit.rs:32-72
+  * variable allocation, aux_offset, skipped `0*LC=0` — src/circom_circuit.rs:75-133
+  * `transpile_with_gates_count`, `ConstraintStat`    — src/transpile.rs:18-21,92-107,127-139
+  * `analyse` / `AnalyseResult`                       — src/plonk.rs:57-95
+
+The R1CS -> width-4 transpilation itself lives in bellman_ce's adaptor (not in the reference tree).  Only the
+shapes pinned by the reference's golden vectors (src/tests.rs:14, test/circuits/simple/*) are accepted in
+strict mode; see SURVEY.md App. A.2.  Everything here is serial host bookkeeping (as in the reference); the
+resulting `Assembly` (gate tables) is what the CUDA prover consumes.
+"""
+import json
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from .bn254 import R_MOD, ints_to_limbs
+
+AUX_OFFSET = 1  # src/plonk.rs:24
+SELECTOR_NAMES = ("q_a", "q_b", "q_c", "q_d", "q_m", "q_const", "q_dnext")
+
+LC = List[Tuple[int, int]]  # [(wire index, coefficient)]
+
+
+@dataclass
+class R1CS:  # src/circom_circuit.rs:32-38
+    num_inputs: int
+    num_aux: int
+    num_variables: int
+    constraints: List[Tuple[LC, LC, LC]]
+
+
+@dataclass
+class CircomCircuit:  # src/circom_circuit.rs:40-47
+    r1cs: R1CS
+    witness: Optional[List[int]] = None
+    wire_mapping: Optional[List[int]] = None
+    aux_offset: int = AUX_OFFSET
+
+    def _w(self, i):
+        if self.wire_mapping is None:
+            return self.witness[i]
+        return self.witness[self.wire_mapping[i]]
+
+    def get_public_inputs(self):  # src/circom_circuit.rs:50-59
+        if self.witness is None:
+            return None
+        return [self._w(i) for i in range(1, self.r1cs.num_inputs)]
+
+    def get_public_inputs_json(self) -> str:  # src/circom_circuit.rs:61-68
+        inputs = self.get_public_inputs()
+        if inputs is None:
+            return "[]"
+        return json.dumps([str(x) for x in inputs], indent=2)
+
+
+@dataclass
+class ConstraintStat:  # src/transpile.rs:11-16
+    name: str
+    num_gates: int
+
+
+@dataclass
+class Assembly:
+    """Width-4 gate tables over the domain of size n (a power of two).
+
+    Rows 0..num_inputs-1 are the public-input gates (a = input variable, q_a = -1), then the circuit's gates,
+    then dummy padding; row n-1 is never a gate (bellman pads to n-1 gates).  Variable 0 is bellman's dummy
+    variable (value 0).  SURVEY.md App. A.2.
+    """
+    n: int
+    num_inputs: int
+    wire_idx: np.ndarray                 # (4, n) uint32 variable ids
+    selectors: np.ndarray                # (7, n, 4) uint64 canonical LE limbs, order SELECTOR_NAMES
+    var_values: Optional[np.ndarray]     # (nvars, 4) uint64 canonical LE limbs, or None (setup only)
+    nvars: int
+    num_gates: int = 0                   # gates before padding (incl. input gates)
+
+    def public_inputs(self):
+        from .bn254 import limbs_to_ints
+        if self.var_values is None:
+            return None
+        return limbs_to_ints(self.var_values[self.wire_idx[0, :self.num_inputs]])
+
+
+class UnpinnedTranspilation(NotImplementedError):
+    """Raised for R1CS constraint shapes whose width-4 layout no reference fixture pins."""
+
+
+def _norm_lc(lc: LC):
+    """-> (sorted [(var, coeff)], constant); wire 0 is the constant ONE (src/circom_circuit.rs:107-113)"""
+    acc = {}
+    const = 0
+    for idx, coeff in lc:
+        coeff %= R_MOD
+        if idx == 0:
+            const = (const + coeff) % R_MOD
+        else:
+            acc[idx] = (acc.get(idx, 0) + coeff) % R_MOD
+    terms = sorted((i, c) for i, c in acc.items() if c != 0)
+    return terms, const
+
+
+@dataclass
+class _Gates:
+    rows: list = field(default_factory=list)   # (a, b, c, d, [7 selector ints])
+    values: list = field(default_factory=list)  # variable values (None when no witness)
+    hints: int = 0
+    stats: list = field(default_factory=list)
+
+
+def _transpile(circuit: CircomCircuit, strict: bool = True) -> _Gates:
+    r = circuit.r1cs
+    have_w = circuit.witness is not None
+    g = _Gates()
+    # variable id == witness index: Input(i) -> i ; Aux(j + aux_offset) -> num_inputs + j  (circom_circuit.rs:75-105)
+    if have_w:
+        g.values = [0] + [circuit._w(i) % R_MOD for i in range(1, r.num_variables)]
+    else:
+        g.values = [None] * r.num_variables
+    # public-input gates first
+    for i in range(1, r.num_inputs):
+        g.rows.append((i, 0, 0, 0, [R_MOD - 1, 0, 0, 0, 0, 0, 0]))
+
+    def new_var(val):
+        g.values.append(val)
+        return len(g.values) - 1
+
+    for ci, (A, B, C) in enumerate(r.constraints):
+        if (len(A) == 0 or len(B) == 0) and len(C) == 0:  # 0 * LC = 0 is ignored (circom_circuit.rs:122-123)
+            continue
+        before = len(g.rows)
+        (ta, ka), (tb, kb), (tc, kc) = _norm_lc(A), _norm_lc(B), _norm_lc(C)
+        if not (len(ta) == 1 and ka == 0 and len(tb) == 1 and kb == 0):
+            raise UnpinnedTranspilation("constraint %d: A and B must be single-variable terms" % ci)
+        (x, alpha), (y, beta) = ta[0], tb[0]
+        qm = alpha * beta % R_MOD
+        if len(tc) == 1 and kc == 0:
+            z, gamma = tc[0]
+            g.rows.append((x, y, z, 0, [0, 0, (R_MOD - gamma) % R_MOD, 0, qm, 0, 0]))
+        elif len(tc) == 2:
+            (v1, c1), (v2, c2) = tc
+            tval = None
+            if have_w:
+                tval = (c1 * g.values[v1] + c2 * g.values[v2] + kc) % R_MOD
+            t = new_var(tval)
+            g.rows.append((v1, v2, t, 0, [c1, c2, R_MOD - 1, 0, 0, kc, 0]))
+            g.rows.append((x, y, t, 0, [0, 0, R_MOD - 1, 0, qm, 0, 0]))
+        else:
+            if strict:
+                raise UnpinnedTranspilation("constraint %d: C side with %d variables is not pinned by any fixture" % (ci, len(tc)))
+            raise UnpinnedTranspilation("constraint %d" % ci)
+        g.hints += 1
+        g.stats.append(ConstraintStat(str(ci), len(g.rows) - before))
+    return g
+
+
+def transpile_with_gates_count(circuit: CircomCircuit):
+    """src/transpile.rs:127-139 -> (gates_count, hints_count).  Counts exclude the public-input gates."""
+    g = _transpile(circuit)
+    n_in = circuit.r1cs.num_inputs - 1
+    return len(g.rows) - n_in, g.hints
+
+
+def synthesize(circuit: CircomCircuit, strict: bool = True) -> Assembly:
+    g = _transpile(circuit, strict)
+    return assembly_from_rows(g.rows, g.values, circuit.r1cs.num_inputs - 1)
+
+
+def assembly_from_rows(rows, values, num_inputs) -> Assembly:
+    n_gates = len(rows)
+    n = 1
+    while n < n_gates + 1:
+        n *= 2
+    wire_idx = np.zeros((4, n), dtype=np.uint32)
+    sel = [[0] * n for _ in range(7)]
+    for r, (a, b, c, d, q) in enumerate(rows):
+        wire_idx[0, r], wire_idx[1, r], wire_idx[2, r], wire_idx[3, r] = a, b, c, d
+        for s in range(7):
+            sel[s][r] = q[s]
+    selectors = np.stack([ints_to_limbs(s) for s in sel])
+    var_values = None
+    if values and values[-1] is not None and all(v is not None for v in values):
+        var_values = ints_to_limbs(values)
+    return Assembly(n=n, num_inputs=num_inputs, wire_idx=wire_idx, selectors=selectors, var_values=var_values,
+                    nvars=len(values), num_gates=n_gates)
+
+
+def analyse(circuit: CircomCircuit) -> dict:
+    """src/plonk.rs:72-95 (field order as serialised by the reference; src/tests.rs:14)"""
+    g = _transpile(circuit)
+    r = circuit.r1cs
+    res = {
+        "num_inputs": r.num_inputs,
+        "num_aux": r.num_aux,
+        "num_variables": r.num_variables,
+        "num_constraints": len(r.constraints),
+        "num_nontrivial_constraints": len(g.stats),
+        "num_gates": len(g.rows) - (r.num_inputs - 1),
+        "num_hints": g.hints,
+    }
+    if g.stats:
+        res["constraint_stats"] = [{"name": s.name, "num_gates": s.num_gates} for s in g.stats]
+    return res
+
+
+def is_satisfied(asm: Assembly) -> bool:
+    """is_satisfied_using_one_shot_check (src/plonk.rs:137) on the gate tables — host check, small circuits."""
+    from .bn254 import limbs_to_ints
+    if asm.var_values is None:
+        return False
+    vals = limbs_to_ints(asm.var_values)
+    sel = [limbs_to_ints(asm.selectors[s]) for s in range(7)]
+    w = [[vals[i] for i in asm.wire_idx[c]] for c in range(4)]
+    for r in range(asm.n - 1):
+        pi = w[0][r] if r < asm.num_inputs else 0
+        acc = (sel[0][r] * w[0][r] + sel[1][r] * w[1][r] + sel[2][r] * w[2][r] + sel[3][r] * w[3][r]
+               + sel[4][r] * w[0][r] * w[1][r] + sel[5][r] + sel[6][r] * w[3][r + 1] + pi)
+        if acc % R_MOD:
+            return False
+    return True

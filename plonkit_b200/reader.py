@@ -1,0 +1,321 @@
+"""File formats on either side of the prove path (wire contract of the reference).
+
+Mirrors src/reader.rs (loaders) and the bellman `Crs::{read,write}`, `Proof::{read,write}`,
+`VerificationKey::{read,write}` encodings those loaders call: big-endian, canonical field elements,
+G1 uncompressed = x || y with infinity = 0x40 followed by 63 zero bytes.  In memory everything is
+little-endian u64 limbs (see bn254.py).
+"""
+import json
+import struct
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from .bn254 import R_MOD, be_bytes_to_limbs, ints_to_limbs, limbs_to_be_bytes, limbs_to_ints
+from .circuit import R1CS
+
+_PRIME_LE = bytes.fromhex("010000f093f5e1439170b97948e833285d588181b64550b829a031e1724e6430")  # reader.rs:155
+
+
+# ---------------------------------------------------------------- G1 encodings
+def g1_from_bytes(buf: bytes, n: int) -> np.ndarray:
+    """n uncompressed points (64 B each) -> (n, 8) uint64 canonical LE, infinity -> (0, 0)"""
+    raw = np.frombuffer(buf, dtype=np.uint8, count=64 * n).reshape(n, 64)
+    flags = raw[:, 0] & 0xC0
+    pts = be_bytes_to_limbs(raw.tobytes(), 2 * n).reshape(n, 8)
+    inf = flags != 0
+    if inf.any():
+        if (flags[inf] != 0x40).any():
+            raise ValueError("compressed G1 encodings are not expected in .key/.bin files")
+        pts[inf] = 0
+    return pts
+
+
+def g1_to_bytes(pts) -> bytes:
+    pts = np.ascontiguousarray(pts, dtype=np.uint64).reshape(-1, 8)
+    out = bytearray(limbs_to_be_bytes(pts.reshape(-1, 4)))
+    inf = ~pts.any(axis=1)
+    for i in np.nonzero(inf)[0]:
+        out[64 * i] = 0x40
+    return bytes(out)
+
+
+# ---------------------------------------------------------------- SRS (.key): Crs::read / Crs::write  (App. B.1)
+@dataclass
+class Crs:
+    """bellman `Crs<Bn256, CrsForMonomialForm | CrsForLagrangeForm>`: g1 bases + the two G2 elements (kept raw)."""
+    g1_bases: np.ndarray            # (n, 8) uint64 canonical LE affine
+    g2_raw: bytes = b""             # n_g2 * 128 bytes exactly as in the file (verify-side only)
+    form: str = "monomial"
+
+    @property
+    def size(self):
+        return self.g1_bases.shape[0]
+
+    @staticmethod
+    def read(f) -> "Crs":
+        n = struct.unpack(">Q", f.read(8))[0]
+        g1 = g1_from_bytes(f.read(64 * n), n)
+        n2 = struct.unpack(">Q", f.read(8))[0]
+        g2 = f.read(128 * n2)
+        return Crs(g1, g2)
+
+    def write(self, f):
+        f.write(struct.pack(">Q", self.size))
+        f.write(g1_to_bytes(self.g1_bases))
+        f.write(struct.pack(">Q", len(self.g2_raw) // 128))
+        f.write(self.g2_raw)
+
+
+def load_key_monomial_form(filename: str) -> Crs:  # src/reader.rs:74-77
+    with open(filename, "rb") as f:
+        return Crs.read(f)
+
+
+def maybe_load_key_lagrange_form(option_filename: Optional[str]) -> Optional[Crs]:  # src/reader.rs:80-89
+    if option_filename is None:
+        return None
+    with open(option_filename, "rb") as f:
+        crs = Crs.read(f)
+    crs.form = "lagrange"
+    return crs
+
+
+# ---------------------------------------------------------------- Proof (App. B.2)
+@dataclass
+class Proof:
+    """bellman `Proof<Bn256, PlonkCsWidth4WithNextStepParams>`; field order = contrib/template.sol:330-344."""
+    n: int
+    num_inputs: int
+    input_values: List[int]
+    wire_commitments: np.ndarray               # (4, 8)
+    grand_product_commitment: np.ndarray       # (8,)
+    quotient_poly_commitments: np.ndarray      # (4, 8)
+    wire_values_at_z: List[int]
+    wire_values_at_z_omega: List[int]
+    grand_product_at_z_omega: int
+    quotient_polynomial_at_z: int
+    linearization_polynomial_at_z: int
+    permutation_polynomials_at_z: List[int]
+    opening_at_z_proof: np.ndarray             # (8,)
+    opening_at_z_omega_proof: np.ndarray       # (8,)
+
+    def write(self, f):
+        def frs(vals):
+            return limbs_to_be_bytes(ints_to_limbs(vals))
+        f.write(struct.pack(">QQ", self.n, self.num_inputs))
+        f.write(frs(self.input_values))
+        f.write(struct.pack(">Q", 4) + g1_to_bytes(self.wire_commitments))
+        f.write(g1_to_bytes(self.grand_product_commitment))
+        f.write(struct.pack(">Q", 4) + g1_to_bytes(self.quotient_poly_commitments))
+        f.write(struct.pack(">Q", 4) + frs(self.wire_values_at_z))
+        f.write(struct.pack(">Q", 1) + frs(self.wire_values_at_z_omega))
+        f.write(frs([self.grand_product_at_z_omega, self.quotient_polynomial_at_z, self.linearization_polynomial_at_z]))
+        f.write(struct.pack(">Q", 3) + frs(self.permutation_polynomials_at_z))
+        f.write(g1_to_bytes(self.opening_at_z_proof))
+        f.write(g1_to_bytes(self.opening_at_z_omega_proof))
+
+    def to_bytes(self) -> bytes:
+        import io
+        b = io.BytesIO()
+        self.write(b)
+        return b.getvalue()
+
+    @staticmethod
+    def read(f) -> "Proof":
+        def u64():
+            return struct.unpack(">Q", f.read(8))[0]
+
+        def frs(k):
+            return limbs_to_ints(be_bytes_to_limbs(f.read(32 * k), k))
+
+        def g1s(k):
+            return g1_from_bytes(f.read(64 * k), k)
+        n, ni = u64(), u64()
+        inputs = frs(ni)
+        assert u64() == 4
+        wc = g1s(4)
+        gp = g1s(1)[0]
+        assert u64() == 4
+        qc = g1s(4)
+        assert u64() == 4
+        wz = frs(4)
+        assert u64() == 1
+        wzo = frs(1)
+        gpz, tz, rz = frs(3)
+        assert u64() == 3
+        pz = frs(3)
+        o1, o2 = g1s(1)[0], g1s(1)[0]
+        return Proof(n, ni, inputs, wc, gp, qc, wz, wzo, gpz, tz, rz, pz, o1, o2)
+
+
+def load_proof(filename: str) -> Proof:  # src/reader.rs:23-25
+    with open(filename, "rb") as f:
+        return Proof.read(f)
+
+
+# ---------------------------------------------------------------- VerificationKey (App. B.3)
+@dataclass
+class VerificationKey:
+    n: int
+    num_inputs: int
+    selector_commitments: np.ndarray             # (6, 8): q_a,q_b,q_c,q_d,q_m,q_const
+    next_step_selector_commitments: np.ndarray   # (1, 8): q_dnext
+    permutation_commitments: np.ndarray          # (4, 8)
+    non_residues: List[int] = field(default_factory=lambda: [5, 7, 10])
+    g2_raw: bytes = b""                          # 2 x 128 B (G2 generator, [tau] G2) as in the SRS file
+
+    def write(self, f):
+        f.write(struct.pack(">QQ", self.n, self.num_inputs))
+        f.write(struct.pack(">Q", 6) + g1_to_bytes(self.selector_commitments))
+        f.write(struct.pack(">Q", 1) + g1_to_bytes(self.next_step_selector_commitments))
+        f.write(struct.pack(">Q", 4) + g1_to_bytes(self.permutation_commitments))
+        f.write(struct.pack(">Q", 3) + limbs_to_be_bytes(ints_to_limbs(self.non_residues)))
+        f.write(self.g2_raw)
+
+    def to_bytes(self) -> bytes:
+        import io
+        b = io.BytesIO()
+        self.write(b)
+        return b.getvalue()
+
+    @staticmethod
+    def read(f) -> "VerificationKey":
+        def u64():
+            return struct.unpack(">Q", f.read(8))[0]
+        n, ni = u64(), u64()
+        assert u64() == 6
+        sel = g1_from_bytes(f.read(64 * 6), 6)
+        assert u64() == 1
+        nxt = g1_from_bytes(f.read(64), 1)
+        assert u64() == 4
+        perm = g1_from_bytes(f.read(64 * 4), 4)
+        assert u64() == 3
+        nr = limbs_to_ints(be_bytes_to_limbs(f.read(96), 3))
+        g2 = f.read(256)
+        return VerificationKey(n, ni, sel, nxt, perm, nr, g2)
+
+
+def load_verification_key(filename: str) -> VerificationKey:  # src/reader.rs:56-59
+    with open(filename, "rb") as f:
+        return VerificationKey.read(f)
+
+
+# ---------------------------------------------------------------- witness (App. B.4)
+def load_witness_from_file(filename: str) -> List[int]:  # src/reader.rs:92-98
+    if filename.endswith("json"):
+        with open(filename) as f:
+            return [int(x) % R_MOD for x in json.load(f)]
+    with open(filename, "rb") as f:
+        return load_witness_from_array(f.read())
+
+
+def load_witness_from_array(buffer: bytes) -> List[int]:  # src/reader.rs:119-175
+    if buffer[:4] != b"wtns":
+        raise ValueError("invalid file header")
+    version, num_sections = struct.unpack_from("<II", buffer, 4)
+    if version > 2:
+        raise ValueError("unsupported file version")
+    if num_sections != 2:
+        raise ValueError("invalid num sections")
+    off = 12
+    sec_type, sec_size = struct.unpack_from("<IQ", buffer, off)
+    off += 12
+    if sec_type != 1:
+        raise ValueError("invalid section type")
+    if sec_size != 4 + 32 + 4:
+        raise ValueError("invalid section len")
+    field_size = struct.unpack_from("<I", buffer, off)[0]
+    off += 4
+    if field_size != 32:
+        raise ValueError("invalid field byte size")
+    if buffer[off:off + 32] != _PRIME_LE:
+        raise ValueError("invalid curve prime")
+    off += 32
+    witness_len = struct.unpack_from("<I", buffer, off)[0]
+    off += 4
+    sec_type, sec_size = struct.unpack_from("<IQ", buffer, off)
+    off += 12
+    if sec_type != 2:
+        raise ValueError("invalid section type")
+    if sec_size != witness_len * field_size:
+        raise ValueError("invalid witness section size %d" % sec_size)
+    vals = [int.from_bytes(buffer[off + 32 * i:off + 32 * i + 32], "little") for i in range(witness_len)]
+    if any(v >= R_MOD for v in vals):
+        raise ValueError("witness element is not in the field")
+    return vals
+
+
+# ---------------------------------------------------------------- R1CS (App. B.5 / B.6)
+def load_r1cs(filename: str) -> R1CS:  # src/reader.rs:178-185
+    if filename.endswith("json"):
+        with open(filename) as f:
+            return load_r1cs_from_json(json.load(f))
+    with open(filename, "rb") as f:
+        r1cs, _wire_mapping = load_r1cs_from_bin(f.read())
+    return r1cs
+
+
+def load_r1cs_from_json(cj: dict) -> R1CS:  # src/reader.rs:194-218
+    num_inputs = cj["nPubInputs"] + cj["nOutputs"] + 1
+    num_aux = cj["nVars"] - num_inputs
+
+    def conv(lc):
+        # BTreeMap<String, String>: iteration order = lexicographic order of the index strings
+        return [(int(k), int(v) % R_MOD) for k, v in sorted(lc.items())]
+    constraints = [(conv(c[0]), conv(c[1]), conv(c[2])) for c in cj["constraints"]]
+    return R1CS(num_inputs, num_aux, cj["nVars"], constraints)
+
+
+def load_r1cs_from_bin(buf: bytes):  # src/r1cs_file.rs:100-154 + src/reader.rs:227-241
+    if buf[:4] != b"r1cs":
+        raise ValueError("Invalid magic number")
+    version, num_sections = struct.unpack_from("<II", buf, 4)
+    if version != 1:
+        raise ValueError("Unsupported version")
+    off = 12
+    sections = {}
+    for _ in range(num_sections):
+        st, ss = struct.unpack_from("<IQ", buf, off)
+        off += 12
+        sections[st] = (off, ss)
+        off += ss
+    h_off, h_size = sections[1]
+    field_size = struct.unpack_from("<I", buf, h_off)[0]
+    if h_size != 32 + field_size:
+        raise ValueError("Invalid header section size")
+    if field_size != 32:
+        raise ValueError("This parser only supports 32-byte fields")
+    if buf[h_off + 4:h_off + 36] != _PRIME_LE:
+        raise ValueError("This parser only supports bn256")
+    n_wires, n_pub_out, n_pub_in, n_prv_in, n_labels, n_constraints = struct.unpack_from("<IIIIQI", buf, h_off + 36)
+    c_off, _ = sections[2]
+    constraints = []
+    p = c_off
+
+    def read_vec(p):
+        k = struct.unpack_from("<I", buf, p)[0]
+        p += 4
+        out = []
+        for _ in range(k):
+            w = struct.unpack_from("<I", buf, p)[0]
+            v = int.from_bytes(buf[p + 4:p + 36], "little")
+            if v >= R_MOD:
+                raise ValueError("coefficient is not in the field")
+            out.append((w, v))
+            p += 36
+        return out, p
+    for _ in range(n_constraints):
+        a, p = read_vec(p)
+        b, p = read_vec(p)
+        c, p = read_vec(p)
+        constraints.append((a, b, c))
+    m_off, m_size = sections[3]
+    if m_size != n_wires * 8:
+        raise ValueError("Invalid map section size")
+    wire_mapping = list(struct.unpack_from("<%dQ" % n_wires, buf, m_off))
+    if wire_mapping and wire_mapping[0] != 0:
+        raise ValueError("Wire 0 should always be mapped to 0")
+    num_inputs = 1 + n_pub_in + n_pub_out
+    return R1CS(num_inputs, n_wires - num_inputs, n_wires, constraints), wire_mapping
