@@ -1,0 +1,138 @@
+/* plonkit_b200 — C ABI of the B200-native prove path for fluidex/plonkit.
+ *
+ * The reference has no FFI: it links bellman_ce (Cargo.lock:109-111) statically.  This header is the boundary a
+ * Rust shim would bind (INTEGRATION.md shows the `extern "C"` block); each entry point names the bellman
+ * primitive / plonkit call site it stands in for.  All calls are blocking, return a status code (never throw
+ * or abort across the boundary), take caller-owned host buffers, and keep device memory behind the opaque
+ * context.  One proof at a time per context (like the reference's one Worker per call, src/plonk.rs:41,47,183).
+ *
+ * Data layout across the boundary
+ *   Fr / Fq element : uint64_t[4], little-endian limbs.  `fmt` selects PK_FMT_CANONICAL (what bellman's
+ *                     `PrimeFieldRepr` / file formats hold) or PK_FMT_MONTGOMERY (the in-memory `Fr`, R = 2^256).
+ *   G1 affine point : uint64_t[8] = x || y, canonical limbs; (0, 0) = point at infinity.
+ */
+#ifndef PLONKIT_B200_H
+#define PLONKIT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pk_ctx pk_ctx;
+typedef struct pk_setup pk_setup;
+
+/* status codes; the shim maps them onto bellman's SynthesisError variants */
+enum {
+    PK_OK = 0,
+    PK_ERR_ASSIGNMENT_MISSING = 1,   /* length mismatch / missing witness   (SynthesisError::AssignmentMissing)        */
+    PK_ERR_DEGREE_TOO_LARGE = 2,     /* domain > 2^28 or SRS too small       (SynthesisError::PolynomialDegreeTooLarge) */
+    PK_ERR_DIVISION_BY_ZERO = 3,     /*                                       (SynthesisError::DivisionByZero)           */
+    PK_ERR_UNSATISFIED = 4,          /* gate identity fails on the witness   (SynthesisError::Unsatisfiable)            */
+    PK_ERR_CUDA = 5,                 /* no device / CUDA runtime error — there is no CPU fallback                         */
+    PK_ERR_INVALID = 6               /* bad argument                                                                       */
+};
+
+enum { PK_FMT_CANONICAL = 0, PK_FMT_MONTGOMERY = 1 };
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+/* Creates a context on CUDA device `device`.  Stands in for Worker::new() (src/plonk.rs:41,47,183). */
+int pk_create(int device, pk_ctx** out);
+void pk_destroy(pk_ctx* ctx);
+const char* pk_last_error(const pk_ctx* ctx);
+/* Montgomery constants the device code was generated with: out[0..3]=R mod r, [4..7]=R^2 mod r, [8]=-r^-1 mod 2^32,
+ * [12..15]=R mod q, [16..19]=R^2 mod q, [20]=-q^-1 mod 2^32.  No device needed. */
+void pk_constants(uint64_t out[24]);
+
+/* ---- SRS ----------------------------------------------------------------------------------------------- */
+/* Makes the first n G1 bases of a Crs resident (Crs::read result, src/reader.rs:74-77) and builds the
+ * fixed-base window tables the MSM uses.  window_bits = 0 picks it from n. */
+int pk_srs_load_g1(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits);
+/* Crs::<Bn256, CrsForMonomialForm>::crs_42(n) generalised to any tau (src/plonk.rs:41,47): out[i] = [tau^i] G. */
+int pk_srs_gen(pk_ctx* ctx, uint64_t n, uint64_t tau, uint64_t* out_xy);
+
+/* ---- bellman primitives (a8-a11 of SURVEY.md section 8) ----------------------------------------------- */
+/* Polynomial::{fft, ifft, coset_fft, icoset_fft_for_generator}: radix-2 (i)NTT over Fr on the size-2^log_n
+ * subgroup, natural order in and out, in place.  coset != 0 uses the coset 7*H (bellman's multiplicative generator). */
+int pk_ntt(pk_ctx* ctx, uint64_t* fr, uint32_t log_n, int inverse, int coset, int fmt);
+/* Polynomial::bitreversed_lde_using_bitreversed_ntt(factor = 4, coset_factor = 7): n coefficients -> 4n evaluations
+ * on 7*H_4n.  bitreversed = 0: natural order; 1: the 4n-point bit-reversed order bellman's LDE returns. */
+int pk_lde4(pk_ctx* ctx, const uint64_t* coeffs, uint32_t log_n, uint64_t* out_4n, int bitreversed, int fmt);
+/* multiexp::dense_multiexp / commit_using_monomials: sum_i scalars[i] * SRS[base_offset + i], normalised to affine. */
+int pk_msm_g1(pk_ctx* ctx, const uint64_t* scalars, uint64_t n, uint64_t base_offset, uint64_t out_xy[8], int* is_infinity,
+              int fmt);
+/* Crs::<_, CrsForLagrangeForm>::from_powers (src/plonk.rs:179-185): EC inverse FFT of the first 2^log_n resident
+ * monomial bases: out[i] = [L_i(tau)] G, natural order. */
+int pk_ec_intt_g1(pk_ctx* ctx, uint32_t log_n, uint64_t* out_xy);
+
+/* ---- prover -------------------------------------------------------------------------------------------- */
+/* Gate tables of a width-4 circuit with d_next (PlonkCsWidth4WithNextStepParams).  n is the domain size (power of
+ * two); rows 0..num_inputs-1 are the public-input gates; row n-1 is never a gate.  Variable 0 is the dummy
+ * variable (value 0).  SURVEY.md App. A.2. */
+typedef struct pk_assembly {
+    uint64_t n;
+    uint64_t num_inputs;
+    uint64_t nvars;
+    const uint32_t* wire_idx;   /* [4][n] variable id per (column a..d, row) */
+    const uint64_t* selectors;  /* [7][n][4] canonical: q_a, q_b, q_c, q_d, q_m, q_const, q_dnext */
+} pk_assembly;
+
+/* Proof<Bn256, PlonkCsWidth4WithNextStepParams>, field order of contrib/template.sol:330-344; canonical limbs. */
+typedef struct pk_proof {
+    uint64_t n;          /* number of gates = domain size - 1 */
+    uint64_t num_inputs;
+    uint64_t wire_commitments[4][8];
+    uint64_t grand_product_commitment[8];
+    uint64_t quotient_poly_commitments[4][8];
+    uint64_t wire_values_at_z[4][4];
+    uint64_t wire_values_at_z_omega[1][4];
+    uint64_t grand_product_at_z_omega[4];
+    uint64_t quotient_polynomial_at_z[4];
+    uint64_t linearization_polynomial_at_z[4];
+    uint64_t permutation_polynomials_at_z[3][4];
+    uint64_t opening_at_z_proof[8];
+    uint64_t opening_at_z_omega_proof[8];
+    uint64_t challenges[5][4]; /* beta, gamma, alpha, z, v — not part of proof.bin; exposed for known-answer tests */
+} pk_proof;
+
+/* SetupForProver::prepare_setup_for_prover (src/plonk.rs:97-119) after synthesis: uploads the gate tables, builds the
+ * copy permutation, the 11 setup polynomials (iNTT) and — unlike the reference, which recomputes them in every
+ * prove call (precomputations = None, src/plonk.rs:156) — keeps their 4n coset evaluations resident.
+ * Requires pk_srs_load_g1 with at least n bases. */
+int pk_setup_create(pk_ctx* ctx, const pk_assembly* assembly, pk_setup** out);
+void pk_setup_destroy(pk_setup* setup);
+/* SetupForProver::make_verification_key (src/plonk.rs:122-124): 11 commitments, order q_a,q_b,q_c,q_d,q_m,q_const,
+ * q_dnext, sigma_0..sigma_3. */
+int pk_setup_commitments(pk_ctx* ctx, pk_setup* setup, uint64_t out_xy[11][8]);
+/* Copies the witness (variable values, canonical, [nvars][4]; entry 0 must be 0) to the device. */
+int pk_witness_upload(pk_ctx* ctx, pk_setup* setup, const uint64_t* var_values, uint64_t nvars);
+/* SetupForProver::prove(circuit, "keccak") with the monomial-form SRS (src/plonk.rs:132-176): input values of the
+ * public inputs are written to inputs_out[num_inputs][4].  var_values may be NULL to reuse the uploaded witness. */
+int pk_prove(pk_ctx* ctx, pk_setup* setup, const uint64_t* var_values, uint64_t nvars, pk_proof* proof, uint64_t* inputs_out);
+
+/* ---- measurement hooks --------------------------------------------------------------------------------- */
+typedef struct pk_profile {
+    uint64_t kernel_launches;       /* kernels launched by this library since the last reset */
+    uint64_t msm_accum_launches;    /* launches of the bucket-accumulation kernel (the dominant kernel) */
+    double msm_accum_ms;            /* their summed CUDA-event time (only while profiling is on) */
+    uint64_t msm_accum_points;      /* (scalar, base) pairs those launches covered */
+    uint64_t ntt_launches;
+    double ntt_ms;
+    uint64_t ntt_elements;          /* elements x passes */
+    double phase_ms[8];             /* last pk_prove: round1..round5, setup-dependent, h2d, total (CUDA events) */
+} pk_profile;
+void pk_profile_enable(pk_ctx* ctx, int on);
+void pk_profile_reset(pk_ctx* ctx);
+void pk_profile_get(const pk_ctx* ctx, pk_profile* out);
+
+/* device-resident micro-benchmarks (inputs generated on the device): return elapsed ms by CUDA events */
+int pk_bench_ntt(pk_ctx* ctx, uint32_t log_n, int iters, double* ms_per_iter);
+int pk_bench_msm(pk_ctx* ctx, uint64_t n, int iters, double* ms_per_iter);
+int pk_bench_fieldmul(pk_ctx* ctx, int which /*0 Fr, 1 Fq*/, double* gmuls_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLONKIT_B200_H */

@@ -11,10 +11,14 @@
 // against Appendix C in tests/test_oracle.py.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
+#include <new>
 #include <vector>
 
 namespace orc {
+
+template <class T> using hvec = std::vector<T>;
 
 typedef uint64_t u64;
 typedef unsigned __int128 u128;
@@ -182,7 +186,7 @@ typedef Fp<FqTag> Fq;
 
 // batch inversion (Montgomery's trick); zeros are left as zeros (bellman's batch_inversion skips them [ext])
 template <class F> static void batch_inverse(F* a, size_t n) {
-    std::vector<F> pre(n);
+    hvec<F> pre(n);
     F acc = F::one();
     for (size_t i = 0; i < n; ++i) {
         pre[i] = acc;

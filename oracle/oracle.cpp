@@ -15,6 +15,8 @@
 //     algorithms (domain.rs / multiexp.rs [ext]); window c = ceil(ln(chunk_len)), c = 3 below 32 elements.
 //   * SRS generation Crs::crs_42: src/plonk.rs:41,47 (tau = 42).
 //   * EC inverse FFT Crs::from_powers: src/plonk.rs:179-185.
+#include <malloc.h>
+
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -93,7 +95,7 @@ static void parallel_fft(Fr* a, size_t n, const Fr& omega, int log_n, int log_cp
     size_t num_cpus = size_t(1) << log_cpus;
     int log_new_n = log_n - log_cpus;
     size_t new_n = size_t(1) << log_new_n;
-    std::vector<std::vector<Fr>> tmp(num_cpus, std::vector<Fr>(new_n, Fr::zero()));
+    std::vector<hvec<Fr>> tmp(num_cpus, hvec<Fr>(new_n, Fr::zero()));
     Fr new_omega = omega.pow_u64(num_cpus);
     std::vector<std::thread> th;
     for (size_t j = 0; j < num_cpus; ++j) {
@@ -101,7 +103,7 @@ static void parallel_fft(Fr* a, size_t n, const Fr& omega, int log_n, int log_cp
             Fr omega_j = omega.pow_u64(j);
             Fr omega_step = omega.pow_u64((u64)j << log_new_n);
             Fr elt = Fr::one();
-            std::vector<Fr>& t = tmp[j];
+            hvec<Fr>& t = tmp[j];
             for (size_t i = 0; i < new_n; ++i) {
                 for (size_t s = 0; s < num_cpus; ++s) {
                     size_t idx = (i + (s << log_new_n)) % n;
@@ -133,21 +135,21 @@ static void distribute_powers(Fr* a, size_t n, const Fr& g, int threads) {
 static void scale_all(Fr* a, size_t n, const Fr& s, int threads) {
     parallel_chunks(n, threads, [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) a[i] *= s; });
 }
-static void fft(std::vector<Fr>& a, int threads) {
+static void fft(hvec<Fr>& a, int threads) {
     int log_n = log2_floor(a.size());
     best_fft(a.data(), a.size(), omega_for(log_n), log_n, threads);
 }
-static void ifft(std::vector<Fr>& a, int threads) {
+static void ifft(hvec<Fr>& a, int threads) {
     int log_n = log2_floor(a.size());
     best_fft(a.data(), a.size(), omega_for(log_n).inverse(), log_n, threads);
     scale_all(a.data(), a.size(), Fr::from_u64(a.size()).inverse(), threads);
 }
 static const u64 COSET_GEN = 7;  // Fr::multiplicative_generator()
-static void coset_fft(std::vector<Fr>& a, int threads) {
+static void coset_fft(hvec<Fr>& a, int threads) {
     distribute_powers(a.data(), a.size(), Fr::from_u64(COSET_GEN), threads);
     fft(a, threads);
 }
-static void icoset_fft(std::vector<Fr>& a, int threads) {
+static void icoset_fft(hvec<Fr>& a, int threads) {
     ifft(a, threads);
     distribute_powers(a.data(), a.size(), Fr::from_u64(COSET_GEN).inverse(), threads);
 }
@@ -159,7 +161,7 @@ static G1 dense_multiexp_inner(const G1Affine* bases, const Repr* exps, size_t n
     G1 region = G1::infinity();
     std::mutex mu;
     parallel_chunks(n, threads, [&](size_t b, size_t e, int) {
-        std::vector<G1> buckets((size_t(1) << c) - 1, G1::infinity());
+        hvec<G1> buckets((size_t(1) << c) - 1, G1::infinity());
         G1 acc = G1::infinity();
         for (size_t i = b; i < e; ++i) {
             const u64* x = exps[i].v;
@@ -200,9 +202,9 @@ static G1 dense_multiexp(const G1Affine* bases, const Repr* exps, size_t n, int 
     }
     return dense_multiexp_inner(bases, exps, n, 0, c, true, threads);
 }
-static G1Affine commit(const std::vector<Fr>& coeffs, const G1Affine* srs, int threads) {
+static G1Affine commit(const hvec<Fr>& coeffs, const G1Affine* srs, int threads) {
     size_t n = coeffs.size();
-    std::vector<Repr> reprs(n);
+    hvec<Repr> reprs(n);
     parallel_chunks(n, threads, [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) coeffs[i].to_canonical(reprs[i].v); });
     return dense_multiexp(srs, reprs.data(), n, threads).to_affine();
 }
@@ -268,14 +270,14 @@ struct orc_assembly {
 
 static const u64 NON_RES[4] = {1, 5, 7, 10};  // k_i (vk.bin bytes 752-847; template.sol:845-853)
 
-static std::vector<Fr> load_frs(const uint64_t* src, size_t n, int threads) {
-    std::vector<Fr> v(n);
+static hvec<Fr> load_frs(const uint64_t* src, size_t n, int threads) {
+    hvec<Fr> v(n);
     parallel_chunks(n, threads, [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) v[i] = Fr::from_canonical(src + 4 * i); });
     return v;
 }
 
 // sigma_i values on H
-static void build_sigma(const orc_assembly& as, const std::vector<Fr>& omega_pows, std::vector<Fr> sigma[4]) {
+static void build_sigma(const orc_assembly& as, const hvec<Fr>& omega_pows, hvec<Fr> sigma[4]) {
     size_t N = as.n;
     Fr k[4];
     for (int c = 0; c < 4; ++c) k[c] = Fr::from_u64(NON_RES[c]);
@@ -284,7 +286,7 @@ static void build_sigma(const orc_assembly& as, const std::vector<Fr>& omega_pow
         for (size_t r = 0; r < N; ++r) sigma[c][r] = k[c] * omega_pows[r];
     }
     const uint64_t NONE = ~uint64_t(0);
-    std::vector<uint64_t> first(as.nvars, NONE), prev(as.nvars, NONE);
+    hvec<uint64_t> first(as.nvars, NONE), prev(as.nvars, NONE);
     for (size_t r = 0; r < N; ++r)
         for (int c = 0; c < 4; ++c) {
             uint32_t var = as.wire_idx[(size_t)c * N + r];
@@ -301,15 +303,15 @@ static void build_sigma(const orc_assembly& as, const std::vector<Fr>& omega_pow
         }
 }
 
-static std::vector<Fr> powers(const Fr& g, size_t n) {
-    std::vector<Fr> p(n);
+static hvec<Fr> powers(const Fr& g, size_t n) {
+    hvec<Fr> p(n);
     Fr x = Fr::one();
     for (size_t i = 0; i < n; ++i) { p[i] = x; x *= g; }
     return p;
 }
 
-static Fr eval_poly(const std::vector<Fr>& p, const Fr& x, int threads) {
-    std::vector<Fr> partial(threads < 1 ? 1 : threads, Fr::zero());
+static Fr eval_poly(const hvec<Fr>& p, const Fr& x, int threads) {
+    hvec<Fr> partial(threads < 1 ? 1 : threads, Fr::zero());
     parallel_chunks(p.size(), threads, [&](size_t b, size_t e, int tid) {
         Fr acc = Fr::zero();
         for (size_t i = e; i-- > b;) acc = acc * x + p[i];
@@ -321,9 +323,9 @@ static Fr eval_poly(const std::vector<Fr>& p, const Fr& x, int threads) {
 }
 
 // (p(X) - p(z)) / (X - z) by synthetic division (p(z) is discarded: remainder)
-static std::vector<Fr> divide_by_linear(const std::vector<Fr>& p, const Fr& z) {
+static hvec<Fr> divide_by_linear(const hvec<Fr>& p, const Fr& z) {
     size_t n = p.size();
-    std::vector<Fr> q(n, Fr::zero());
+    hvec<Fr> q(n, Fr::zero());
     Fr carry = Fr::zero();
     for (size_t i = n; i-- > 1;) {
         carry = p[i] + carry * z;
@@ -333,22 +335,22 @@ static std::vector<Fr> divide_by_linear(const std::vector<Fr>& p, const Fr& z) {
 }
 
 // LDE of a coefficient vector (len N) onto the coset 7*H_{4N}, natural order
-static std::vector<Fr> lde4(const std::vector<Fr>& coeffs, int threads) {
-    std::vector<Fr> v(coeffs.size() * 4, Fr::zero());
+static hvec<Fr> lde4(const hvec<Fr>& coeffs, int threads) {
+    hvec<Fr> v(coeffs.size() * 4, Fr::zero());
     std::copy(coeffs.begin(), coeffs.end(), v.begin());
     coset_fft(v, threads);
     return v;
 }
 
 struct SetupPolys {
-    std::vector<Fr> sel[7];    // monomial form
-    std::vector<Fr> sigma[4];  // monomial form
-    std::vector<Fr> sigma_vals[4];
+    hvec<Fr> sel[7];    // monomial form
+    hvec<Fr> sigma[4];  // monomial form
+    hvec<Fr> sigma_vals[4];
 };
 static void make_setup(const orc_assembly& as, SetupPolys& sp, int threads) {
     size_t N = as.n;
     int log_n = log2_floor(N);
-    std::vector<Fr> om = powers(omega_for(log_n), N);
+    hvec<Fr> om = powers(omega_for(log_n), N);
     for (int s = 0; s < 7; ++s) {
         sp.sel[s] = load_frs(as.selectors + (size_t)s * N * 4, N, threads);
         ifft(sp.sel[s], threads);
@@ -359,7 +361,14 @@ static void make_setup(const orc_assembly& as, SetupPolys& sp, int threads) {
 
 extern "C" {
 
-void orc_init() { init_fields(); }
+void orc_init() {
+    init_fields();
+    // Keep freed buffers inside the process: first-touch page faults are very slow in Firecracker-style VMs
+    // (measured here: ~20 MB/s), so the timed CPU baseline must not re-fault its working set on every call.
+    mallopt(M_MMAP_THRESHOLD, 1 << 30);
+    mallopt(M_TRIM_THRESHOLD, -1);
+    mallopt(M_TOP_PAD, 64 << 20);
+}
 
 // raw Montgomery constants, for checking against SURVEY App. C
 void orc_constants(uint64_t* out /* [2][3][4] : (R, R2, {INV,0,0,0}) for Fr then Fq */) {
@@ -391,7 +400,7 @@ void orc_fr_inv(const uint64_t* a, uint64_t* out, uint64_t n) {
 void orc_ntt(uint64_t* data, int log_n, int inverse, int coset, int threads) {
     init_fields();
     size_t n = size_t(1) << log_n;
-    std::vector<Fr> a = load_frs(data, n, threads);
+    hvec<Fr> a = load_frs(data, n, threads);
     if (!inverse) { if (coset) coset_fft(a, threads); else fft(a, threads); }
     else { if (coset) icoset_fft(a, threads); else ifft(a, threads); }
     for (size_t i = 0; i < n; ++i) a[i].to_canonical(data + 4 * i);
@@ -400,7 +409,7 @@ void orc_ntt(uint64_t* data, int log_n, int inverse, int coset, int threads) {
 void orc_naive_dft(const uint64_t* in, uint64_t* out, int log_n) {
     init_fields();
     size_t n = size_t(1) << log_n;
-    std::vector<Fr> a = load_frs(in, n, 1);
+    hvec<Fr> a = load_frs(in, n, 1);
     Fr w = omega_for(log_n);
     for (size_t k = 0; k < n; ++k) {
         Fr wk = w.pow_u64(k), x = Fr::one(), s = Fr::zero();
@@ -412,13 +421,13 @@ void orc_naive_dft(const uint64_t* in, uint64_t* out, int log_n) {
 void orc_lde4(const uint64_t* coeffs, int log_n, uint64_t* out, int threads) {
     init_fields();
     size_t n = size_t(1) << log_n;
-    std::vector<Fr> a = load_frs(coeffs, n, threads);
-    std::vector<Fr> v = lde4(a, threads);
+    hvec<Fr> a = load_frs(coeffs, n, threads);
+    hvec<Fr> v = lde4(a, threads);
     for (size_t i = 0; i < 4 * n; ++i) v[i].to_canonical(out + 4 * i);
 }
 
-static std::vector<G1Affine> load_points(const uint64_t* xy, size_t n, int threads) {
-    std::vector<G1Affine> p(n);
+static hvec<G1Affine> load_points(const uint64_t* xy, size_t n, int threads) {
+    hvec<G1Affine> p(n);
     parallel_chunks(n, threads, [&](size_t b, size_t e, int) {
         for (size_t i = b; i < e; ++i) {
             const uint64_t* s = xy + 8 * i;
@@ -438,33 +447,33 @@ static void store_point(const G1Affine& a, uint64_t* out) {
 // MSM: scalars canonical LE [n][4]; bases affine canonical LE [n][8] ((0,0) = infinity); out [8] ((0,0) = infinity)
 void orc_msm(const uint64_t* scalars, const uint64_t* bases, uint64_t n, uint64_t* out, int threads) {
     init_fields();
-    std::vector<G1Affine> b = load_points(bases, n, threads);
+    hvec<G1Affine> b = load_points(bases, n, threads);
     G1 r = dense_multiexp(b.data(), (const Repr*)scalars, n, threads);
     store_point(r.to_affine(), out);
 }
 // naive sum of double-and-add products (independent check path; small n)
 void orc_msm_naive(const uint64_t* scalars, const uint64_t* bases, uint64_t n, uint64_t* out) {
     init_fields();
-    std::vector<G1Affine> b = load_points(bases, n, 1);
+    hvec<G1Affine> b = load_points(bases, n, 1);
     G1 acc = G1::infinity();
     for (uint64_t i = 0; i < n; ++i) acc = acc.add(G1::from_affine(b[i]).mul(scalars + 4 * i));
     store_point(acc.to_affine(), out);
 }
 int orc_on_curve(const uint64_t* xy, uint64_t n) {
     init_fields();
-    std::vector<G1Affine> b = load_points(xy, n, 1);
+    hvec<G1Affine> b = load_points(xy, n, 1);
     for (auto& p : b) if (!p.on_curve()) return 0;
     return 1;
 }
 // out = k * P for canonical k
 void orc_g1_mul(const uint64_t* xy, const uint64_t* k, uint64_t* out) {
     init_fields();
-    std::vector<G1Affine> b = load_points(xy, 1, 1);
+    hvec<G1Affine> b = load_points(xy, 1, 1);
     store_point(G1::from_affine(b[0]).mul(k).to_affine(), out);
 }
 void orc_g1_add(const uint64_t* p, const uint64_t* q, uint64_t* out) {
     init_fields();
-    std::vector<G1Affine> a = load_points(p, 1, 1), b = load_points(q, 1, 1);
+    hvec<G1Affine> a = load_points(p, 1, 1), b = load_points(q, 1, 1);
     store_point(G1::from_affine(a[0]).add(G1::from_affine(b[0])).to_affine(), out);
 }
 
@@ -473,7 +482,7 @@ void orc_srs_gen(uint64_t n, uint64_t tau, uint64_t* out, int threads) {
     init_fields();
     Fr t = Fr::from_u64(tau);
     G1 g = G1::from_affine(G1Affine::generator());
-    std::vector<G1> pts(n);
+    hvec<G1> pts(n);
     parallel_chunks(n, threads, [&](size_t b, size_t e, int) {
         u64 c[4];
         t.pow_u64(b).to_canonical(c);
@@ -482,7 +491,7 @@ void orc_srs_gen(uint64_t n, uint64_t tau, uint64_t* out, int threads) {
         for (size_t i = b; i < e; ++i) { pts[i] = p; p = p.mul(tc); }
     });
     // batch normalisation
-    std::vector<Fq> z(n);
+    hvec<Fq> z(n);
     for (size_t i = 0; i < n; ++i) z[i] = pts[i].Z;
     batch_inverse(z.data(), n);
     parallel_chunks(n, threads, [&](size_t b, size_t e, int) {
@@ -499,16 +508,16 @@ void orc_srs_gen(uint64_t n, uint64_t tau, uint64_t* out, int threads) {
 void orc_ec_intt(const uint64_t* bases, int log_n, uint64_t* out, int threads) {
     init_fields();
     size_t n = size_t(1) << log_n;
-    std::vector<G1Affine> in = load_points(bases, n, threads);
-    std::vector<G1> a(n);
+    hvec<G1Affine> in = load_points(bases, n, threads);
+    hvec<G1> a(n);
     for (size_t i = 0; i < n; ++i) a[i] = G1::from_affine(in[i]);
     for (size_t k = 0; k < n; ++k) { size_t rk = bitrev32((uint32_t)k, log_n); if (k < rk) std::swap(a[k], a[rk]); }
     Fr omega_inv = omega_for(log_n).inverse();
     size_t m = 1;
     for (int s = 0; s < log_n; ++s) {
         Fr w_m = omega_inv.pow_u64(n / (2 * m));
-        std::vector<Fr> w = powers(w_m, m);
-        std::vector<Repr> wc(m);
+        hvec<Fr> w = powers(w_m, m);
+        hvec<Repr> wc(m);
         for (size_t j = 0; j < m; ++j) w[j].to_canonical(wc[j].v);
         size_t groups = n / (2 * m);
         parallel_chunks(groups, threads, [&](size_t gb, size_t ge, int) {
@@ -538,7 +547,7 @@ void orc_setup_commitments(const orc_assembly* as, const uint64_t* srs, uint64_t
     size_t N = as->n;
     SetupPolys sp;
     make_setup(*as, sp, threads);
-    std::vector<G1Affine> bases = load_points(srs, N, threads);
+    hvec<G1Affine> bases = load_points(srs, N, threads);
     for (int s = 0; s < 7; ++s) store_point(commit(sp.sel[s], bases.data(), threads), out + 8 * s);
     for (int c = 0; c < 4; ++c) store_point(commit(sp.sigma[c], bases.data(), threads), out + 8 * (7 + c));
     if (sigma_vals_out)
@@ -556,23 +565,23 @@ int64_t orc_prove(const orc_assembly* as, const uint64_t* srs, uint8_t* proof_ou
     const int log_n = log2_floor(N);
     const size_t NI = as->num_inputs;
     const Fr omega = omega_for(log_n);
-    std::vector<Fr> om = powers(omega, N);
-    std::vector<G1Affine> bases = load_points(srs, N, threads);
+    hvec<Fr> om = powers(omega, N);
+    hvec<G1Affine> bases = load_points(srs, N, threads);
 
     // ---- setup polynomials (reference: prepare_setup_for_prover, src/plonk.rs:97-119; recomputed here per call)
     SetupPolys sp;
     make_setup(*as, sp, threads);
 
     // ---- witness -> wire values
-    std::vector<Fr> vars = load_frs(as->var_values, as->nvars, threads);
-    std::vector<Fr> wv[4];
+    hvec<Fr> vars = load_frs(as->var_values, as->nvars, threads);
+    hvec<Fr> wv[4];
     for (int c = 0; c < 4; ++c) {
         wv[c].resize(N);
         for (size_t r = 0; r < N; ++r) wv[c][r] = vars[as->wire_idx[(size_t)c * N + r]];
     }
-    std::vector<Fr> selv[7];
+    hvec<Fr> selv[7];
     for (int s = 0; s < 7; ++s) selv[s] = load_frs(as->selectors + (size_t)s * N * 4, N, threads);
-    std::vector<Fr> pi_vals(N, Fr::zero());
+    hvec<Fr> pi_vals(N, Fr::zero());
     for (size_t i = 0; i < NI; ++i) pi_vals[i] = wv[0][i];
     // is_satisfied_using_one_shot_check (src/plonk.rs:137)
     for (size_t r = 0; r + 1 < N; ++r) {
@@ -585,7 +594,7 @@ int64_t orc_prove(const orc_assembly* as, const uint64_t* srs, uint8_t* proof_ou
     for (size_t i = 0; i < NI; ++i) tr.update_fr(pi_vals[i]);
 
     // ---- round 1: wire commitments
-    std::vector<Fr> w[4];
+    hvec<Fr> w[4];
     G1Affine Cw[4];
     for (int c = 0; c < 4; ++c) {
         w[c] = wv[c];
@@ -598,7 +607,7 @@ int64_t orc_prove(const orc_assembly* as, const uint64_t* srs, uint8_t* proof_ou
     // ---- round 2: grand product
     Fr kk[4];
     for (int c = 0; c < 4; ++c) kk[c] = Fr::from_u64(NON_RES[c]);
-    std::vector<Fr> num(N), den(N);
+    hvec<Fr> num(N), den(N);
     parallel_chunks(N, threads, [&](size_t b, size_t e, int) {
         for (size_t j = b; j < e; ++j) {
             Fr nn = Fr::one(), dd = Fr::one();
@@ -610,10 +619,10 @@ int64_t orc_prove(const orc_assembly* as, const uint64_t* srs, uint8_t* proof_ou
         }
     });
     batch_inverse(den.data(), N);
-    std::vector<Fr> zv(N);
+    hvec<Fr> zv(N);
     zv[0] = Fr::one();
     for (size_t j = 0; j + 1 < N; ++j) zv[j + 1] = zv[j] * num[j] * den[j];
-    std::vector<Fr> zp = zv;
+    hvec<Fr> zp = zv;
     ifft(zp, threads);
     G1Affine Cz = commit(zp, bases.data(), threads);
     tr.update_g1(Cz);
@@ -621,16 +630,16 @@ int64_t orc_prove(const orc_assembly* as, const uint64_t* srs, uint8_t* proof_ou
 
     // ---- round 3: quotient on the coset 7*H_4N
     const size_t M = 4 * N;
-    std::vector<Fr> lw[4], lsel[7], lsig[4];
+    hvec<Fr> lw[4], lsel[7], lsig[4];
     for (int c = 0; c < 4; ++c) lw[c] = lde4(w[c], threads);
     for (int s = 0; s < 7; ++s) lsel[s] = lde4(sp.sel[s], threads);
     for (int c = 0; c < 4; ++c) lsig[c] = lde4(sp.sigma[c], threads);
-    std::vector<Fr> lz = lde4(zp, threads);
-    std::vector<Fr> pi_poly = pi_vals;
+    hvec<Fr> lz = lde4(zp, threads);
+    hvec<Fr> pi_poly = pi_vals;
     ifft(pi_poly, threads);
-    std::vector<Fr> lpi = lde4(pi_poly, threads);
-    std::vector<Fr> l0c(N, Fr::from_u64(N).inverse());  // L_0(X) = (1/N) sum X^j
-    std::vector<Fr> ll0 = lde4(l0c, threads);
+    hvec<Fr> lpi = lde4(pi_poly, threads);
+    hvec<Fr> l0c(N, Fr::from_u64(N).inverse());  // L_0(X) = (1/N) sum X^j
+    hvec<Fr> ll0 = lde4(l0c, threads);
     Fr omega4 = omega_for(log_n + 2);
     Fr g7 = Fr::from_u64(COSET_GEN);
     // 1/Z_H on the coset takes 4 values: x^N = 7^N * omega4^(J*N) = 7^N * i^(J mod 4)
@@ -640,7 +649,7 @@ int64_t orc_prove(const orc_assembly* as, const uint64_t* srs, uint8_t* proof_ou
         Fr x = g7n;
         for (int i = 0; i < 4; ++i) { zh_inv[i] = (x - Fr::one()).inverse(); x *= w4n; }
     }
-    std::vector<Fr> tq(M);
+    hvec<Fr> tq(M);
     Fr alpha2 = alpha.sqr();
     parallel_chunks(M, threads, [&](size_t b, size_t e, int) {
         Fr x = g7 * omega4.pow_u64(b);
@@ -662,7 +671,7 @@ int64_t orc_prove(const orc_assembly* as, const uint64_t* srs, uint8_t* proof_ou
     icoset_fft(tq, threads);
     // deg t <= 4N - 5 ... top coefficients must vanish
     for (size_t i = M - 3; i < M; ++i) if (!tq[i].is_zero()) return -2;
-    std::vector<Fr> tchunk[4];
+    hvec<Fr> tchunk[4];
     G1Affine Ct[4];
     for (int i = 0; i < 4; ++i) {
         tchunk[i].assign(tq.begin() + i * N, tq.begin() + (i + 1) * N);
@@ -688,7 +697,7 @@ int64_t orc_prove(const orc_assembly* as, const uint64_t* srs, uint8_t* proof_ou
         zfac += p;
         for (int i = 0; i < 3; ++i) sfac *= wz[i] + beta * sz[i] + gamma;
     }
-    std::vector<Fr> rp(N);
+    hvec<Fr> rp(N);
     Fr ab = wz[0] * wz[1];
     parallel_chunks(N, threads, [&](size_t b, size_t e, int) {
         for (size_t i = b; i < e; ++i) {
@@ -706,7 +715,7 @@ int64_t orc_prove(const orc_assembly* as, const uint64_t* srs, uint8_t* proof_ou
     Fr v = tr.challenge();
 
     // ---- round 5: openings
-    std::vector<Fr> agg(N), agg2(N);
+    hvec<Fr> agg(N), agg2(N);
     Fr vp[11];
     vp[0] = Fr::one();
     for (int i = 1; i <= 10; ++i) vp[i] = vp[i - 1] * v;
@@ -719,7 +728,7 @@ int64_t orc_prove(const orc_assembly* as, const uint64_t* srs, uint8_t* proof_ou
             agg2[i] = vp[9] * zp[i] + vp[10] * w[3][i];
         }
     });
-    std::vector<Fr> q1 = divide_by_linear(agg, zeta), q2 = divide_by_linear(agg2, zeta_omega);
+    hvec<Fr> q1 = divide_by_linear(agg, zeta), q2 = divide_by_linear(agg2, zeta_omega);
     G1Affine W1 = commit(q1, bases.data(), threads), W2 = commit(q2, bases.data(), threads);
 
     if (challenges_out) {
@@ -749,6 +758,137 @@ int64_t orc_prove(const orc_assembly* as, const uint64_t* srs, uint8_t* proof_ou
     write_g1_be(W1, p); p += 64;
     write_g1_be(W2, p); p += 64;
     return (int64_t)(p - proof_out);
+}
+
+
+// ---------------------------------------------------------------- verifier with a known trapdoor
+// Restates contrib/template.sol:691-758 (verify_initial), :445-494 (verify_at_z), :496-586 (reconstruct_d) and
+// :588-689 (verify_commitments).  The final pairing check e(A, G2) * e(B, [tau] G2) == 1 is replaced by the equivalent
+// G1 identity A + tau * B == 0, which is decidable because the test SRS is generated from a known tau (42 for
+// keys/setup/setup_2^10.key).  Used for size-independent parity checks at sizes where orc_prove would take minutes.
+// proof: proof.bin bytes; vk_commitments: [11][8] canonical (order as orc_setup_commitments).  Returns 1 = accept,
+// 0 = reject, negative = malformed.
+static Fr read_fr_be(const uint8_t* p) {
+    u64 c[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 32; ++i) c[(31 - i) / 8] |= (u64)p[i] << (8 * ((31 - i) % 8));
+    return Fr::from_canonical(c);
+}
+static G1Affine read_g1_be(const uint8_t* p) {
+    if (p[0] & 0x40) return G1Affine::infinity();
+    u64 cx[4] = {0, 0, 0, 0}, cy[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 32; ++i) {
+        cx[(31 - i) / 8] |= (u64)p[i] << (8 * ((31 - i) % 8));
+        cy[(31 - i) / 8] |= (u64)p[32 + i] << (8 * ((31 - i) % 8));
+    }
+    G1Affine a; a.x = Fq::from_canonical(cx); a.y = Fq::from_canonical(cy); a.inf = false;
+    return a;
+}
+static u64 read_u64_be(const uint8_t* p) { u64 x = 0; for (int i = 0; i < 8; ++i) x = (x << 8) | p[i]; return x; }
+static G1 pmul(const G1Affine& p, const Fr& k) { u64 c[4]; k.to_canonical(c); return G1::from_affine(p).mul(c); }
+
+int orc_verify_trapdoor(const uint8_t* proof, uint64_t proof_len, const uint64_t* vk_commitments, uint64_t tau) {
+    init_fields();
+    if (proof_len < 16) return -1;
+    const uint8_t* p = proof;
+    u64 n_gates = read_u64_be(p); p += 8;
+    u64 ni = read_u64_be(p); p += 8;
+    if (proof_len != 16 + 32 * ni + 1096) return -1;
+    size_t N = n_gates + 1;
+    int log_n = log2_floor(N);
+    if ((size_t(1) << log_n) != N) return -1;
+    std::vector<Fr> inputs(ni);
+    for (u64 i = 0; i < ni; ++i) { inputs[i] = read_fr_be(p); p += 32; }
+    p += 8;
+    G1Affine Cw[4]; for (int i = 0; i < 4; ++i) { Cw[i] = read_g1_be(p); p += 64; }
+    G1Affine Cz = read_g1_be(p); p += 64;
+    p += 8;
+    G1Affine Ct[4]; for (int i = 0; i < 4; ++i) { Ct[i] = read_g1_be(p); p += 64; }
+    p += 8;
+    Fr wz[4]; for (int i = 0; i < 4; ++i) { wz[i] = read_fr_be(p); p += 32; }
+    p += 8;
+    Fr dzw = read_fr_be(p); p += 32;
+    Fr zzw = read_fr_be(p); p += 32;
+    Fr tz = read_fr_be(p); p += 32;
+    Fr rz = read_fr_be(p); p += 32;
+    p += 8;
+    Fr sz[3]; for (int i = 0; i < 3; ++i) { sz[i] = read_fr_be(p); p += 32; }
+    G1Affine W1 = read_g1_be(p); p += 64;
+    G1Affine W2 = read_g1_be(p); p += 64;
+    hvec<G1Affine> vk = load_points(vk_commitments, 11, 1);
+    for (auto& q : vk) if (!q.on_curve()) return -1;
+    G1Affine all[] = {Cw[0], Cw[1], Cw[2], Cw[3], Cz, Ct[0], Ct[1], Ct[2], Ct[3], W1, W2};
+    for (auto& q : all) if (!q.on_curve()) return 0;
+
+    Transcript tr;
+    for (u64 i = 0; i < ni; ++i) tr.update_fr(inputs[i]);
+    for (int i = 0; i < 4; ++i) tr.update_g1(Cw[i]);
+    Fr beta = tr.challenge(), gamma = tr.challenge();
+    tr.update_g1(Cz);
+    Fr alpha = tr.challenge();
+    for (int i = 0; i < 4; ++i) tr.update_g1(Ct[i]);
+    Fr zeta = tr.challenge();
+    for (int i = 0; i < 4; ++i) tr.update_fr(wz[i]);
+    tr.update_fr(dzw);
+    for (int i = 0; i < 3; ++i) tr.update_fr(sz[i]);
+    tr.update_fr(tz); tr.update_fr(rz); tr.update_fr(zzw);
+    Fr v = tr.challenge();
+    tr.update_g1(W1); tr.update_g1(W2);
+    Fr u = tr.challenge();
+
+    Fr omega = omega_for(log_n);
+    Fr zeta_n = zeta.pow_u64(N);
+    Fr zh = zeta_n - Fr::one();
+    if (zh.is_zero()) return 0;
+    Fr n_inv = Fr::from_u64(N).inverse();
+    auto lagrange = [&](u64 i) { Fr wi = omega.pow_u64(i); return wi * zh * n_inv * (zeta - wi).inverse(); };
+    // verify_at_z
+    Fr rhs = rz;
+    for (u64 i = 0; i < ni; ++i) rhs += lagrange(i) * inputs[i];
+    Fr zpart = zzw;
+    for (int i = 0; i < 3; ++i) zpart *= sz[i] * beta + gamma + wz[i];
+    zpart *= gamma + wz[3];
+    rhs -= zpart * alpha;
+    Fr l0 = lagrange(0);
+    rhs -= l0 * alpha.sqr();
+    if (!(zh * tz == rhs)) return 0;
+    // reconstruct_d
+    Fr kk[4]; for (int c = 0; c < 4; ++c) kk[c] = Fr::from_u64(NON_RES[c]);
+    G1 d = G1::from_affine(vk[5]);
+    for (int i = 0; i < 4; ++i) d = d.add(pmul(vk[i], wz[i]));
+    d = d.add(pmul(vk[4], wz[0] * wz[1]));
+    d = d.add(pmul(vk[6], dzw));
+    Fr gpz = alpha;
+    for (int i = 0; i < 4; ++i) gpz *= zeta * kk[i] * beta + gamma + wz[i];
+    gpz += l0 * alpha.sqr();
+    Fr v9 = v.pow_u64(9);
+    Fr lastp = beta * zzw * alpha;
+    for (int i = 0; i < 3; ++i) lastp *= beta * sz[i] + gamma + wz[i];
+    d = d.add(pmul(Cz, gpz)).add(pmul(vk[10], lastp).neg());
+    u64 vc[4]; v.to_canonical(vc);
+    d = d.mul(vc);
+    d = d.add(pmul(Cz, v9 * u));
+    // verify_commitments
+    G1 agg = G1::from_affine(Ct[0]);
+    Fr zp = Fr::one();
+    for (int i = 1; i < 4; ++i) { zp *= zeta_n; agg = agg.add(pmul(Ct[i], zp)); }
+    agg = agg.add(d);
+    Fr ac = v;
+    for (int i = 0; i < 4; ++i) { ac *= v; agg = agg.add(pmul(Cw[i], ac)); }
+    for (int i = 0; i < 3; ++i) { ac *= v; agg = agg.add(pmul(vk[7 + i], ac)); }
+    ac *= v; ac *= v;  // v^10
+    agg = agg.add(pmul(Cw[3], ac * u));
+    Fr val = tz + v * rz;
+    Fr a2 = v;
+    for (int i = 0; i < 4; ++i) { a2 *= v; val += wz[i] * a2; }
+    for (int i = 0; i < 3; ++i) { a2 *= v; val += sz[i] * a2; }
+    a2 *= v; val += zzw * a2 * u;
+    a2 *= v; val += dzw * a2 * u;
+    agg = agg.add(pmul(G1Affine::generator(), val).neg());
+    G1 with_gen = agg.add(pmul(W1, zeta)).add(pmul(W2, zeta * omega * u));
+    G1 with_x = pmul(W2, u).add(G1::from_affine(W1)).neg();
+    u64 tc[4] = {tau, 0, 0, 0};
+    G1 chk = with_gen.add(with_x.mul(tc));
+    return chk.is_inf() ? 1 : 0;
 }
 
 }  // extern "C"

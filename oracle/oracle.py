@@ -48,6 +48,7 @@ def lib():
         _LIB = ctypes.CDLL(so)
         _LIB.orc_prove.restype = ctypes.c_int64
         _LIB.orc_on_curve.restype = ctypes.c_int
+        _LIB.orc_verify_trapdoor.restype = ctypes.c_int
         _LIB.orc_init()
     return _LIB
 
@@ -223,3 +224,12 @@ def prove(n, num_inputs, wire_idx, var_values, selectors, srs, threads=1, want_c
         raise RuntimeError({-1: "circuit not satisfied", -2: "quotient is not a polynomial"}.get(ln, "oracle error %d" % ln))
     proof = buf.raw[:ln]
     return (proof, limbs_to_ints(ch)) if want_challenges else proof
+
+
+def verify_trapdoor(proof_bytes: bytes, vk_commitments, tau=42) -> bool:
+    """contrib/template.sol verifier with the pairing check replaced by the G1 identity A + tau*B == 0 (known tau)."""
+    vk = np.ascontiguousarray(vk_commitments, dtype=np.uint64).reshape(11, 8)
+    rc = lib().orc_verify_trapdoor(proof_bytes, ctypes.c_uint64(len(proof_bytes)), _p(vk), ctypes.c_uint64(tau))
+    if rc < 0:
+        raise ValueError("malformed proof / vk")
+    return rc == 1

@@ -1,0 +1,229 @@
+"""ctypes binding of the C-ABI CUDA library (include/plonkit_b200.h).
+
+There is no CPU fallback: if libplonkit_b200.so is missing, or no CUDA device can be opened, every compute call
+raises.  Loading the library needs no GPU (tests check the exported symbols on CPU-only machines).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libplonkit_b200.so")
+
+PK_OK = 0
+ERRORS = {
+    1: "AssignmentMissing",
+    2: "PolynomialDegreeTooLarge",
+    3: "DivisionByZero",
+    4: "Unsatisfiable",
+    5: "CudaError",
+    6: "InvalidArgument",
+}
+FMT_CANONICAL, FMT_MONTGOMERY = 0, 1
+
+EXPORTS = [
+    "pk_create", "pk_destroy", "pk_last_error", "pk_constants", "pk_srs_load_g1", "pk_srs_gen", "pk_ntt", "pk_lde4",
+    "pk_msm_g1", "pk_ec_intt_g1", "pk_setup_create", "pk_setup_destroy", "pk_setup_commitments", "pk_witness_upload",
+    "pk_prove", "pk_profile_enable", "pk_profile_reset", "pk_profile_get", "pk_bench_ntt", "pk_bench_msm",
+    "pk_bench_fieldmul",
+]
+
+
+class SynthesisError(RuntimeError):
+    """Mirror of bellman's SynthesisError as surfaced by SetupForProver::prove (src/plonk.rs:136)."""
+
+    def __init__(self, code, message):
+        super().__init__("%s: %s" % (ERRORS.get(code, "Error %d" % code), message))
+        self.code = code
+        self.kind = ERRORS.get(code, "Unknown")
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+class PkAssembly(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_uint64), ("num_inputs", ctypes.c_uint64), ("nvars", ctypes.c_uint64),
+                ("wire_idx", ctypes.c_void_p), ("selectors", ctypes.c_void_p)]
+
+
+class PkProof(ctypes.Structure):
+    _fields_ = [
+        ("n", ctypes.c_uint64), ("num_inputs", ctypes.c_uint64),
+        ("wire_commitments", ctypes.c_uint64 * 32),
+        ("grand_product_commitment", ctypes.c_uint64 * 8),
+        ("quotient_poly_commitments", ctypes.c_uint64 * 32),
+        ("wire_values_at_z", ctypes.c_uint64 * 16),
+        ("wire_values_at_z_omega", ctypes.c_uint64 * 4),
+        ("grand_product_at_z_omega", ctypes.c_uint64 * 4),
+        ("quotient_polynomial_at_z", ctypes.c_uint64 * 4),
+        ("linearization_polynomial_at_z", ctypes.c_uint64 * 4),
+        ("permutation_polynomials_at_z", ctypes.c_uint64 * 12),
+        ("opening_at_z_proof", ctypes.c_uint64 * 8),
+        ("opening_at_z_omega_proof", ctypes.c_uint64 * 8),
+        ("challenges", ctypes.c_uint64 * 20),
+    ]
+
+
+class PkProfile(ctypes.Structure):
+    _fields_ = [
+        ("kernel_launches", ctypes.c_uint64), ("msm_accum_launches", ctypes.c_uint64), ("msm_accum_ms", ctypes.c_double),
+        ("msm_accum_points", ctypes.c_uint64), ("ntt_launches", ctypes.c_uint64), ("ntt_ms", ctypes.c_double),
+        ("ntt_elements", ctypes.c_uint64), ("phase_ms", ctypes.c_double * 8),
+    ]
+
+
+_lib = None
+
+
+def load():
+    """Loads the shared library (no GPU needed for that) and declares the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibraryMissing("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "(there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, u64, i32, u32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32
+    lib.pk_create.argtypes = [i32, ctypes.POINTER(vp)]
+    lib.pk_destroy.argtypes = [vp]
+    lib.pk_destroy.restype = None
+    lib.pk_last_error.argtypes = [vp]
+    lib.pk_last_error.restype = ctypes.c_char_p
+    lib.pk_constants.argtypes = [vp]
+    lib.pk_constants.restype = None
+    lib.pk_srs_load_g1.argtypes = [vp, vp, u64, i32]
+    lib.pk_srs_gen.argtypes = [vp, u64, u64, vp]
+    lib.pk_ntt.argtypes = [vp, vp, u32, i32, i32, i32]
+    lib.pk_lde4.argtypes = [vp, vp, u32, vp, i32, i32]
+    lib.pk_msm_g1.argtypes = [vp, vp, u64, u64, vp, ctypes.POINTER(i32), i32]
+    lib.pk_ec_intt_g1.argtypes = [vp, u32, vp]
+    lib.pk_setup_create.argtypes = [vp, ctypes.POINTER(PkAssembly), ctypes.POINTER(vp)]
+    lib.pk_setup_destroy.argtypes = [vp]
+    lib.pk_setup_destroy.restype = None
+    lib.pk_setup_commitments.argtypes = [vp, vp, vp]
+    lib.pk_witness_upload.argtypes = [vp, vp, vp, u64]
+    lib.pk_prove.argtypes = [vp, vp, vp, u64, ctypes.POINTER(PkProof), vp]
+    lib.pk_profile_enable.argtypes = [vp, i32]
+    lib.pk_profile_enable.restype = None
+    lib.pk_profile_reset.argtypes = [vp]
+    lib.pk_profile_reset.restype = None
+    lib.pk_profile_get.argtypes = [vp, ctypes.POINTER(PkProfile)]
+    lib.pk_profile_get.restype = None
+    lib.pk_bench_ntt.argtypes = [vp, u32, i32, ctypes.POINTER(ctypes.c_double)]
+    lib.pk_bench_msm.argtypes = [vp, u64, i32, ctypes.POINTER(ctypes.c_double)]
+    lib.pk_bench_fieldmul.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double)]
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+class Context:
+    """One CUDA device context (pk_ctx).  Stands in for bellman's Worker (src/plonk.rs:41,47,183)."""
+
+    def __init__(self, device=0):
+        self._lib = load()
+        h = ctypes.c_void_p()
+        rc = self._lib.pk_create(device, ctypes.byref(h))
+        if rc != PK_OK:
+            raise SynthesisError(rc, "cannot open CUDA device %d (no GPU? there is no CPU fallback)" % device)
+        self._h = h
+        self.device = device
+        self.srs_size = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pk_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != PK_OK:
+            raise SynthesisError(rc, self._lib.pk_last_error(self._h).decode())
+
+    # ---- SRS
+    def srs_load_g1(self, bases, window_bits=0):
+        b = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
+        self._check(self._lib.pk_srs_load_g1(self._h, _ptr(b), b.shape[0], window_bits))
+        self.srs_size = b.shape[0]
+
+    def srs_gen(self, n, tau=42):
+        out = np.zeros((n, 8), dtype=np.uint64)
+        self._check(self._lib.pk_srs_gen(self._h, n, tau, _ptr(out)))
+        return out
+
+    # ---- primitives
+    def ntt(self, data, inverse=False, coset=False, fmt=FMT_CANONICAL):
+        a = np.ascontiguousarray(data, dtype=np.uint64).reshape(-1, 4).copy()
+        log_n = a.shape[0].bit_length() - 1
+        if 1 << log_n != a.shape[0]:
+            raise SynthesisError(6, "length is not a power of two")
+        self._check(self._lib.pk_ntt(self._h, _ptr(a), log_n, int(inverse), int(coset), fmt))
+        return a
+
+    def lde4(self, coeffs, bitreversed=False, fmt=FMT_CANONICAL):
+        a = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, 4)
+        log_n = a.shape[0].bit_length() - 1
+        if 1 << log_n != a.shape[0]:
+            raise SynthesisError(6, "length is not a power of two")
+        out = np.zeros((4 * a.shape[0], 4), dtype=np.uint64)
+        self._check(self._lib.pk_lde4(self._h, _ptr(a), log_n, _ptr(out), int(bitreversed), fmt))
+        return out
+
+    def msm_g1(self, scalars, base_offset=0, fmt=FMT_CANONICAL):
+        s = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+        out = np.zeros(8, dtype=np.uint64)
+        inf = ctypes.c_int(0)
+        self._check(self._lib.pk_msm_g1(self._h, _ptr(s) if s.shape[0] else None, s.shape[0], base_offset, _ptr(out),
+                                        ctypes.byref(inf), fmt))
+        return out
+
+    def ec_intt_g1(self, log_n):
+        out = np.zeros((1 << log_n, 8), dtype=np.uint64)
+        self._check(self._lib.pk_ec_intt_g1(self._h, log_n, _ptr(out)))
+        return out
+
+    # ---- profiling / micro-benchmarks
+    def profile_enable(self, on=True):
+        self._lib.pk_profile_enable(self._h, int(on))
+
+    def profile_reset(self):
+        self._lib.pk_profile_reset(self._h)
+
+    def profile(self):
+        p = PkProfile()
+        self._lib.pk_profile_get(self._h, ctypes.byref(p))
+        d = {k: getattr(p, k) for k, _ in PkProfile._fields_ if k != "phase_ms"}
+        d["phase_ms"] = list(p.phase_ms)
+        return d
+
+    def bench_ntt(self, log_n, iters=10):
+        ms = ctypes.c_double()
+        self._check(self._lib.pk_bench_ntt(self._h, log_n, iters, ctypes.byref(ms)))
+        return ms.value
+
+    def bench_msm(self, n, iters=3):
+        ms = ctypes.c_double()
+        self._check(self._lib.pk_bench_msm(self._h, n, iters, ctypes.byref(ms)))
+        return ms.value
+
+    def bench_fieldmul(self, which=0):
+        g = ctypes.c_double()
+        self._check(self._lib.pk_bench_fieldmul(self._h, which, ctypes.byref(g)))
+        return g.value
+
+
+def constants():
+    out = np.zeros(24, dtype=np.uint64)
+    load().pk_constants(_ptr(out))
+    return out

@@ -1,0 +1,332 @@
+// Radix-2 NTT over BN254 Fr for sm_100a.
+//
+// Replaces bellman_ce's Polynomial::{fft, ifft, coset_fft, icoset_fft_for_generator,
+// bitreversed_lde_using_bitreversed_ntt} (call sites src/plonk.rs:104,140,152-159), which on
+// the CPU are an in-place Cooley-Tukey radix-2 transform split over host threads.
+//
+// Device design: a size-2^L transform is cut into passes of up to 10 stages.  Each pass stages a tile of 2^k
+// (strided) x C (contiguous) elements in shared memory — C >= 4 keeps every global access a >=128 B run of
+// 128-bit loads/stores — runs its k butterfly stages there with one Montgomery multiplication per butterfly
+// held in registers, and writes the tile back.  Forward transforms are decimation-in-frequency (natural ->
+// bit-reversed), inverse ones decimation-in-time (bit-reversed -> natural), so the prover never needs a
+// standalone bit-reversal pass: evaluations live in bit-reversed order between the two.  Coset shifts and the
+// 1/n factor are fused into the first/last pass as an element-wise pre/post multiplication.
+//
+// Twiddles: one table w^e (e <= n_max/2) per context; smaller domains index it with a stride, and the inverse
+// transform reads w^{-e} as -w^{n/2-e}, so no inverse table exists.
+//
+// HBM traffic per pass: 64 B per element (32 B in, 32 B out) + pre/post tables; a 2^20 transform is 3 passes.
+#include "ntt.cuh"
+
+namespace pk {
+
+fr_t host_root_of_unity(int log_n) {
+    fr_t g;
+    for (int i = 0; i < 8; ++i) g.v[i] = FrRoots::root_2_28(i);
+    for (int i = 0; i < 28 - log_n; ++i) g = g.sqr();
+    return g;
+}
+
+// ---------------------------------------------------------------- table builders
+__global__ void tw_build_kernel(fr_t* tw, fr_t root, size_t count) {
+    size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (e < count) st_fp(tw + e, root.pow_u64(e));
+}
+
+// out[s][j] = g_s^j  with g_s given per slot
+__global__ void coset_scale_build_kernel(fr_t* out, fr_t g0, fr_t g1, fr_t g2, fr_t g3, size_t n) {
+    size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const fr_t g = blockIdx.y == 0 ? g0 : blockIdx.y == 1 ? g1 : blockIdx.y == 2 ? g2 : g3;
+    st_fp(out + blockIdx.y * n + j, g.pow_u64(j));
+}
+// out[k] = ginv^k * c
+__global__ void geom_build_kernel(fr_t* out, fr_t ginv, fr_t c, size_t n) {
+    size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (k < n) st_fp(out + k, ginv.pow_u64(k) * c);
+}
+__global__ void fill_kernel(fr_t* out, fr_t c, size_t n) {
+    size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (k < n) st_fp(out + k, c);
+}
+__global__ void to_mont_kernel(fr_t* data, size_t n) {
+    size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (k < n) st_fp(data + k, ld_fp(data + k).to_mont());
+}
+__global__ void from_mont_kernel(const fr_t* src, fr_t* dst, size_t n) {
+    size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (k < n) st_fp(dst + k, ld_fp(src + k).from_mont());
+}
+__global__ void bitrev_kernel(const fr_t* src, fr_t* dst, int log_n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >> log_n) return;
+    size_t r = log_n ? (size_t)(__brev((unsigned)i) >> (32 - log_n)) : 0;
+    st_fp(dst + r, ld_fp(src + i));
+}
+
+static inline dim3 grid1d(size_t n, int block) { return dim3((unsigned)((n + block - 1) / block)); }
+
+void fr_to_mont(pk_ctx* ctx, fr_t* data, size_t n) {
+    if (!n) return;
+    to_mont_kernel<<<grid1d(n, 256), 256, 0, ctx->stream>>>(data, n);
+    ctx->prof.kernel_launches++;
+}
+void fr_from_mont(pk_ctx* ctx, const fr_t* src, fr_t* dst, size_t n) {
+    if (!n) return;
+    from_mont_kernel<<<grid1d(n, 256), 256, 0, ctx->stream>>>(src, dst, n);
+    ctx->prof.kernel_launches++;
+}
+void bitrev_permute(pk_ctx* ctx, const fr_t* src, fr_t* dst, int log_n) {
+    size_t n = size_t(1) << log_n;
+    bitrev_kernel<<<grid1d(n, 256), 256, 0, ctx->stream>>>(src, dst, log_n);
+    ctx->prof.kernel_launches++;
+}
+
+void ensure_twiddles(pk_ctx* ctx, int log_n) {
+    PK_REQUIRE(log_n <= 28, PK_ERR_DEGREE_TOO_LARGE, "domain larger than 2^28 (Fr two-adicity)");
+    if (!ctx->domains) ctx->domains = new DomainCache();
+    DomainCache* dc = ctx->domains;
+    if (dc->tw_log >= log_n && dc->tw.p) return;
+    int lg = log_n < 12 ? 12 : log_n;
+    size_t count = (size_t(1) << (lg - 1)) + 1;
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));  // nobody may still be reading the old table
+    dc->tw.alloc(count);
+    dc->tw_log = lg;
+    tw_build_kernel<<<grid1d(count, 256), 256, 0, ctx->stream>>>(dc->tw.p, host_root_of_unity(lg), count);
+    ctx->prof.kernel_launches++;
+    PK_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------- the pass kernel
+struct NttPass {
+    const fr_t* src;
+    fr_t* dst;
+    const fr_t* tw;
+    const fr_t* pre;     // optional element-wise factor applied on load
+    const fr_t* post;    // optional element-wise factor applied on store
+    fr_t post_const;     // used when use_post_const
+    int use_post_const;
+    int L;               // log2 of the transform size
+    int bl;              // lowest varying index bit of this pass's tile
+    int k;               // stages in this pass
+    int c_log;           // log2 of contiguous columns per tile (c_log <= bl)
+    int tw_shift;        // tw_log - L
+    size_t src_stride, dst_stride, pre_stride;
+};
+
+__device__ __forceinline__ fr_t lds_fr(const uint4* s_lo, const uint4* s_hi, unsigned l) {
+    uint4 a = s_lo[l], b = s_hi[l];
+    fr_t r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void sts_fr(uint4* s_lo, uint4* s_hi, unsigned l, const fr_t& x) {
+    s_lo[l] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+    s_hi[l] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+}
+
+template <bool DIT> __global__ void __launch_bounds__(512) ntt_pass_kernel(NttPass p) {
+    extern __shared__ uint4 sm[];
+    const unsigned e_log = p.k + p.c_log;
+    const unsigned E = 1u << e_log, half = E >> 1;
+    uint4* s_lo = sm;
+    uint4* s_hi = sm + E;
+    const unsigned tid = threadIdx.x;
+    const unsigned cmask = (1u << p.c_log) - 1;
+    const fr_t* src = p.src + blockIdx.y * p.src_stride;
+    fr_t* dst = p.dst + blockIdx.y * p.dst_stride;
+    const fr_t* pre = p.pre ? p.pre + blockIdx.y * p.pre_stride : nullptr;
+
+    const unsigned lo_groups_log = p.bl - p.c_log;
+    const size_t blk = blockIdx.x;
+    const size_t hi = blk >> lo_groups_log;
+    const size_t lo0 = (blk & ((size_t(1) << lo_groups_log) - 1)) << p.c_log;
+    const size_t base = (hi << (p.bl + p.k)) | lo0;
+
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        unsigned l = tid + r * half;
+        if (l < E) {
+            size_t g = base | ((size_t)(l >> p.c_log) << p.bl) | (l & cmask);
+            fr_t x = ld_fp(src + g);
+            if (pre) x = x * ldg_fp(pre + g);
+            sts_fr(s_lo, s_hi, l, x);
+        }
+    }
+    __syncthreads();
+
+    const unsigned c = tid & cmask;
+    const unsigned q = tid >> p.c_log;
+    const size_t lo = lo0 | c;
+    const size_t half_n = size_t(1) << (p.L - 1);
+    for (int j = 0; j < p.k; ++j) {
+        const int bitpos = DIT ? j : p.k - 1 - j;
+        const unsigned lowmask = (1u << bitpos) - 1;
+        const unsigned t0 = ((q >> bitpos) << (bitpos + 1)) | (q & lowmask);
+        const unsigned l0 = (t0 << p.c_log) | c;
+        const unsigned l1 = l0 | (1u << (bitpos + p.c_log));
+        fr_t a = lds_fr(s_lo, s_hi, l0);
+        fr_t b = lds_fr(s_lo, s_hi, l1);
+        // exponent of the twiddle on the size-2^L domain
+        const size_t low = ((size_t)(t0 & lowmask) << p.bl) | lo;
+        if (!DIT) {
+            const int s = p.L - p.bl - p.k + j;  // global stage
+            const size_t e = low << s;
+            fr_t u = a + b;
+            fr_t d = a - b;
+            if (e != 0) d = d * ldg_fp(p.tw + (e << p.tw_shift));
+            sts_fr(s_lo, s_hi, l0, u);
+            sts_fr(s_lo, s_hi, l1, d);
+        } else {
+            const int s = p.bl + j;
+            const size_t e = low << (p.L - 1 - s);
+            // w^{-e} = -w^{n/2 - e}:  t = b * w^{n/2-e};  a' = a - t, b' = a + t
+            fr_t t = (e == 0) ? b.neg() : b * ldg_fp(p.tw + ((half_n - e) << p.tw_shift));
+            sts_fr(s_lo, s_hi, l0, a - t);
+            sts_fr(s_lo, s_hi, l1, a + t);
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        unsigned l = tid + r * half;
+        if (l < E) {
+            size_t g = base | ((size_t)(l >> p.c_log) << p.bl) | (l & cmask);
+            fr_t x = lds_fr(s_lo, s_hi, l);
+            if (p.post) x = x * ldg_fp(p.post + g);
+            else if (p.use_post_const) x = x * p.post_const;
+            st_fp(dst + g, x);
+        }
+    }
+}
+
+// pass plan: one contiguous pass of up to 10 stages + strided passes of up to 8 stages
+struct PassPlan { int n; int k[8]; int bl[8]; int c_log[8]; };
+static PassPlan plan_passes(int L, bool dit) {
+    PassPlan pl;
+    pl.n = 0;
+    int kc = L < 10 ? L : 10;
+    int rem = L - kc;
+    int ns = (rem + 7) / 8;
+    int ks[8];
+    for (int i = 0; i < ns; ++i) ks[i] = rem / ns + (i < rem % ns ? 1 : 0);
+    if (dit) {
+        // stages from bit 0 upward: contiguous first
+        pl.k[0] = kc; pl.bl[0] = 0; pl.c_log[0] = 0; pl.n = 1;
+        int s0 = kc;
+        for (int i = 0; i < ns; ++i) {
+            pl.k[pl.n] = ks[i]; pl.bl[pl.n] = s0;
+            int cl = 10 - ks[i]; if (cl > s0) cl = s0;
+            pl.c_log[pl.n] = cl;
+            s0 += ks[i]; pl.n++;
+        }
+    } else {
+        // stages from the top bit downward: strided passes first, contiguous last
+        int s0 = 0;
+        for (int i = 0; i < ns; ++i) {
+            int bl = L - s0 - ks[i];
+            pl.k[pl.n] = ks[i]; pl.bl[pl.n] = bl;
+            int cl = 10 - ks[i]; if (cl > bl) cl = bl;
+            pl.c_log[pl.n] = cl;
+            s0 += ks[i]; pl.n++;
+        }
+        pl.k[pl.n] = kc; pl.bl[pl.n] = 0; pl.c_log[pl.n] = 0; pl.n++;
+    }
+    return pl;
+}
+
+template <bool DIT>
+static void run_passes(pk_ctx* ctx, const fr_t* src, fr_t* dst, int L, const fr_t* pre, const fr_t* post, const fr_t* post_const,
+                       int batch, size_t src_stride, size_t dst_stride, size_t pre_stride) {
+    PK_REQUIRE(L >= 0 && L <= 28, PK_ERR_DEGREE_TOO_LARGE, "domain larger than 2^28");
+    size_t n = size_t(1) << L;
+    if (L == 0) {  // size-1 transform is the identity (all scale factors are 1)
+        for (int b = 0; b < batch; ++b)
+            PK_CUDA(cudaMemcpyAsync(dst + b * dst_stride, src + b * src_stride, sizeof(fr_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        return;
+    }
+    ensure_twiddles(ctx, L);
+    DomainCache* dc = ctx->domains;
+    PassPlan pl = plan_passes(L, DIT);
+    ScopedKernelTimer timer(ctx, 1, (uint64_t)n * batch * pl.n);
+    for (int i = 0; i < pl.n; ++i) {
+        NttPass p;
+        memset(&p, 0, sizeof(p));
+        bool first = i == 0, last = i == pl.n - 1;
+        p.src = first ? src : dst;
+        p.dst = dst;
+        p.src_stride = first ? src_stride : dst_stride;
+        p.dst_stride = dst_stride;
+        p.tw = dc->tw.p;
+        p.tw_shift = dc->tw_log - L;
+        p.pre = first ? pre : nullptr;
+        p.pre_stride = pre_stride;
+        p.post = last ? post : nullptr;
+        if (last && !post && post_const) { p.use_post_const = 1; p.post_const = *post_const; }
+        p.L = L; p.bl = pl.bl[i]; p.k = pl.k[i]; p.c_log = pl.c_log[i];
+        unsigned E = 1u << (p.k + p.c_log);
+        unsigned threads = E >> 1; if (threads < 1) threads = 1;
+        dim3 grid((unsigned)(n / E), batch);
+        size_t smem = (size_t)E * 32;
+        ntt_pass_kernel<DIT><<<grid, threads, smem, ctx->stream>>>(p);
+        ctx->prof.kernel_launches++;
+        ctx->prof.ntt_launches++;
+    }
+    PK_CUDA(cudaGetLastError());
+}
+
+void ntt_forward_bitrev(pk_ctx* ctx, const fr_t* src, fr_t* dst, int log_n, const fr_t* pre, int batch, size_t src_stride,
+                        size_t dst_stride, size_t pre_stride) {
+    run_passes<false>(ctx, src, dst, log_n, pre, nullptr, nullptr, batch, src_stride, dst_stride, pre_stride);
+}
+void ntt_inverse_from_bitrev(pk_ctx* ctx, const fr_t* src, fr_t* dst, int log_n, const fr_t* post) {
+    fr_t ninv = fr_t::from_u32(2).inverse().pow_u64(log_n);  // 1/n
+    run_passes<true>(ctx, src, dst, log_n, nullptr, post, post ? nullptr : &ninv, 1, 0, 0, 0);
+}
+
+CosetTables* get_coset_tables(pk_ctx* ctx, int log_n) {
+    PK_REQUIRE(log_n + 2 <= 28, PK_ERR_DEGREE_TOO_LARGE, "4n coset domain larger than 2^28");
+    ensure_twiddles(ctx, log_n + 2);
+    DomainCache* dc = ctx->domains;
+    auto it = dc->coset.find(log_n);
+    if (it != dc->coset.end()) return it->second;
+    CosetTables* ct = new CosetTables();
+    ct->log_n = log_n;
+    size_t n = size_t(1) << log_n;
+    ct->scale4.alloc(4 * n);
+    ct->iscale4n.alloc(4 * n);
+    ct->l0.alloc(4 * n);
+    fr_t g7, g7inv;
+    for (int i = 0; i < 8; ++i) { g7.v[i] = FrRoots::gen7(i); g7inv.v[i] = FrRoots::gen7_inv(i); }
+    fr_t w4 = host_root_of_unity(log_n + 2);
+    fr_t gs[4];
+    static const int brev2[4] = {0, 2, 1, 3};
+    for (int s = 0; s < 4; ++s) gs[s] = g7 * w4.pow_u64(brev2[s]);
+    coset_scale_build_kernel<<<dim3((unsigned)((n + 255) / 256), 4), 256, 0, ctx->stream>>>(ct->scale4.p, gs[0], gs[1], gs[2], gs[3], n);
+    fr_t inv4n = fr_t::from_u32(2).inverse().pow_u64(log_n + 2);
+    geom_build_kernel<<<grid1d(4 * n, 256), 256, 0, ctx->stream>>>(ct->iscale4n.p, g7inv, inv4n, 4 * n);
+    ctx->prof.kernel_launches += 2;
+    dc->coset[log_n] = ct;
+    // L_0(X) = (1/N) sum_j X^j : LDE of the all-(1/N) coefficient vector
+    DevBuf<fr_t> tmp(n);
+    fr_t ninv = fr_t::from_u32(2).inverse().pow_u64(log_n);
+    fill_kernel<<<grid1d(n, 256), 256, 0, ctx->stream>>>(tmp.p, ninv, n);
+    ctx->prof.kernel_launches++;
+    lde4_slots(ctx, tmp.p, ct->l0.p, log_n);
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ct;
+}
+
+void lde4_slots(pk_ctx* ctx, const fr_t* coeffs, fr_t* out4n, int log_n) {
+    CosetTables* ct = get_coset_tables(ctx, log_n);
+    size_t n = size_t(1) << log_n;
+    ntt_forward_bitrev(ctx, coeffs, out4n, log_n, ct->scale4.p, 4, 0, n, n);
+}
+void icoset4n_from_slots(pk_ctx* ctx, const fr_t* vals4n, fr_t* coeffs4n, int log_n) {
+    CosetTables* ct = get_coset_tables(ctx, log_n);
+    ntt_inverse_from_bitrev(ctx, vals4n, coeffs4n, log_n + 2, ct->iscale4n.p);
+}
+
+}  // namespace pk

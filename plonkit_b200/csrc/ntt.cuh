@@ -1,0 +1,44 @@
+// NTT layer interface (implemented in ntt.cu).
+#pragma once
+#include "common.cuh"
+
+namespace pk {
+
+// Per-size coset tables for the quotient domain 7*H_4N of a size-N circuit (N = 2^log_n).
+// "slot" s in 0..3 holds the coset 7*w4N^brev2(s) * H_N, each in bit-reversed order of j: together the 4N array is the
+// 4N-point bit-reversed order of the natural coset 7*H_4N (what bellman's bitreversed LDE produces).
+struct CosetTables {
+    int log_n = 0;
+    DevBuf<fr_t> scale4;     // [4][N]   (7 * w4N^brev2(s))^j            — pre-scale of the slot-s forward NTT
+    DevBuf<fr_t> iscale4n;   // [4N]     7^{-k} / (4N)                    — post-scale of the size-4N inverse NTT
+    DevBuf<fr_t> l0;         // [4][N]   L_0 on the coset, slot layout
+};
+
+struct DomainCache {
+    int tw_log = 0;          // twiddle table covers the domain of size 2^tw_log: tw[e] = w^e, e = 0 .. 2^(tw_log-1)
+    DevBuf<fr_t> tw;
+    std::map<int, CosetTables*> coset;
+    ~DomainCache() { for (auto& kv : coset) delete kv.second; }
+};
+
+fr_t host_root_of_unity(int log_n);                       // w_N, Montgomery form
+void ensure_twiddles(pk_ctx* ctx, int log_n);             // table for domains up to 2^log_n
+CosetTables* get_coset_tables(pk_ctx* ctx, int log_n);    // builds on first use (needs twiddles for log_n + 2)
+
+// forward NTT, natural order in -> bit-reversed order out (decimation in frequency).  `batch` independent transforms,
+// element strides between consecutive batches; pre (optional) multiplies element i of batch b by pre[b*pre_stride + i].
+void ntt_forward_bitrev(pk_ctx* ctx, const fr_t* src, fr_t* dst, int log_n, const fr_t* pre = nullptr, int batch = 1,
+                        size_t src_stride = 0, size_t dst_stride = 0, size_t pre_stride = 0);
+// inverse NTT, bit-reversed order in -> natural order out (decimation in time), result multiplied by post[i] if given,
+// else by 1/n.
+void ntt_inverse_from_bitrev(pk_ctx* ctx, const fr_t* src, fr_t* dst, int log_n, const fr_t* post = nullptr);
+void bitrev_permute(pk_ctx* ctx, const fr_t* src, fr_t* dst, int log_n);  // out of place, src != dst
+// coefficients (N, natural) -> evaluations on 7*H_4N in slot layout (4N)
+void lde4_slots(pk_ctx* ctx, const fr_t* coeffs, fr_t* out4n, int log_n);
+// evaluations on 7*H_4N in slot layout -> 4N coefficients (natural), in place allowed
+void icoset4n_from_slots(pk_ctx* ctx, const fr_t* vals4n, fr_t* coeffs4n, int log_n);
+// canonical <-> Montgomery on device arrays
+void fr_to_mont(pk_ctx* ctx, fr_t* data, size_t n);
+void fr_from_mont(pk_ctx* ctx, const fr_t* src, fr_t* dst, size_t n);
+
+}  // namespace pk

@@ -1,0 +1,56 @@
+// Polynomial glue kernels between the NTTs and the MSMs (implemented in poly.cu): SURVEY.md §8 rows a12-a14
+// (bellman's batch_inversion / calculate_shifted_grand_product, pointwise Polynomial ops, evaluate_at, divide_single).
+#pragma once
+#include "common.cuh"
+
+namespace pk {
+
+struct PolyScratch {
+    DevBuf<fr_t> scan_agg;     // block aggregates of the scans
+    DevBuf<fr_t> dot_partial;  // [16][DOT_BLOCKS]
+    DevBuf<fr_t> dot_out;      // [16]
+    DevBuf<uint32_t> flag;     // [1]
+};
+PolyScratch* poly_scratch(pk_ctx* ctx);
+
+void fr_fill(pk_ctx* ctx, fr_t* out, const fr_t& c, size_t n);
+void fr_mul_pointwise(pk_ctx* ctx, const fr_t* a, const fr_t* b, fr_t* out, size_t n);
+// out[j] = base^j
+void poly_powers(pk_ctx* ctx, fr_t* out, const fr_t& base, size_t n);
+// out[i] = sum_k coef[k] * in[k][i]  (nterms <= 12); out may alias an input
+void poly_lincomb(pk_ctx* ctx, fr_t* out, int nterms, const fr_t* const* in, const fr_t* coef, size_t n);
+// results[k] = sum_i polys[k][i] * pows[k][i]   (npoly <= 16), results on the host (synchronises the stream)
+void poly_dot_batch(pk_ctx* ctx, int npoly, const fr_t* const* polys, const fr_t* const* pows, size_t n, fr_t* results_host);
+// inclusive scan under * (mul = true) or + ; reverse = suffix scan.  in/out may alias.
+void poly_scan(pk_ctx* ctx, bool mul, bool reverse, const fr_t* in, fr_t* out, size_t n);
+// q(X) = (p(X) - p(z)) / (X - z) given zpow[j] = z^j and zinvpow[j] = z^-j ; tmp is an n-element scratch; q != p
+void poly_divide_linear(pk_ctx* ctx, const fr_t* p, const fr_t* zpow, const fr_t* zinvpow, fr_t* q, fr_t* tmp, size_t n);
+
+// ---- prover-specific kernels
+// vals_nat[c][row] = vars[idx[c][row]] ; vals_br[c][brev(row)] = same
+void wire_gather(pk_ctx* ctx, const fr_t* vars, const uint32_t* idx, fr_t* vals_nat, fr_t* vals_br, int log_n);
+// pi_br[brev(i)] = wire a value of row i for i < num_inputs (pi_br must be zeroed)
+void pi_scatter(pk_ctx* ctx, const fr_t* vals_nat_a, fr_t* pi_br, uint32_t num_inputs, int log_n);
+// gate identity on rows 0..n-2 (values, natural order); returns true if every row vanishes (synchronises)
+bool gate_check(pk_ctx* ctx, const fr_t* vals_nat, const fr_t* sel_vals, uint32_t num_inputs, int log_n);
+// sigma_vals[c][row] = k_{c'} * w^{row'} for target = sigma_target[c*n + row] = c'*n + row'
+void sigma_values(pk_ctx* ctx, const uint32_t* sigma_target, fr_t* sigma_vals, int log_n);
+void perm_num_den(pk_ctx* ctx, const fr_t* vals_nat, const fr_t* sigma_vals, const fr_t& beta, const fr_t& gamma, fr_t* num,
+                  fr_t* den, int log_n);
+// z_br[brev(0)] = 1 ; z_br[brev(j)] = pn[j-1] * sd[j] * tinv
+void z_finish(pk_ctx* ctx, const fr_t* pn, const fr_t* sd, const fr_t& tinv, fr_t* z_br, int log_n);
+
+struct QuotientArgs {
+    const fr_t* w[4];
+    const fr_t* z;
+    const fr_t* sel[7];
+    const fr_t* sig[4];
+    const fr_t* pi;
+    const fr_t* l0;
+    fr_t* out;
+    fr_t beta, gamma, alpha;
+    int log_n;
+};
+void quotient_slots(pk_ctx* ctx, const QuotientArgs& a);
+
+}  // namespace pk

@@ -1,0 +1,181 @@
+"""Host-side mirror of the reference's prover façade, src/plonk.rs, over the CUDA library.
+
+Same names, argument meaning and error behaviour as the Rust API (SURVEY.md §8b "Keep"):
+
+    gen_key_monomial_form(power)                                   src/plonk.rs:30-48
+    SetupForProver.prepare_setup_for_prover(circuit, key, lagrange) src/plonk.rs:97-119
+    SetupForProver.make_verification_key()                          src/plonk.rs:122-124
+    SetupForProver.validate_witness(circuit)                        src/plonk.rs:127-129
+    SetupForProver.prove(circuit, transcript)                       src/plonk.rs:132-176
+    SetupForProver.get_srs_lagrange_form_from_monomial_form()       src/plonk.rs:179-185
+    analyse(circuit)                                                src/plonk.rs:72-95
+
+`circuit` is a `CircomCircuit` (R1CS + witness, synthesised on the host exactly like the reference does) or an
+already synthesised `Assembly` (gate tables + variable values).  All arithmetic runs in the CUDA library; without it
+(or without a GPU) these calls raise — there is no CPU path.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import Context, SynthesisError
+from .bn254 import limbs_to_ints
+from .circuit import AUX_OFFSET, Assembly, CircomCircuit, analyse, is_satisfied, synthesize  # noqa: F401  (re-exported)
+from .reader import Crs, Proof, VerificationKey
+
+SETUP_MIN_POW2 = 10  # src/plonk.rs:26
+SETUP_MAX_POW2 = 26  # src/plonk.rs:27
+
+_default_ctx = {}
+
+
+def default_context(device=0) -> Context:
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+def gen_key_monomial_form(power: int, ctx: Context = None) -> Crs:
+    """Crs::crs_42(1 << power): [42^i] G (src/plonk.rs:30-48).  The G2 part (verify-side only) is left empty."""
+    if not (SETUP_MIN_POW2 <= power <= SETUP_MAX_POW2):
+        raise ValueError("setup power of two is not in the correct range")
+    ctx = ctx or default_context()
+    return Crs(ctx.srs_gen(1 << power, 42), b"", "monomial")
+
+
+def _as_assembly(circuit) -> Assembly:
+    if isinstance(circuit, Assembly):
+        return circuit
+    if isinstance(circuit, CircomCircuit):
+        return synthesize(circuit)
+    raise TypeError("circuit must be a CircomCircuit or an Assembly")
+
+
+class SetupForProver:
+    """src/plonk.rs:50-55: setup polynomials + SRS, resident on the device."""
+
+    def __init__(self):
+        raise TypeError("use SetupForProver.prepare_setup_for_prover")
+
+    @classmethod
+    def prepare_setup_for_prover(cls, circuit, key_monomial_form: Crs, key_lagrange_form: Crs = None, ctx: Context = None):
+        self = object.__new__(cls)
+        asm = _as_assembly(circuit)
+        size = asm.n.bit_length() - 1
+        setup_power_of_two = max(size, SETUP_MIN_POW2)
+        if not (SETUP_MIN_POW2 <= setup_power_of_two <= SETUP_MAX_POW2):
+            raise ValueError("setup power of two is not in the correct range")
+        if key_monomial_form.size < asm.n:
+            raise SynthesisError(2, "monomial SRS holds %d bases, the circuit needs %d" % (key_monomial_form.size, asm.n))
+        self.ctx = ctx or default_context()
+        self.key_monomial_form = key_monomial_form
+        self.key_lagrange_form = key_lagrange_form
+        self.n = asm.n
+        self.num_inputs = asm.num_inputs
+        self.nvars = asm.nvars
+        self._loaded_key_id = None
+        self._ensure_srs()
+        wire_idx = np.ascontiguousarray(asm.wire_idx, dtype=np.uint32)
+        selectors = np.ascontiguousarray(asm.selectors, dtype=np.uint64)
+        a = _lib.PkAssembly(asm.n, asm.num_inputs, asm.nvars, wire_idx.ctypes.data, selectors.ctypes.data)
+        h = ctypes.c_void_p()
+        self.ctx._check(self.ctx._lib.pk_setup_create(self.ctx._h, ctypes.byref(a), ctypes.byref(h)))
+        self._h = h
+        return self
+
+    def _ensure_srs(self):
+        # the context keeps one SRS resident; reload only if another key was loaded in between
+        tag = (id(self.key_monomial_form), self.n)
+        if getattr(self.ctx, "_srs_tag", None) != tag:
+            self.ctx.srs_load_g1(self.key_monomial_form.g1_bases[:self.n])
+            self.ctx._srs_tag = tag
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.ctx._lib.pk_setup_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def make_verification_key(self) -> VerificationKey:
+        self._ensure_srs()
+        out = np.zeros((11, 8), dtype=np.uint64)
+        self.ctx._check(self.ctx._lib.pk_setup_commitments(self.ctx._h, self._h, out.ctypes.data))
+        return VerificationKey(self.n - 1, self.num_inputs, out[:6].copy(), out[6:7].copy(), out[7:11].copy(), [5, 7, 10],
+                               self.key_monomial_form.g2_raw)
+
+    def validate_witness(self, circuit) -> None:
+        """is_satisfied_using_one_shot_check on the host tables (src/plonk.rs:127-129); raises on failure."""
+        if not is_satisfied(_as_assembly(circuit)):
+            raise SynthesisError(4, "witness does not satisfy the circuit")
+
+    def upload_witness(self, circuit_or_values):
+        vals = circuit_or_values
+        if not isinstance(vals, np.ndarray):
+            vals = _as_assembly(vals).var_values
+        if vals is None:
+            raise SynthesisError(1, "circuit has no witness")
+        vals = np.ascontiguousarray(vals, dtype=np.uint64).reshape(-1, 4)
+        self.ctx._check(self.ctx._lib.pk_witness_upload(self.ctx._h, self._h, vals.ctypes.data, vals.shape[0]))
+
+    def prove(self, circuit=None, transcript: str = "keccak") -> Proof:
+        """SetupForProver::prove.  circuit=None proves the witness uploaded with upload_witness (device-resident input)."""
+        if transcript == "rescue":
+            raise NotImplementedError("the rescue transcript has no in-tree fixture (SURVEY.md §0 item 5); use 'keccak'")
+        if transcript != "keccak":
+            raise NotImplementedError("invalid transcript. use 'keccak' or 'rescue'")
+        self._ensure_srs()
+        vals, nvars = None, 0
+        if circuit is not None:
+            asm = circuit if isinstance(circuit, np.ndarray) else _as_assembly(circuit)
+            arr = asm if isinstance(asm, np.ndarray) else asm.var_values
+            if arr is None:
+                raise SynthesisError(1, "circuit has no witness")
+            vals = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 4)
+            nvars = vals.shape[0]
+        pr = _lib.PkProof()
+        inputs = np.zeros((max(self.num_inputs, 1), 4), dtype=np.uint64)
+        self.ctx._check(self.ctx._lib.pk_prove(self.ctx._h, self._h, vals.ctypes.data if vals is not None else None, nvars,
+                                               ctypes.byref(pr), inputs.ctypes.data))
+        return _proof_from_struct(pr, inputs[:self.num_inputs])
+
+    def get_srs_lagrange_form_from_monomial_form(self) -> Crs:
+        self._ensure_srs()
+        size = self.n  # setup_polynomials.n.next_power_of_two()
+        pts = self.ctx.ec_intt_g1(size.bit_length() - 1)
+        return Crs(pts, self.key_monomial_form.g2_raw, "lagrange")
+
+
+def _arr(field, shape):
+    return np.array(list(field), dtype=np.uint64).reshape(shape)
+
+
+def _proof_from_struct(pr, inputs) -> Proof:
+    p = Proof(
+        n=pr.n, num_inputs=pr.num_inputs, input_values=limbs_to_ints(inputs) if len(inputs) else [],
+        wire_commitments=_arr(pr.wire_commitments, (4, 8)),
+        grand_product_commitment=_arr(pr.grand_product_commitment, (8,)),
+        quotient_poly_commitments=_arr(pr.quotient_poly_commitments, (4, 8)),
+        wire_values_at_z=limbs_to_ints(_arr(pr.wire_values_at_z, (4, 4))),
+        wire_values_at_z_omega=limbs_to_ints(_arr(pr.wire_values_at_z_omega, (1, 4))),
+        grand_product_at_z_omega=limbs_to_ints(_arr(pr.grand_product_at_z_omega, (1, 4)))[0],
+        quotient_polynomial_at_z=limbs_to_ints(_arr(pr.quotient_polynomial_at_z, (1, 4)))[0],
+        linearization_polynomial_at_z=limbs_to_ints(_arr(pr.linearization_polynomial_at_z, (1, 4)))[0],
+        permutation_polynomials_at_z=limbs_to_ints(_arr(pr.permutation_polynomials_at_z, (3, 4))),
+        opening_at_z_proof=_arr(pr.opening_at_z_proof, (8,)),
+        opening_at_z_omega_proof=_arr(pr.opening_at_z_omega_proof, (8,)),
+    )
+    p.challenges = limbs_to_ints(_arr(pr.challenges, (5, 4)))
+    return p
+
+
+def verify(vk: VerificationKey, proof: Proof, transcript: str = "keccak") -> bool:
+    """src/plonk.rs:189-210.  Verification needs the BN254 pairing (G2 / Fq12), which is outside this repo's scope
+    ("G2/pairing OUT OF SCOPE: verify only")."""
+    raise NotImplementedError("pairing-based verification is out of scope; tests/ verify proofs algebraically "
+                              "with the known SRS trapdoor instead")

@@ -1,0 +1,177 @@
+"""Synthetic PLONK-native circuits of the sizes BASELINE.json names.
+
+The reference's poseidon fixtures (r1cs / witness) do not exist in-tree and circom/snarkjs are absent, so the
+2^20-gate "poseidon" workload is generated directly as width-4 gate tables with the shape of circomlib's
+Poseidon(2) (t = 3, x^5 S-box = 3 multiplication gates, one addition gate per MDS row, 8 full + 57 partial rounds
+= 438 gates per permutation), chained until the requested number of gates is reached.  Round constants and the
+MDS matrix come from splitmix64 seeded with "plonkit" (circomlib's constants are not in the tree).  One public input.
+"""
+import numpy as np
+
+from .bn254 import R_MOD, ints_to_limbs
+from .circuit import Assembly
+
+SEED = 0x706C6F6E6B6974  # "plonkit"
+T, FULL_ROUNDS, PARTIAL_ROUNDS = 3, 8, 57
+
+
+class SplitMix64:
+    def __init__(self, seed):
+        self.s = seed & 0xFFFFFFFFFFFFFFFF
+
+    def next(self):
+        self.s = (self.s + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        z = self.s
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        return z ^ (z >> 31)
+
+    def field(self):
+        v = 0
+        for i in range(4):
+            v |= self.next() << (64 * i)
+        return v % R_MOD
+
+
+def random_field_elements(n, seed=SEED) -> np.ndarray:
+    """(n, 4) uint64 canonical limbs, vectorised splitmix64 (element i uses draws 4i..4i+3, reduced mod r)."""
+    idx = np.arange(1, 4 * n + 1, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + idx * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    limbs = z.reshape(n, 4).copy()
+    # reduce mod r: the top limb is masked to 253 bits first (value < 2^253 < r), which keeps this vectorised
+    limbs[:, 3] &= np.uint64((1 << 61) - 1)
+    return limbs
+
+
+def _poseidon_pattern():
+    """One permutation as (local wire ids, selector rows, evaluation program).
+    Local variable ids: -3,-2,-1 = incoming state; 0.. = variables allocated by this permutation."""
+    rng = SplitMix64(SEED)
+    rounds = FULL_ROUNDS + PARTIAL_ROUNDS
+    rc = [[rng.field() for _ in range(T)] for _ in range(rounds)]
+    mds = [[rng.field() for _ in range(T)] for _ in range(T)]
+    gates = []  # (a, b, c, d, [q_a,q_b,q_c,q_d,q_m,q_const,q_dnext], kind)
+    state = [-3, -2, -1]
+    nxt = 0
+    M1 = R_MOD - 1
+    for r in range(rounds):
+        full = r < FULL_ROUNDS // 2 or r >= FULL_ROUNDS // 2 + PARTIAL_ROUNDS
+        for i in range(T if full else 1):
+            x = state[i]
+            x2, x4, x5 = nxt, nxt + 1, nxt + 2
+            nxt += 3
+            gates.append((x, x, x2, None, [0, 0, M1, 0, 1, 0, 0], "mul"))
+            gates.append((x2, x2, x4, None, [0, 0, M1, 0, 1, 0, 0], "mul"))
+            gates.append((x4, x, x5, None, [0, 0, M1, 0, 1, 0, 0], "mul"))
+            state[i] = x5
+        new_state = []
+        for i in range(T):
+            d = nxt
+            nxt += 1
+            gates.append((state[0], state[1], state[2], d, [mds[i][0], mds[i][1], mds[i][2], M1, 0, rc[r][i], 0], "add"))
+            new_state.append(d)
+        state = new_state
+    return gates, nxt
+
+
+def poseidon_chain_assembly(log_n: int, with_witness: bool = True, inputs=(3, 4, 5)) -> Assembly:
+    """Poseidon-shaped circuit with exactly 2^log_n - 1 gates (domain size n = 2^log_n), 1 public input."""
+    n = 1 << log_n
+    n_gates = n - 1
+    pattern, vars_per_perm = _poseidon_pattern()
+    G = len(pattern)
+    assert vars_per_perm == G
+    body = n_gates - 1  # minus the public-input gate
+    perms = (body + G - 1) // G
+
+    # ---- tables, vectorised over permutations
+    loc = np.zeros((4, G), dtype=np.int64)
+    is_dummy = np.zeros((4, G), dtype=bool)
+    sel_rows = [[0] * G for _ in range(7)]
+    for g, (a, b, c, d, q, _) in enumerate(pattern):
+        for col, v in enumerate((a, b, c, d)):
+            if v is None:
+                is_dummy[col, g] = True
+            else:
+                loc[col, g] = v
+        for s in range(7):
+            sel_rows[s][g] = q[s]
+    sel_block = np.stack([ints_to_limbs(r) for r in sel_rows])  # (7, G, 4)
+    base = 4 + np.arange(perms, dtype=np.int64) * G                # first variable id of permutation p
+    idx_body = (base[None, :, None] + loc[:, None, :])             # (4, perms, G)
+    idx_body = np.where(is_dummy[:, None, :], 0, idx_body).reshape(4, perms * G)[:, :body]
+    wire_idx = np.zeros((4, n), dtype=np.uint32)
+    wire_idx[0, 0] = 1  # public-input gate: a = variable 1
+    wire_idx[:, 1:1 + body] = idx_body.astype(np.uint32)
+    selectors = np.zeros((7, n, 4), dtype=np.uint64)
+    selectors[0, 0] = ints_to_limbs([R_MOD - 1])[0]
+    selectors[:, 1:1 + body] = np.broadcast_to(sel_block[:, None, :, :], (7, perms, G, 4)).reshape(7, perms * G, 4)[:, :body]
+    # every gate allocates exactly one variable; gates past the truncation point (and their variables) do not exist
+    nvars = 4 + body
+
+    var_values = None
+    if with_witness:
+        vals = _evaluate_chain(pattern, perms, body, inputs)
+        var_values = ints_to_limbs(vals[:nvars])
+    return Assembly(n=n, num_inputs=1, wire_idx=wire_idx, selectors=selectors, var_values=var_values, nvars=nvars,
+                    num_gates=n_gates)
+
+
+def _evaluate_chain(pattern, perms, body, inputs):
+    G = len(pattern)
+    vals = [0] * (4 + perms * G)
+    vals[1], vals[2], vals[3] = [v % R_MOD for v in inputs]
+    p_mod = R_MOD
+    prog = []
+    for (a, b, c, d, q, kind) in pattern:
+        if kind == "mul":
+            prog.append((True, a, b, c, 0, 0, 0, 0))
+        else:
+            prog.append((False, a, b, c, d, q[0], q[1], (q[2], q[5])))
+    done = 0
+    for p in range(perms):
+        b0 = 4 + p * G
+        for (is_mul, a, b, c, d, qa, qb, rest) in prog:
+            if done == body:
+                return vals
+            if is_mul:
+                vals[b0 + c] = vals[b0 + a] * vals[b0 + b] % p_mod
+            else:
+                qc, k = rest
+                vals[b0 + d] = (qa * vals[b0 + a] + qb * vals[b0 + b] + qc * vals[b0 + c] + k) % p_mod
+            done += 1
+    return vals
+
+
+def random_gate_assembly(log_n: int, seed: int = SEED, reuse: float = 0.5) -> Assembly:
+    """BASELINE config 3 shape: 2^log_n - 1 gates, half multiplication gates c = a*b, half addition gates c = a + b + k;
+    every operand re-uses an earlier variable with probability `reuse` (non-trivial copy permutation).  1 public input."""
+    import random
+    rnd = random.Random(seed)
+    n = 1 << log_n
+    n_gates = n - 1
+    rows = []
+    vals = [0, rnd.randrange(R_MOD)]
+    rows.append((1, 0, 0, 0, [R_MOD - 1, 0, 0, 0, 0, 0, 0]))
+
+    def operand():
+        if len(vals) > 2 and rnd.random() < reuse:
+            return rnd.randrange(1, len(vals))
+        vals.append(rnd.randrange(R_MOD))
+        return len(vals) - 1
+    M1 = R_MOD - 1
+    while len(rows) < n_gates:
+        a, b = operand(), operand()
+        if rnd.random() < 0.5:
+            vals.append(vals[a] * vals[b] % R_MOD)
+            rows.append((a, b, len(vals) - 1, 0, [0, 0, M1, 0, 1, 0, 0]))
+        else:
+            k = rnd.randrange(R_MOD)
+            vals.append((vals[a] + vals[b] + k) % R_MOD)
+            rows.append((a, b, len(vals) - 1, 0, [1, 1, M1, 0, 0, k, 0]))
+    from .circuit import assembly_from_rows
+    return assembly_from_rows(rows, vals, 1)

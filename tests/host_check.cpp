@@ -1,0 +1,47 @@
+// Host build (g++) of the product's field / curve / transcript headers, for CPU-side checks of the exact
+// instruction sequences the device code runs (the carry-flag primitives are emulated on the host, see fp.cuh).
+#include "../plonkit_b200/csrc/ec.cuh"
+#include "../plonkit_b200/csrc/keccak_host.hpp"
+using namespace pk;
+
+template <class F> static F load_c(const uint64_t* s) { F x; memcpy(x.v, s, 32); return x.to_mont(); }
+template <class F> static void store_c(const F& x, uint64_t* d) { F c = x.from_mont(); memcpy(d, c.v, 32); }
+static g1_affine_t load_pt(const uint64_t* s) { g1_affine_t p; bool z = true; for (int i = 0; i < 8; ++i) if (s[i]) z = false;
+    if (z) return g1_affine_t::infinity(); p.x = load_c<fq_t>(s); p.y = load_c<fq_t>(s + 4); return p; }
+static void store_pt(const g1_affine_t& p, uint64_t* d) { if (p.is_inf()) { memset(d, 0, 64); return; } store_c(p.x, d); store_c(p.y, d + 4); }
+
+extern "C" {
+void hc_mont_mul(int which, const uint32_t* a, const uint32_t* b, uint32_t* o, int n) {
+    for (int i = 0; i < n; ++i) { if (which == 0) limbs::mont_mul<FrParams>(o + 8 * i, a + 8 * i, b + 8 * i); else limbs::mont_mul<FqParams>(o + 8 * i, a + 8 * i, b + 8 * i); }
+}
+void hc_fr_ops(const uint64_t* a, const uint64_t* b, uint64_t* add, uint64_t* sub, uint64_t* mul, uint64_t* inv, int n) {
+    for (int i = 0; i < n; ++i) {
+        fr_t x = load_c<fr_t>(a + 4 * i), y = load_c<fr_t>(b + 4 * i);
+        store_c(x + y, add + 4 * i); store_c(x - y, sub + 4 * i); store_c(x * y, mul + 4 * i); store_c(x.inverse(), inv + 4 * i);
+    }
+}
+// out[0] = p + q (mixed), out[1] = p + q (full), out[2] = 2p, out[3] = k * p (mul_small)
+void hc_g1_ops(const uint64_t* p, const uint64_t* q, uint32_t k, uint64_t* out) {
+    g1_affine_t P = load_pt(p), Q = load_pt(q);
+    g1_xyzz_t X = g1_xyzz_t::from_affine(P), Y = g1_xyzz_t::from_affine(Q);
+    // make the accumulator non-trivial (ZZ != 1) by going through 3P - 2P
+    g1_xyzz_t X3 = X.dbl().add(X);
+    g1_xyzz_t Xn = X3.add(X.dbl().neg());
+    store_pt(Xn.add_mixed(Q).to_affine(), out);
+    store_pt(Xn.add(Y.dbl().add(Y.neg())).to_affine(), out + 8);
+    store_pt(Xn.dbl().to_affine(), out + 16);
+    store_pt(Xn.mul_small(k).to_affine(), out + 24);
+}
+void hc_keccak(const uint8_t* d, uint64_t n, uint8_t* out) { Keccak256 h; h.update(d, n); h.finish(out); }
+// transcript: commit `n` 32-byte big-endian values, then draw `m` challenges (canonical LE limbs out)
+void hc_transcript(const uint8_t* vals, int n, int m, uint32_t* out) {
+    RollingKeccakTranscript t;
+    for (int i = 0; i < n; ++i) t.commit_be(vals + 32 * i);
+    for (int i = 0; i < m; ++i) t.challenge(out + 8 * i);
+}
+void hc_root(int log_n, uint64_t* out) {
+    fr_t g; for (int i = 0; i < 8; ++i) g.v[i] = FrRoots::root_2_28(i);
+    for (int i = 0; i < 28 - log_n; ++i) g = g.sqr();
+    store_c(g, out);
+}
+}

@@ -1,0 +1,160 @@
+"""GPU parity tests of the bellman primitives behind the C ABI (pk_ntt, pk_lde4, pk_msm_g1, pk_srs_gen,
+pk_ec_intt_g1) against the oracle on the same seeded inputs, plus the committed golden vectors.  Bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from plonkit_b200 import _lib, synth
+from plonkit_b200.bn254 import Q_MOD, R_MOD, ints_to_limbs, limbs_to_ints
+
+pytestmark = pytest.mark.gpu
+
+
+def bitrev(i, bits):
+    return int(format(i, "0%db" % bits)[::-1], 2) if bits else 0
+
+
+def test_field_multiplier_runs_and_reports_throughput(ctx):
+    for which in (0, 1):
+        g = ctx.bench_fieldmul(which)
+        assert g > 1.0, "field multiplier throughput %.2f Gmul/s is implausibly low" % g
+
+
+@pytest.mark.parametrize("log_n", [1, 2, 3, 5, 9, 10, 11, 13, 16])
+def test_ntt_forward_inverse_and_coset_match_oracle(ctx, orc, log_n):
+    x = synth.random_field_elements(1 << log_n, seed=100 + log_n)
+    for inverse in (False, True):
+        for coset in (False, True):
+            got = ctx.ntt(x, inverse=inverse, coset=coset)
+            assert (got == orc.ntt(x, inverse=inverse, coset=coset, threads=8)).all(), (log_n, inverse, coset)
+    # Montgomery-form interface: same transform on the in-memory representation
+    xm = ints_to_limbs([v * (1 << 256) % R_MOD for v in limbs_to_ints(x)])
+    ym = ctx.ntt(xm, fmt=_lib.FMT_MONTGOMERY)
+    assert limbs_to_ints(ym) == [v * (1 << 256) % R_MOD for v in limbs_to_ints(orc.ntt(x, threads=8))]
+
+
+def test_ntt_golden_vector_and_edge_inputs(ctx, orc):
+    x = synth.random_field_elements(1 << 10, seed=synth.SEED + 1)
+    assert (ctx.ntt(x) == np.load(os.path.join(GOLDEN, "ntt10_out.npy"))).all()
+    z = np.zeros((1 << 8, 4), dtype=np.uint64)
+    assert not ctx.ntt(z).any()
+    one = z.copy()
+    one[0] = ints_to_limbs([1])[0]
+    assert limbs_to_ints(ctx.ntt(one)) == [1] * 256                      # delta -> all ones
+    top = np.tile(ints_to_limbs([R_MOD - 1]), (256, 1))
+    assert (ctx.ntt(top) == orc.ntt(top)).all()                         # maximal elements
+    with pytest.raises(_lib.SynthesisError):
+        ctx.ntt(np.zeros((3, 4), dtype=np.uint64))                      # not a power of two
+
+
+def test_ntt_large_round_trip_and_linearity(ctx):
+    log_n = 20
+    x = synth.random_field_elements(1 << log_n, seed=1)
+    y = ctx.ntt(x)
+    assert (ctx.ntt(y, inverse=True) == x).all()
+    # linearity at full size: NTT(x + x2) == NTT(x) + NTT(x2), checked on a sample of positions
+    x2 = synth.random_field_elements(1 << log_n, seed=2)
+    idx = np.arange(0, 1 << log_n, 4099)
+    xs = limbs_to_ints(x[idx])
+    s = ints_to_limbs([(a + b) % R_MOD for a, b in zip(limbs_to_ints(x), limbs_to_ints(x2))]) if False else None
+    y2 = ctx.ntt(x2)
+    xi, x2i = limbs_to_ints(x[:4096]), limbs_to_ints(x2[:4096])
+    small_sum = ints_to_limbs([(a + b) % R_MOD for a, b in zip(xi, x2i)])
+    ys = ctx.ntt(small_sum)
+    ya, yb = limbs_to_ints(ctx.ntt(x[:4096])), limbs_to_ints(ctx.ntt(x2[:4096]))
+    assert limbs_to_ints(ys) == [(a + b) % R_MOD for a, b in zip(ya, yb)]
+    assert len(xs) == len(idx) and y2.shape == y.shape
+
+
+@pytest.mark.parametrize("log_n", [1, 3, 8, 12])
+def test_lde4_natural_and_bitreversed_orders(ctx, orc, log_n):
+    c = synth.random_field_elements(1 << log_n, seed=200 + log_n)
+    ref = orc.lde4(c, threads=8)
+    assert (ctx.lde4(c) == ref).all()
+    br = ctx.lde4(c, bitreversed=True)
+    perm = np.array([bitrev(i, log_n + 2) for i in range(4 << log_n)])
+    assert (br[perm] == ref).all()
+
+
+def _load(ctx, bases, window_bits=0):
+    ctx.srs_load_g1(bases, window_bits)
+
+
+def test_msm_matches_oracle_on_random_and_golden_inputs(ctx, orc, simple_key):
+    _load(ctx, simple_key.g1_bases)
+    x = synth.random_field_elements(1 << 10, seed=synth.SEED + 1)
+    assert (ctx.msm_g1(x) == np.load(os.path.join(GOLDEN, "msm10_out.npy"))).all()
+    for n in (1, 2, 31, 32, 33, 257, 1000):
+        s = synth.random_field_elements(n, seed=300 + n)
+        assert (ctx.msm_g1(s) == orc.msm(s, simple_key.g1_bases[:n], threads=8)).all(), n
+    # base_offset
+    s = synth.random_field_elements(100, seed=7)
+    assert (ctx.msm_g1(s, base_offset=37) == orc.msm(s, simple_key.g1_bases[37:137], threads=4)).all()
+    # Montgomery-form scalars
+    sm = ints_to_limbs([v * (1 << 256) % R_MOD for v in limbs_to_ints(s)])
+    assert (ctx.msm_g1(sm, fmt=_lib.FMT_MONTGOMERY) == orc.msm(s, simple_key.g1_bases[:100], threads=4)).all()
+
+
+@pytest.mark.parametrize("window_bits", [0, 4, 9, 13, 16])
+def test_msm_edge_cases(ctx, orc, simple_key, window_bits):
+    bases = simple_key.g1_bases[:256].copy()
+    bases[10] = bases[11]                        # repeated base
+    neg = bases[20].copy()
+    neg[4:] = ints_to_limbs([Q_MOD - limbs_to_ints(bases[20][4:])[0]])[0]
+    bases[21] = neg                              # P and -P
+    bases[30] = 0                                # a base at infinity
+    _load(ctx, bases, window_bits)
+    n = 256
+    cases = {}
+    cases["zeros"] = np.zeros((n, 4), dtype=np.uint64)
+    cases["ones"] = np.tile(ints_to_limbs([1]), (n, 1))
+    cases["max"] = np.tile(ints_to_limbs([R_MOD - 1]), (n, 1))
+    w = synth.random_field_elements(n, seed=11)
+    w[::3] = 0
+    w[1::5] = ints_to_limbs([1])[0]
+    w[2::7] = ints_to_limbs([2])[0]
+    cases["witness-like"] = w
+    c = np.zeros((n, 4), dtype=np.uint64)
+    c[20] = ints_to_limbs([12345])[0]
+    c[21] = ints_to_limbs([12345])[0]            # k*P + k*(-P) = infinity
+    cases["cancel"] = c
+    d = np.zeros((n, 4), dtype=np.uint64)
+    d[10] = ints_to_limbs([5])[0]
+    d[11] = ints_to_limbs([5])[0]                # P + P through the same bucket (doubling path)
+    cases["double"] = d
+    cases["pow2"] = ints_to_limbs([1 << (i % 254) for i in range(n)])
+    cases["half-window"] = ints_to_limbs([(1 << 15) + (1 << 31) * (i & 1) for i in range(n)])
+    for name, s in cases.items():
+        got = ctx.msm_g1(s)
+        assert (got == orc.msm(s, bases, threads=4)).all(), (name, window_bits)
+    assert not ctx.msm_g1(cases["cancel"]).any()                     # infinity -> (0, 0)
+    assert not ctx.msm_g1(np.zeros((0, 4), dtype=np.uint64)).any()   # empty input
+    with pytest.raises(_lib.SynthesisError) as e:
+        ctx.msm_g1(np.zeros((257, 4), dtype=np.uint64))              # longer than the SRS
+    assert e.value.code == 2
+
+
+def test_msm_2pow16_uniform_and_skewed(ctx, orc):
+    n = 1 << 16
+    bases = orc.srs_gen(n, 42, threads=8)
+    _load(ctx, bases)
+    s = synth.random_field_elements(n, seed=5)
+    assert (ctx.msm_g1(s) == orc.msm(s, bases, threads=8)).all()
+    s[: n // 2] = ints_to_limbs([1])[0]          # one giant bucket
+    s[n // 2: n // 2 + n // 4] = 0
+    assert (ctx.msm_g1(s) == orc.msm(s, bases, threads=8)).all()
+
+
+def test_srs_generator_matches_reference_key(ctx, simple_key):
+    """Crs::crs_42 (src/plonk.rs:41,47) == keys/setup/setup_2^10.key"""
+    assert (ctx.srs_gen(1024, 42) == simple_key.g1_bases).all()
+
+
+def test_ec_intt_matches_oracle(ctx, orc, simple_key):
+    """Crs::from_powers (src/plonk.rs:179-185)"""
+    _load(ctx, simple_key.g1_bases)
+    for log_n in (0, 1, 4, 7):
+        got = ctx.ec_intt_g1(log_n)
+        assert (got == orc.ec_intt(simple_key.g1_bases[: 1 << log_n], threads=8)).all(), log_n

@@ -1,0 +1,112 @@
+"""GPU parity tests of the prover path through the reference-shaped API (plonkit_b200.plonk) and the C ABI:
+golden proof.bin / vk.bin of the reference, oracle equality on synthetic circuits, error behaviour, and
+size-independent checks (trapdoor verification) at BASELINE.json's full size."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, SIMPLE, vk_commitments
+from plonkit_b200 import _lib, circuit, plonk, synth
+from plonkit_b200.bn254 import R_MOD, ints_to_limbs
+
+pytestmark = pytest.mark.gpu
+
+
+def test_prove_reproduces_reference_proof_bin(ctx, simple_circuit, simple_key):
+    """src/tests.rs:48-73 (test_prove) through the CUDA path"""
+    setup = plonk.SetupForProver.prepare_setup_for_prover(simple_circuit, simple_key, None, ctx=ctx)
+    setup.validate_witness(simple_circuit)
+    proof = setup.prove(simple_circuit, "keccak")
+    assert proof.to_bytes() == open(os.path.join(SIMPLE, "proof.bin"), "rb").read()
+    assert proof.challenges[0] == 0x0f72cf563829c88d02442b32aa5bc8b0aff226697faa846756e813710804a058  # beta
+    # proving twice gives the same bytes (no blinding) and the resident-witness path agrees
+    setup.upload_witness(simple_circuit)
+    assert setup.prove(None).to_bytes() == proof.to_bytes()
+
+
+def test_verification_key_reproduces_reference_vk_bin(ctx, simple_circuit, simple_key):
+    """src/tests.rs:30-46 (test_export_verification_key) through the CUDA path"""
+    c = circuit.CircomCircuit(simple_circuit.r1cs, None)
+    setup = plonk.SetupForProver.prepare_setup_for_prover(c, simple_key, None, ctx=ctx)
+    assert setup.make_verification_key().to_bytes() == open(os.path.join(SIMPLE, "vk.bin"), "rb").read()
+
+
+def test_lagrange_srs_matches_oracle(ctx, orc, simple_circuit, simple_key):
+    """src/tests.rs:66 calls get_srs_lagrange_form_from_monomial_form and discards it; here it is checked"""
+    setup = plonk.SetupForProver.prepare_setup_for_prover(simple_circuit, simple_key, None, ctx=ctx)
+    crs = setup.get_srs_lagrange_form_from_monomial_form()
+    assert crs.form == "lagrange" and crs.size == 8
+    assert (crs.g1_bases == orc.ec_intt(simple_key.g1_bases[:8])).all()
+
+
+def test_poseidon_shaped_golden_fixture(ctx, simple_key):
+    asm = synth.poseidon_chain_assembly(9)
+    setup = plonk.SetupForProver.prepare_setup_for_prover(asm, simple_key, None, ctx=ctx)
+    assert setup.prove(asm).to_bytes() == open(os.path.join(GOLDEN, "poseidon9_proof.bin"), "rb").read()
+    vk = setup.make_verification_key()
+    assert (vk_commitments(vk) == np.load(os.path.join(GOLDEN, "poseidon9_vk_commitments.npy"))).all()
+
+
+@pytest.mark.parametrize("kind,log_n", [("poseidon", 4), ("poseidon", 10), ("poseidon", 12), ("random", 6), ("random", 11),
+                                        ("poseidon", 14)])
+def test_proofs_equal_oracle_on_synthetic_circuits(ctx, orc, kind, log_n):
+    asm = synth.poseidon_chain_assembly(log_n) if kind == "poseidon" else synth.random_gate_assembly(log_n, seed=log_n)
+    srs = orc.srs_gen(asm.n, 42, threads=8)
+    from plonkit_b200.reader import Crs
+    key = Crs(srs, b"", "monomial")
+    setup = plonk.SetupForProver.prepare_setup_for_prover(asm, key, None, ctx=ctx)
+    proof = setup.prove(asm)
+    ref = orc.prove(asm.n, asm.num_inputs, asm.wire_idx, asm.var_values, asm.selectors, srs, threads=8)
+    assert proof.to_bytes() == ref
+    com = orc.setup_commitments(asm.n, asm.num_inputs, asm.wire_idx, asm.selectors, srs, nvars=asm.nvars, threads=8)
+    assert (vk_commitments(setup.make_verification_key()) == com).all()
+    assert orc.verify_trapdoor(proof.to_bytes(), com, 42)
+
+
+def test_error_behaviour_mirrors_reference(ctx, orc, simple_circuit, simple_key):
+    setup = plonk.SetupForProver.prepare_setup_for_prover(simple_circuit, simple_key, None, ctx=ctx)
+    # wrong witness: the reference panics in is_satisfied_using_one_shot_check ("must satisfy", src/plonk.rs:137)
+    bad = circuit.CircomCircuit(simple_circuit.r1cs, [1, 36, 3, 9])
+    with pytest.raises(_lib.SynthesisError) as e:
+        setup.prove(bad)
+    assert e.value.code == 4
+    with pytest.raises(_lib.SynthesisError):
+        setup.validate_witness(bad)
+    # witness of the wrong length -> AssignmentMissing
+    with pytest.raises(_lib.SynthesisError) as e:
+        setup.prove(np.zeros((3, 4), dtype=np.uint64))
+    assert e.value.code == 1
+    # transcript names (src/plonk.rs:147-173)
+    with pytest.raises(NotImplementedError):
+        setup.prove(simple_circuit, "blake")
+    # SRS smaller than the circuit
+    from plonkit_b200.reader import Crs
+    asm = synth.poseidon_chain_assembly(11)
+    with pytest.raises(_lib.SynthesisError) as e:
+        plonk.SetupForProver.prepare_setup_for_prover(asm, Crs(simple_key.g1_bases, b""), None, ctx=ctx)
+    assert e.value.code == 2
+
+
+def test_full_size_2pow20_poseidon_proof_verifies(ctx, orc):
+    """BASELINE.json configs[1] size.  The oracle prover would need minutes here, so parity is checked through
+    size-independent properties: the proof verifies against the device-made verification key with the trapdoor
+    verifier (restated contrib/template.sol, pinned by the reference's golden proof), it is deterministic, and a
+    tampered witness is rejected."""
+    log_n = 20
+    asm = synth.poseidon_chain_assembly(log_n)
+    srs = ctx.srs_gen(1 << log_n, 42)
+    assert (srs[:1024] == orc.srs_gen(1024, 42, threads=8)).all()
+    from plonkit_b200.reader import Crs
+    setup = plonk.SetupForProver.prepare_setup_for_prover(asm, Crs(srs, b""), None, ctx=ctx)
+    proof = setup.prove(asm)
+    com = vk_commitments(setup.make_verification_key())
+    assert orc.verify_trapdoor(proof.to_bytes(), com, 42)
+    assert setup.prove(None).to_bytes() == proof.to_bytes()
+    # commitment spot check in the exponent: C_a = a(tau) G with the oracle's MSM on the same scalars is too slow at
+    # this size; instead check one opening identity already covered by the verifier and the public input echo
+    assert proof.input_values == [3]
+    vals = asm.var_values.copy()
+    vals[1000] = ints_to_limbs([(int(vals[1000][0]) + 1) % R_MOD])[0]
+    with pytest.raises(_lib.SynthesisError):
+        setup.prove(vals)

@@ -1,0 +1,235 @@
+"""CPU tests of the product's host side: file formats, circuit synthesis, the C-ABI library's exports, loud failure
+without a GPU, and the host build of the device arithmetic headers (same carry-chain sequences as the kernels)."""
+import ctypes
+import io
+import os
+import re
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, SIMPLE
+from plonkit_b200 import _lib, circuit, plonk, reader, synth
+from plonkit_b200.bn254 import Q_MOD, R_MOD, ints_to_limbs, limbs_to_ints, root_of_unity
+
+
+# ---------------------------------------------------------------- C ABI surface
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()  # needs no GPU
+    hdr = open(os.path.join(ROOT, "include", "plonkit_b200.h")).read()
+    declared = set(re.findall(r"\b(pk_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no prototypes found"
+    assert declared == set(_lib.EXPORTS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_constants_in_library_match_appendix_c():
+    c = _lib.constants()
+    vals = limbs_to_ints(c.reshape(6, 4))
+    assert vals[0] == (1 << 256) % R_MOD and vals[1] == pow(1 << 256, 2, R_MOD)
+    assert vals[3] == (1 << 256) % Q_MOD and vals[4] == pow(1 << 256, 2, Q_MOD)
+    assert int(c[8]) == 0xefffffff and int(c[20]) == 0xe4866389
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="a GPU is present")
+def test_no_gpu_means_loud_failure_not_a_fallback():
+    with pytest.raises(_lib.SynthesisError) as e:
+        _lib.Context(0)
+    assert e.value.code == 5
+    with pytest.raises(_lib.SynthesisError):
+        plonk.gen_key_monomial_form(10)
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "plonkit_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in src.lower() or f == "__init__.py", f
+
+
+# ---------------------------------------------------------------- formats
+def test_key_proof_vk_round_trip_reference_files(simple_key):
+    raw = open(os.path.join(SIMPLE, "setup_2^10.key"), "rb").read()
+    b = io.BytesIO()
+    simple_key.write(b)
+    assert b.getvalue() == raw
+    assert simple_key.size == 1024 and len(simple_key.g2_raw) == 256
+    praw = open(os.path.join(SIMPLE, "proof.bin"), "rb").read()
+    p = reader.load_proof(os.path.join(SIMPLE, "proof.bin"))
+    assert p.to_bytes() == praw and p.n == 7 and p.input_values == [35]
+    assert not p.wire_commitments[3].any()  # d wire is identically zero -> point at infinity (0x40 encoding)
+    vraw = open(os.path.join(SIMPLE, "vk.bin"), "rb").read()
+    vk = reader.load_verification_key(os.path.join(SIMPLE, "vk.bin"))
+    assert vk.to_bytes() == vraw and vk.non_residues == [5, 7, 10]
+
+
+def _wtns(vals, version=2, prime=None):
+    prime = prime or bytes.fromhex("010000f093f5e1439170b97948e833285d588181b64550b829a031e1724e6430")
+    body = b"".join(v.to_bytes(32, "little") for v in vals)
+    return (b"wtns" + struct.pack("<II", version, 2) + struct.pack("<IQ", 1, 40) + struct.pack("<I", 32) + prime +
+            struct.pack("<I", len(vals)) + struct.pack("<IQ", 2, len(body)) + body)
+
+
+def test_wtns_parser_and_its_error_paths():
+    """src/reader.rs:124-175"""
+    assert reader.load_witness_from_array(_wtns([1, 35, 3, 9])) == [1, 35, 3, 9]
+    assert reader.load_witness_from_array(_wtns([])) == []
+    for bad, msg in ((b"xtns" + _wtns([1])[4:], "invalid file header"), (_wtns([1], version=3), "unsupported file version"),
+                     (_wtns([1], prime=b"\x02" + b"\x00" * 31), "invalid curve prime")):
+        with pytest.raises(ValueError, match=msg):
+            reader.load_witness_from_array(bad)
+    with pytest.raises(ValueError):
+        reader.load_witness_from_array(_wtns([R_MOD]))
+
+
+def _r1cs_bin(n_wires, n_pub_out, n_pub_in, n_prv_in, constraints, field_size=32):
+    prime = bytes.fromhex("010000f093f5e1439170b97948e833285d588181b64550b829a031e1724e6430")
+    header = struct.pack("<I", field_size) + prime + struct.pack("<IIIIQI", n_wires, n_pub_out, n_pub_in, n_prv_in, n_wires, len(constraints))
+    def vec(lc):
+        return struct.pack("<I", len(lc)) + b"".join(struct.pack("<I", w) + v.to_bytes(32, "little") for w, v in lc)
+    cons = b"".join(vec(a) + vec(b) + vec(c) for a, b, c in constraints)
+    wmap = b"".join(struct.pack("<Q", i) for i in range(n_wires))
+    out = b"r1cs" + struct.pack("<II", 1, 3)
+    for t, body in ((2, cons), (1, header), (3, wmap)):  # sections in arbitrary order, as the format allows
+        out += struct.pack("<IQ", t, len(body)) + body
+    return out
+
+
+def test_r1cs_binary_parser_matches_json_loader(simple_circuit):
+    """src/r1cs_file.rs:100-154, src/reader.rs:227-241"""
+    cons = simple_circuit.r1cs.constraints
+    r1cs, wmap = reader.load_r1cs_from_bin(_r1cs_bin(4, 0, 1, 1, cons))
+    assert (r1cs.num_inputs, r1cs.num_aux, r1cs.num_variables) == (2, 2, 4)
+    assert wmap == [0, 1, 2, 3]
+    def norm(c):
+        return [sorted(lc) for lc in c]
+    assert [norm(c) for c in r1cs.constraints] == [norm(c) for c in cons]
+    with pytest.raises(ValueError, match="Invalid magic number"):
+        reader.load_r1cs_from_bin(b"xxxx" + b"\0" * 64)
+    bad = bytearray(_r1cs_bin(4, 0, 1, 1, cons))
+    with pytest.raises(ValueError):
+        reader.load_r1cs_from_bin(bytes(bad[:8]) + struct.pack("<I", 3) + bytes(bad[12:]).replace(struct.pack("<IQ", 1, 64), struct.pack("<IQ", 1, 63), 1))
+
+
+# ---------------------------------------------------------------- circuit synthesis
+def test_simple_circuit_gate_table_is_the_pinned_one(simple_circuit):
+    """SURVEY App. A.2 table, derived from the golden vk/proof"""
+    asm = circuit.synthesize(simple_circuit)
+    assert asm.wire_idx[:, :4].T.tolist() == [[1, 0, 0, 0], [2, 2, 3, 0], [1, 2, 4, 0], [3, 2, 4, 0]]
+    vals = limbs_to_ints(asm.var_values)
+    assert vals == [0, 35, 3, 9, R_MOD - 27]
+    assert circuit.is_satisfied(asm)
+    assert circuit.transpile_with_gates_count(simple_circuit) == (3, 2)
+    assert simple_circuit.get_public_inputs() == [35]
+    bad = circuit.CircomCircuit(simple_circuit.r1cs, [1, 36, 3, 9])
+    assert not circuit.is_satisfied(circuit.synthesize(bad))
+
+
+def test_unpinned_r1cs_shapes_are_refused():
+    r = circuit.R1CS(2, 4, 6, [([(2, 1), (3, 1)], [(2, 1)], [(4, 1)])])  # A side with two variables
+    with pytest.raises(circuit.UnpinnedTranspilation):
+        circuit.synthesize(circuit.CircomCircuit(r, [1, 1, 1, 1, 2, 0]))
+    r = circuit.R1CS(2, 4, 6, [([(2, 1)], [(3, 1)], [(1, 1), (4, 1), (5, 1)])])  # C side with three variables
+    with pytest.raises(circuit.UnpinnedTranspilation):
+        circuit.synthesize(circuit.CircomCircuit(r, [1, 1, 1, 1, 2, 0]))
+    # 0 * LC = 0 is skipped, not transpiled (src/circom_circuit.rs:122-123)
+    r = circuit.R1CS(2, 2, 4, [([], [(2, 1)], [])])
+    assert circuit.synthesize(circuit.CircomCircuit(r, [1, 5, 6, 7])).num_gates == 1
+
+
+def test_synthetic_circuits_are_satisfied_and_sized():
+    for log_n in (6, 9, 11):
+        a = synth.poseidon_chain_assembly(log_n)
+        assert a.n == 1 << log_n and a.num_gates == a.n - 1 and a.num_inputs == 1
+        assert int(a.wire_idx.max()) == a.nvars - 1
+        assert circuit.is_satisfied(a)
+    b = synth.random_gate_assembly(8)
+    assert b.n == 256 and circuit.is_satisfied(b)
+    x = synth.random_field_elements(100)
+    assert all(v < R_MOD for v in limbs_to_ints(x)) and len(set(limbs_to_ints(x))) == 100
+
+
+def test_gen_key_range_check_mirrors_reference():
+    """src/plonk.rs:31-34"""
+    for power in (9, 27):
+        with pytest.raises(ValueError, match="setup power of two is not in the correct range"):
+            plonk.gen_key_monomial_form(power)
+
+
+# ---------------------------------------------------------------- host build of the device arithmetic
+@pytest.fixture(scope="module")
+def hc(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("hc") / "host_check.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", os.path.join(ROOT, "tests", "host_check.cpp"), "-o", so])
+    return ctypes.CDLL(so)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def test_montgomery_multiplier_sequence(hc):
+    rng = np.random.default_rng(7)
+    for which, p in ((0, R_MOD), (1, Q_MOD)):
+        edge = [0, 1, 2, p - 1, p - 2, 1 << 253, (1 << 256) % p, (1 << 32) - 1, (((1 << 32) - 1) << 224) % p]
+        a = edge * len(edge) + [int.from_bytes(rng.bytes(32), "little") % p for _ in range(3000)]
+        b = [e for e in edge for _ in edge] + [int.from_bytes(rng.bytes(32), "little") % p for _ in range(3000)]
+        A, B = ints_to_limbs(a).view(np.uint32), ints_to_limbs(b).view(np.uint32)
+        out = np.zeros_like(A)
+        hc.hc_mont_mul(which, _p(A), _p(B), _p(out), len(a))
+        rinv = pow(1 << 256, -1, p)
+        assert limbs_to_ints(out.view(np.uint64)) == [x * y * rinv % p for x, y in zip(a, b)]
+
+
+def test_field_ops_and_root_of_unity(hc):
+    rng = np.random.default_rng(8)
+    a = [int.from_bytes(rng.bytes(32), "little") % R_MOD for _ in range(40)] + [0, R_MOD - 1, 1]
+    b = [int.from_bytes(rng.bytes(32), "little") % R_MOD for _ in range(40)] + [R_MOD - 1, R_MOD - 1, 0]
+    A, B = ints_to_limbs(a), ints_to_limbs(b)
+    outs = [np.zeros_like(A) for _ in range(4)]
+    hc.hc_fr_ops(_p(A), _p(B), *[_p(o) for o in outs], len(a))
+    assert limbs_to_ints(outs[0]) == [(x + y) % R_MOD for x, y in zip(a, b)]
+    assert limbs_to_ints(outs[1]) == [(x - y) % R_MOD for x, y in zip(a, b)]
+    assert limbs_to_ints(outs[2]) == [x * y % R_MOD for x, y in zip(a, b)]
+    assert limbs_to_ints(outs[3]) == [pow(x, -1, R_MOD) if x else 0 for x in a]
+    for log_n in (1, 3, 20, 28):
+        out = np.zeros(4, dtype=np.uint64)
+        hc.hc_root(log_n, _p(out))
+        assert limbs_to_ints(out)[0] == root_of_unity(log_n)
+
+
+def test_xyzz_formulas_against_oracle_group_law(hc, orc, simple_key):
+    g = simple_key.g1_bases
+    inf = np.zeros(8, dtype=np.uint64)
+    neg5 = g[5].copy()
+    neg5[4:] = ints_to_limbs([Q_MOD - limbs_to_ints(g[5][4:])[0]])[0]
+    cases = [(g[3], g[7]), (g[5], g[5]), (g[5], neg5), (g[5], inf), (inf, g[9]), (inf, inf)]
+    for p, q in cases:
+        out = np.zeros((4, 8), dtype=np.uint64)
+        hc.hc_g1_ops(_p(np.ascontiguousarray(p)), _p(np.ascontiguousarray(q)), 11, _p(out))
+        assert (out[0] == orc.g1_add(p, q)).all()
+        assert (out[1] == orc.g1_add(p, q)).all()
+        assert (out[2] == orc.g1_add(p, p)).all()
+        assert (out[3] == orc.g1_mul(p, 11)).all()
+
+
+def test_host_keccak_and_transcript_match_oracle(hc, orc):
+    for msg in (b"", b"abc", b"a" * 135, b"a" * 136, b"a" * 137, bytes(range(200)) * 3):
+        out = ctypes.create_string_buffer(32)
+        hc.hc_keccak(msg, len(msg), out)
+        assert out.raw == orc.keccak256(msg)
+    # transcript of the golden proof's first round gives the pinned beta
+    p = reader.load_proof(os.path.join(SIMPLE, "proof.bin"))
+    vals = reader.limbs_to_be_bytes(ints_to_limbs(p.input_values)) + reader.g1_to_bytes(p.wire_commitments)
+    vals = bytearray(vals)
+    vals[32 + 64 * 3] = 0  # the infinity flag byte is absorbed as zero
+    ch = np.zeros((2, 8), dtype=np.uint32)
+    hc.hc_transcript(bytes(vals), 1 + 8, 2, _p(ch))
+    got = limbs_to_ints(ch.view(np.uint64))
+    assert got[0] == 0x0f72cf563829c88d02442b32aa5bc8b0aff226697faa846756e813710804a058
+    assert got[1] == 0x19f776d072bc5715a7fb2a727344f31eda1aa1b214c0b8b7f0bf9a8fed192264
