@@ -1,0 +1,287 @@
+#!/usr/bin/env python3
+"""Benchmark of the prove path (BASELINE.json metric: proofs/sec on a 2^20-gate poseidon-shaped circuit).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port), host cores
+
+A step = one SetupForProver::prove over one synthetic witness.  `value` is measured with the witness already
+resident in HBM; `e2e` goes through the public API with the witness in pinned host memory (H2D copy, proof D2H
+inside the timed region).  Timing is by CUDA events on the library's stream, max over ranks.  One JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "proofs/sec (2^20-gate poseidon)"
+UNIT = "proofs/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 8 and f[0] == str(self.device):
+                self.rows.append(f)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        reasons = []
+        for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6), ("sw_power_cap", 7)):
+            if any(r[col].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        mx = float(self.rows[0][2]) if self.rows else None
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    td = None
+    if world > 1:
+        import torch
+        import torch.distributed as td_
+        torch.cuda.set_device(local)
+        td_.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+        td = td_
+    return world, rank, local, td
+
+
+def max_over_ranks(td, local, x):
+    if td is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64, device="cuda:%d" % local)
+    td.all_reduce(t, op=td.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(td, local):
+    if td is not None:
+        import torch
+        td.barrier(device_ids=[local])
+        torch.cuda.synchronize(local)
+
+
+def cpu_sample_log_n(cores, log_n):
+    if cores >= 64:
+        return log_n
+    if cores >= 16:
+        return min(log_n, 18)
+    return min(log_n, 16)
+
+
+def run_cpu_prove(log_n_s, threads, repeats, warm):
+    """Times the oracle's CPU prover (restated bellman algorithms) on a poseidon-shaped circuit of 2^log_n_s gates."""
+    from oracle import oracle as orc
+    from plonkit_b200 import synth
+    orc.build()
+    asm = synth.poseidon_chain_assembly(log_n_s)
+    srs = orc.srs_gen(asm.n, 42, threads=threads)
+    times = []
+    for i in range(warm + repeats):
+        t0 = time.perf_counter()
+        orc.prove(asm.n, asm.num_inputs, asm.wire_idx, asm.var_values, asm.selectors, srs, threads=threads)
+        wall = time.perf_counter() - t0
+        setup_s, prove_s = orc.last_timings()
+        if i >= warm:
+            times.append((prove_s, wall))
+    return times
+
+
+def bench_reference(args):
+    world, rank, local, td = 1, int(os.environ.get("RANK", "0")), 0, None
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    ls = cpu_sample_log_n(cores, args.log_n)
+    times = run_cpu_prove(ls, cores, args.steps, args.warmup)
+    scale = float(1 << (args.log_n - ls))
+    per_step = sum(t[0] for t in times) / len(times) * scale
+    value = 1.0 / per_step
+    sample = ("one full SetupForProver::prove (setup polynomials excluded, 11 LDE precomputations included as in the "
+              "reference) of the oracle port on a 2^%d-gate poseidon-shaped circuit, %d threads" % (ls, cores))
+    if ls != args.log_n:
+        sample += "; time scaled x%d (linear in gates) to 2^%d" % (int(scale), args.log_n)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64 (4x64-bit Montgomery limbs)", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "restated CPU baseline (bellman's algorithms in C++; the Rust reference cannot be built in this image)",
+    }
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+def workload_config(args, world):
+    return {
+        "workload": "BASELINE configs[1]: 2^%d SRS ([42^i]G), poseidon-shaped circuit with 2^%d-1 gates (1 public input), "
+                    "keccak transcript, single-B200 prove with NTT+MSM on device" % (args.log_n, args.log_n),
+        "log_n": args.log_n,
+        "parallelism": "1 GPU" if world == 1 else "%d independent provers (one per GPU, no data-path collective)" % world,
+        "l2": "per-proof working set ~3 GB >> 126 MB L2: no flush needed between steps",
+    }
+
+
+def bench_ours(args):
+    world, rank, local, td = dist_setup(args.gpus)
+    from plonkit_b200 import _lib, plonk, reader, synth
+    import torch
+    n = 1 << args.log_n
+    ctx = _lib.Context(local)
+    t0 = time.time()
+    asm = synth.poseidon_chain_assembly(args.log_n, inputs=(3 + rank, 4, 5))
+    srs = ctx.srs_gen(n, 42)
+    setup = plonk.SetupForProver.prepare_setup_for_prover(asm, reader.Crs(srs, b""), None, ctx=ctx)
+    prep_s = time.time() - t0
+    # witness in pinned host memory (what a caller of the public API hands over)
+    wit = torch.from_numpy(asm.var_values).pin_memory()
+    wit_np = wit.numpy()
+    h2d_bytes = int(wit_np.nbytes)
+    d2h_bytes = 1144 - 16  # the proof: 9 G1 points + 16 field elements (+ challenges are not copied)
+
+    for _ in range(args.warmup):
+        proof = setup.prove(wit_np)
+    ref_bytes = proof.to_bytes() if args.warmup else None
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- timed region 1: witness resident in HBM
+    setup.upload_witness(wit_np)
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    barrier(td, local)
+    ctx.timer_begin()
+    for _ in range(args.steps):
+        proof = setup.prove(None)
+    ms_dev = ctx.timer_end()
+    barrier(td, local)
+    prof = ctx.profile()
+    ctx.profile_enable(False)
+    ms_dev = max_over_ranks(td, local, ms_dev)
+    # ---- timed region 2: end to end through the public API, host buffers
+    barrier(td, local)
+    ctx.timer_begin()
+    for _ in range(args.steps):
+        proof = setup.prove(wit_np)
+        pbytes = proof.to_bytes()
+    ms_e2e = ctx.timer_end()
+    barrier(td, local)
+    ms_e2e = max_over_ranks(td, local, ms_e2e)
+    clocks = sampler.stop() if rank == 0 else None
+    if ref_bytes is not None:
+        assert pbytes == ref_bytes, "proof bytes changed between runs"
+
+    if rank != 0:
+        return 0
+    value = world * args.steps / (ms_dev * 1e-3)
+    e2e = world * args.steps / (ms_e2e * 1e-3)
+    peak, peak_src = peaks()
+    launches = prof["msm_accum_launches"]
+    accum_ms = prof["msm_accum_ms"] / max(launches, 1)
+    alg_bytes = 96.0 * n  # 32 B scalar + 64 B base per pair, N pairs per launch
+    achieved = alg_bytes / (accum_ms * 1e-3) / 1e9 if launches else 0.0
+    traffic = None
+    summ = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    if os.path.exists(summ):
+        try:
+            traffic = json.load(open(summ)).get("msm_accum_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32 (8x32-bit Montgomery limbs, 254-bit modular integer arithmetic)", "data": "synthetic",
+        "config": workload_config(args, world),
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(prof["kernel_launches"]),
+        "roofline": {"bound": "hbm", "kernel": "msm_accum_kernel<true> (bucket accumulation, 11 launches per proof)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes, "ms_per_launch": accum_ms,
+                     "share_of_step": (prof["msm_accum_ms"] / args.steps) / (ms_dev / args.steps),
+                     "note": "integer-ALU bound (10 x 254-bit Montgomery products per pair and window); see DESIGN.md"},
+        "ntt": {"ms_per_step": prof["ntt_ms"] / args.steps, "launches_per_step": prof["ntt_launches"] / args.steps},
+        "phase_ms": prof["phase_ms"],
+        "clocks": clocks,
+        "prep_s": prep_s,
+    }
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        ls = cpu_sample_log_n(cores, args.log_n)
+        t = run_cpu_prove(ls, cores, 1, 1 if ls < 20 else 0)
+        scale = float(1 << (args.log_n - ls))
+        sample = "one full prove of the oracle port at 2^%d gates, %d threads (setup polynomials excluded)" % (ls, cores)
+        if ls != args.log_n:
+            sample += ", time scaled x%d to 2^%d" % (int(scale), args.log_n)
+        out["cpu_baseline"] = {"value": 1.0 / (t[0][0] * scale), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    else:
+        out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                               "sample": "not run at N > 1 (rank 0 at N = 1 only)"}
+    print(json.dumps(out), flush=True)
+    if td is not None:
+        td.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log-n", type=int, default=20)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 1:
+        args.warmup = 1
+    if args.impl == "reference":
+        return bench_reference(args)
+    return bench_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

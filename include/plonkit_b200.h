@@ -127,6 +127,11 @@ void pk_profile_enable(pk_ctx* ctx, int on);
 void pk_profile_reset(pk_ctx* ctx);
 void pk_profile_get(const pk_ctx* ctx, pk_profile* out);
 
+/* CUDA-event stopwatch on the library's stream: pk_timer_begin records an event, pk_timer_end records a second one,
+ * waits for it and returns the elapsed device time in milliseconds. */
+int pk_timer_begin(pk_ctx* ctx);
+int pk_timer_end(pk_ctx* ctx, double* ms);
+
 /* device-resident micro-benchmarks (inputs generated on the device): return elapsed ms by CUDA events */
 int pk_bench_ntt(pk_ctx* ctx, uint32_t log_n, int iters, double* ms_per_iter);
 int pk_bench_msm(pk_ctx* ctx, uint64_t n, int iters, double* ms_per_iter);

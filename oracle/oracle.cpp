@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -559,8 +560,14 @@ void orc_setup_commitments(const orc_assembly* as, const uint64_t* srs, uint64_t
 // Writes proof.bin bytes to proof_out (capacity >= 16 + 32*num_inputs + 1096) and returns the
 // length, or a negative error code (-1: gate identity unsatisfied, -2: quotient not a polynomial).
 // challenges_out (optional): beta,gamma,alpha,zeta,v canonical LE [5][4].
+static double g_last_setup_s = 0, g_last_prove_s = 0;
+// seconds spent by the last orc_prove in (a) rebuilding the setup polynomials, which the reference does once in
+// prepare_setup_for_prover (src/plonk.rs:104), and (b) everything SetupForProver::prove does per call
+void orc_last_timings(double* out) { out[0] = g_last_setup_s; out[1] = g_last_prove_s; }
+
 int64_t orc_prove(const orc_assembly* as, const uint64_t* srs, uint8_t* proof_out, uint64_t* challenges_out, int threads) {
     init_fields();
+    auto t_start = std::chrono::steady_clock::now();
     const size_t N = as->n;
     const int log_n = log2_floor(N);
     const size_t NI = as->num_inputs;
@@ -571,6 +578,7 @@ int64_t orc_prove(const orc_assembly* as, const uint64_t* srs, uint8_t* proof_ou
     // ---- setup polynomials (reference: prepare_setup_for_prover, src/plonk.rs:97-119; recomputed here per call)
     SetupPolys sp;
     make_setup(*as, sp, threads);
+    auto t_setup = std::chrono::steady_clock::now();
 
     // ---- witness -> wire values
     hvec<Fr> vars = load_frs(as->var_values, as->nvars, threads);
@@ -757,6 +765,9 @@ int64_t orc_prove(const orc_assembly* as, const uint64_t* srs, uint8_t* proof_ou
     for (int c = 0; c < 3; ++c) { write_fr_be(sz[c], p); p += 32; }
     write_g1_be(W1, p); p += 64;
     write_g1_be(W2, p); p += 64;
+    auto t_end = std::chrono::steady_clock::now();
+    g_last_setup_s = std::chrono::duration<double>(t_setup - t_start).count();
+    g_last_prove_s = std::chrono::duration<double>(t_end - t_setup).count();
     return (int64_t)(p - proof_out);
 }
 

@@ -233,3 +233,11 @@ def verify_trapdoor(proof_bytes: bytes, vk_commitments, tau=42) -> bool:
     if rc < 0:
         raise ValueError("malformed proof / vk")
     return rc == 1
+
+
+def last_timings():
+    """(setup_s, prove_s) of the last prove() call: setup polynomials (reference: once, in prepare_setup_for_prover)
+    vs. the per-call work of SetupForProver::prove"""
+    out = (ctypes.c_double * 2)()
+    lib().orc_last_timings(out)
+    return out[0], out[1]

@@ -26,7 +26,7 @@ EXPORTS = [
     "pk_create", "pk_destroy", "pk_last_error", "pk_constants", "pk_srs_load_g1", "pk_srs_gen", "pk_ntt", "pk_lde4",
     "pk_msm_g1", "pk_ec_intt_g1", "pk_setup_create", "pk_setup_destroy", "pk_setup_commitments", "pk_witness_upload",
     "pk_prove", "pk_profile_enable", "pk_profile_reset", "pk_profile_get", "pk_bench_ntt", "pk_bench_msm",
-    "pk_bench_fieldmul",
+    "pk_bench_fieldmul", "pk_timer_begin", "pk_timer_end",
 ]
 
 
@@ -115,6 +115,8 @@ def load():
     lib.pk_bench_ntt.argtypes = [vp, u32, i32, ctypes.POINTER(ctypes.c_double)]
     lib.pk_bench_msm.argtypes = [vp, u64, i32, ctypes.POINTER(ctypes.c_double)]
     lib.pk_bench_fieldmul.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double)]
+    lib.pk_timer_begin.argtypes = [vp]
+    lib.pk_timer_end.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     _lib = lib
     return lib
 
@@ -206,6 +208,14 @@ class Context:
         d = {k: getattr(p, k) for k, _ in PkProfile._fields_ if k != "phase_ms"}
         d["phase_ms"] = list(p.phase_ms)
         return d
+
+    def timer_begin(self):
+        self._check(self._lib.pk_timer_begin(self._h))
+
+    def timer_end(self):
+        ms = ctypes.c_double()
+        self._check(self._lib.pk_timer_end(self._h, ctypes.byref(ms)))
+        return ms.value
 
     def bench_ntt(self, log_n, iters=10):
         ms = ctypes.c_double()

@@ -254,6 +254,28 @@ void pk_profile_get(const pk_ctx* cctx, pk_profile* out) {
     for (int i = 0; i < 8; ++i) out->phase_ms[i] = ctx->prof.phase_ms[i];
 }
 
+static std::map<pk_ctx*, std::pair<cudaEvent_t, cudaEvent_t>> g_timers;
+int pk_timer_begin(pk_ctx* ctx) {
+    PK_API_BEGIN(ctx)
+    auto& t = g_timers[ctx];
+    if (!t.first) { PK_CUDA(cudaEventCreate(&t.first)); PK_CUDA(cudaEventCreate(&t.second)); }
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    PK_CUDA(cudaEventRecord(t.first, ctx->stream));
+    PK_API_END(ctx)
+}
+int pk_timer_end(pk_ctx* ctx, double* ms) {
+    PK_API_BEGIN(ctx)
+    PK_REQUIRE(ms != nullptr, PK_ERR_INVALID, "null output");
+    auto it = g_timers.find(ctx);
+    PK_REQUIRE(it != g_timers.end() && it->second.first, PK_ERR_INVALID, "pk_timer_begin was not called");
+    PK_CUDA(cudaEventRecord(it->second.second, ctx->stream));
+    PK_CUDA(cudaEventSynchronize(it->second.second));
+    float f = 0;
+    PK_CUDA(cudaEventElapsedTime(&f, it->second.first, it->second.second));
+    *ms = f;
+    PK_API_END(ctx)
+}
+
 // ---- device-resident micro-benchmarks
 int pk_bench_ntt(pk_ctx* ctx, uint32_t log_n, int iters, double* ms_per_iter) {
     PK_API_BEGIN(ctx)
