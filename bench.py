@@ -222,7 +222,8 @@ def bench_ours(args):
     peak, peak_src = peaks()
     launches = prof["msm_accum_launches"]
     accum_ms = prof["msm_accum_ms"] / max(launches, 1)
-    alg_bytes = 96.0 * n  # 32 B scalar + 64 B base per pair, N pairs per launch
+    # 32 B scalar + 64 B base per (scalar, base) pair; a launch covers a batch of up to 4 MSMs of N pairs
+    alg_bytes = 96.0 * prof["msm_accum_points"] / max(launches, 1)
     achieved = alg_bytes / (accum_ms * 1e-3) / 1e9 if launches else 0.0
     traffic = None
     summ = os.path.join(ROOT, "profiles", "ncu_summary.json")
@@ -239,7 +240,7 @@ def bench_ours(args):
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(prof["kernel_launches"]),
-        "roofline": {"bound": "hbm", "kernel": "msm_accum_kernel<true> (bucket accumulation, 11 launches per proof)",
+        "roofline": {"bound": "hbm", "kernel": "msm_accum_kernel<true> (bucket accumulation; 4 batched launches cover the 11 MSMs of a proof)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes, "ms_per_launch": accum_ms,
                      "share_of_step": (prof["msm_accum_ms"] / args.steps) / (ms_dev / args.steps),

@@ -9,17 +9,21 @@
 //     W = ceil(255/c) multiples 2^(c*w) * P_i precomputed in affine form (W x N x 64 B; 832 MB at N = 2^20, c = 20 —
 //     HBM is 180 GB).  All windows then share ONE bucket space of 2^(c-1) signed-digit buckets: no per-window
 //     bucket sets and no window-combine doubling chain at all.
+//   * BATCHES.  Commitments that are independent inside a prover round (4 wires, 4 quotient chunks, 2 openings) go
+//     through the kernels together: bucket ids are (set, bucket), so one sort, one accumulation and one reduction
+//     serve up to 4 scalar sets and the latency-bound tail kernels are paid once per round instead of once per MSM.
 //   * kernels (each its own launch, as named in BASELINE.json's north star):
-//       window scan      msm_digits_hist_kernel   scalar -> signed base-2^c digits, bucket histogram
-//       (offsets)        msm_offsets_kernel       exclusive scan of the histogram
-//       scatter          msm_scatter_kernel       counting sort of (table index, sign) by bucket
+//       window scan      msm_digits_kernel<0>     scalar -> signed base-2^c digits, bucket histogram
+//       offsets          u32_scan_*               exclusive scan of the histogram (3 small launches)
+//       scatter          msm_digits_kernel<1>     counting sort of (table index, sign) by bucket
 //       bucket accum     msm_accum_kernel<true>   mixed XYZZ additions; load-balanced segmented reduction:
 //                                                 every thread owns a fixed-length chunk of the sorted list,
 //                                                 whole runs go straight to their bucket, runs cut by a chunk
 //                                                 edge become partial entries for the next level
 //                        msm_accum_kernel<false>  same over partial entries (full XYZZ adds) until one chunk remains
-//       bucket reduce    msm_bucket_reduce_kernel sum (b+1) * B_b by segmented running sums
-//       final fold       msm_final_reduce_kernel  -> one XYZZ point; the host normalises it to affine (1 inversion)
+//       bucket reduce    msm_super_hi/lo_kernel   bucket id = hi*L + lo: G1[hi] = sum_lo B, G0[lo] = sum_hi B (tree sums)
+//                        msm_weighted_kernel      sum_hi (L*hi + 1) G1[hi] + sum_lo lo G0[lo]  ==  sum_b (b + 1) B_b
+//                        msm_fold_kernel          -> one XYZZ point per scalar set; the host normalises it to affine
 //   * work is independent of the scalar distribution (zero digits are skipped; repeated digits cannot unbalance it).
 //
 // Algorithmic HBM bytes: 96 B per (scalar, base) pair.  The kernels are bound by 32-bit integer
@@ -66,6 +70,13 @@ static int pick_window_bits(uint64_t n) {
     return best;
 }
 
+static int max_batch_for(const SrsTables* s) {
+    size_t M = (size_t)s->n * s->W;
+    int nb = MSM_MAX_BATCH;
+    while (nb > 1 && ((size_t)nb * M >= (size_t(1) << 31) || (size_t)nb * M * 8 > (size_t(6) << 30))) --nb;
+    return nb;
+}
+
 void srs_load(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits) {
     PK_REQUIRE(n >= 1, PK_ERR_INVALID, "empty SRS");
     PK_REQUIRE(n <= (uint64_t(1) << 26), PK_ERR_DEGREE_TOO_LARGE, "SRS larger than 2^26 bases (SETUP_MAX_POW2, src/plonk.rs:27)");
@@ -79,30 +90,36 @@ void srs_load(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits
     SrsTables* s = new SrsTables();
     ctx->srs = s;
     s->n = n; s->c = c; s->W = W; s->B = 1u << (c - 1);
+    s->hi_bits = (c - 1) / 2 < 7 ? (c - 1) / 2 : 7;
+    s->lo_bits = (c - 1) - s->hi_bits;
     s->table.alloc((size_t)W * n);
     PK_CUDA(cudaMemcpyAsync(s->table.p, bases_xy, n * 64, cudaMemcpyHostToDevice, ctx->stream));
     bases_to_mont_kernel<<<grid1d(n, 256), 256, 0, ctx->stream>>>(s->table.p, n);
     srs_window_kernel<<<grid1d(n, 128), 128, 0, ctx->stream>>>(s->table.p, n, c, W);
     ctx->prof.kernel_launches += 2;
     PK_CUDA(cudaGetLastError());
+    const int nb = max_batch_for(s);
     size_t M = (size_t)n * W;
-    s->hist.alloc(s->B + 1);
-    s->offsets.alloc(s->B + 1);
-    s->cursor.alloc(s->B);
-    s->keys.alloc(M);
-    s->items.alloc(M);
-    s->buckets.alloc(s->B);
-    // level-1 chunk: keep the chunk count <= 2^19 so the partial lists stay small
+    size_t NB = (size_t)nb * s->B;
+    s->hist.alloc(NB);
+    s->offsets.alloc(NB + 1);
+    s->cursor.alloc(NB);
+    s->scan_sums.alloc((NB + 4095) / 4096 + 1);
+    s->keys.alloc(nb * M);
+    s->items.alloc(nb * M);
+    s->buckets.alloc(NB);
+    // level-1 chunk: keep the chunk count of one scalar set <= 2^19 so the partial lists stay small
     uint32_t chunk = 64;
     while (M / chunk > (size_t(1) << 19)) chunk *= 2;
     s->chunk1 = chunk;
-    size_t nchunks = (M + chunk - 1) / chunk;
+    size_t nchunks = (nb * M + chunk - 1) / chunk;
     for (int k = 0; k < 2; ++k) {
         s->pkeys[k].alloc(2 * nchunks + 2);
         s->ppts[k].alloc(2 * nchunks + 2);
     }
     s->counts.alloc(16);
-    s->red.alloc(4100);
+    s->super.alloc((size_t)nb * ((size_t(1) << s->hi_bits) + (size_t(1) << s->lo_bits)));
+    s->red.alloc((size_t)MSM_MAX_BATCH * 1024 + MSM_MAX_BATCH);
     PK_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
@@ -117,22 +134,25 @@ __device__ __forceinline__ uint32_t raw_window(const uint32_t* k, int w, int c) 
     return v & ((1u << c) - 1);
 }
 
-// MODE 0: histogram; MODE 1: scatter
+struct ScalarSets { const fr_t* s[MSM_MAX_BATCH]; };
+
+// MODE 0: histogram; MODE 1: scatter.  blockIdx.y = scalar set; bucket ids are set * B + bucket.
 template <int MODE>
-__global__ void msm_digits_kernel(const fr_t* scalars, uint32_t n, uint32_t table_n, uint32_t base_offset, int c, int W,
+__global__ void msm_digits_kernel(ScalarSets sets, uint32_t n, uint32_t table_n, uint32_t base_offset, int c, int W,
                                   uint32_t* hist_or_cursor, uint32_t* keys, uint32_t* items) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    fr_t k = ld_fp(scalars + i).from_mont();
+    fr_t k = ld_fp(sets.s[blockIdx.y] + i).from_mont();
     if (k.is_zero()) return;
     uint32_t carry = 0;
     const uint32_t half = 1u << (c - 1);
+    const uint32_t set_base = blockIdx.y * half;
     for (int w = 0; w < W; ++w) {
         uint32_t d = raw_window(k.v, w, c) + carry;
         uint32_t neg = 0;
         if (d > half) { d = (1u << c) - d; neg = 1; carry = 1; } else carry = 0;
         if (d == 0) continue;
-        uint32_t b = d - 1;
+        uint32_t b = set_base + d - 1;
         if (MODE == 0) {
             atomicAdd(hist_or_cursor + b, 1u);
         } else {
@@ -143,32 +163,52 @@ __global__ void msm_digits_kernel(const fr_t* scalars, uint32_t n, uint32_t tabl
     }
 }
 
-// exclusive scan of hist[0..B) into offsets[0..B], cursor = copy; total -> counts[0].  Single block of 1024 threads.
-__global__ void msm_offsets_kernel(const uint32_t* hist, uint32_t* offsets, uint32_t* cursor, uint32_t B, uint32_t* counts) {
-    __shared__ uint32_t sh[1024];
-    const uint32_t tid = threadIdx.x;
-    const uint32_t per = (B + 1023) / 1024;
-    uint32_t lo = tid * per, hi = lo + per;
-    if (hi > B) hi = B;
-    uint32_t sum = 0;
-    for (uint32_t b = lo; b < hi; ++b) sum += hist[b];
-    sh[tid] = sum;
+// ---------------------------------------------------------------- exclusive scan of the histogram (tiles of 4096)
+__device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t v, uint32_t* sh, uint32_t* total) {
+    const unsigned tid = threadIdx.x;
+    sh[tid] = v;
     __syncthreads();
-    for (uint32_t d = 1; d < 1024; d <<= 1) {
-        uint32_t v = tid >= d ? sh[tid - d] : 0;
+    for (unsigned d = 1; d < 1024; d <<= 1) {
+        uint32_t t = tid >= d ? sh[tid - d] : 0;
         __syncthreads();
-        sh[tid] += v;
+        sh[tid] += t;
         __syncthreads();
     }
-    uint32_t run = sh[tid] - sum;  // exclusive prefix of this thread's range
-    for (uint32_t b = lo; b < hi; ++b) {
-        offsets[b] = run;
-        cursor[b] = run;
-        run += hist[b];
-    }
-    if (tid == 1023) {
-        offsets[B] = sh[1023];
-        counts[0] = sh[1023];
+    if (total) *total = sh[1023];
+    return sh[tid] - v;
+}
+__global__ void __launch_bounds__(1024) u32_scan_tile_sums_kernel(const uint32_t* in, uint32_t* sums, uint32_t n) {
+    __shared__ uint32_t sh[1024];
+    const uint32_t base = blockIdx.x * 4096 + threadIdx.x * 4;
+    uint32_t v = 0;
+    for (int r = 0; r < 4; ++r) if (base + r < n) v += in[base + r];
+    uint32_t tot;
+    block_exclusive_scan_1024(v, sh, &tot);
+    if (threadIdx.x == 0) sums[blockIdx.x] = tot;
+}
+// in-place exclusive scan of m tile sums by one block; total -> *total_out and out_last
+__global__ void __launch_bounds__(1024) u32_scan_spine_kernel(uint32_t* sums, uint32_t m, uint32_t* total_out, uint32_t* out_last) {
+    __shared__ uint32_t sh[1024];
+    const uint32_t per = (m + 1023) / 1024;
+    uint32_t lo = threadIdx.x * per, hi = lo + per;
+    if (hi > m) hi = m;
+    uint32_t v = 0;
+    for (uint32_t i = lo; i < hi; ++i) v += sums[i];
+    uint32_t tot;
+    uint32_t run = block_exclusive_scan_1024(v, sh, &tot);
+    for (uint32_t i = lo; i < hi; ++i) { uint32_t x = sums[i]; sums[i] = run; run += x; }
+    if (threadIdx.x == 0) { *total_out = tot; *out_last = tot; }
+}
+__global__ void __launch_bounds__(1024) u32_scan_apply_kernel(const uint32_t* in, const uint32_t* sums, uint32_t* out, uint32_t* out2,
+                                                              uint32_t n) {
+    __shared__ uint32_t sh[1024];
+    const uint32_t base = blockIdx.x * 4096 + threadIdx.x * 4;
+    uint32_t x[4], v = 0;
+    for (int r = 0; r < 4; ++r) { x[r] = (base + r < n) ? in[base + r] : 0; v += x[r]; }
+    uint32_t run = block_exclusive_scan_1024(v, sh, nullptr) + sums[blockIdx.x];
+    for (int r = 0; r < 4; ++r) {
+        if (base + r < n) { out[base + r] = run; out2[base + r] = run; }
+        run += x[r];
     }
 }
 
@@ -242,7 +282,7 @@ template <bool LEVEL1> __global__ void __launch_bounds__(128) msm_accum_kernel(A
     }
 }
 
-// ---------------------------------------------------------------- bucket reduction: sum_b (b + 1) * B_b
+// ---------------------------------------------------------------- bucket reduction: sum_b (b + 1) * B_b, b = hi * L + lo
 __device__ __forceinline__ void block_sum_xyzz(g1_xyzz_t& v, g1_xyzz_t* sh, g1_xyzz_t* out) {
     const unsigned tid = threadIdx.x;
     sh[tid] = v;
@@ -253,29 +293,48 @@ __device__ __forceinline__ void block_sum_xyzz(g1_xyzz_t& v, g1_xyzz_t* sh, g1_x
     }
     if (tid == 0) st_xyzz(out, sh[0]);
 }
-
-__global__ void __launch_bounds__(128) msm_bucket_reduce_kernel(const g1_xyzz_t* buckets, uint32_t B, uint32_t seg, g1_xyzz_t* block_out) {
+// G1[set][hi] = sum_lo B[set][hi * L + lo]; one block per (hi, set)
+__global__ void __launch_bounds__(128) msm_super_hi_kernel(const g1_xyzz_t* buckets, int lo_bits, int hi_bits, g1_xyzz_t* super) {
     __shared__ g1_xyzz_t sh[128];
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t lo = (uint64_t)t * seg;
-    g1_xyzz_t R = g1_xyzz_t::infinity();
-    if (lo < B) {
-        uint32_t hi = (lo + seg < B) ? (uint32_t)(lo + seg) : B;
-        g1_xyzz_t running = g1_xyzz_t::infinity(), sum = g1_xyzz_t::infinity();
-        for (uint32_t b = hi; b-- > (uint32_t)lo;) {
-            running = running.add(ld_xyzz(buckets + b));
-            sum = sum.add(running);
-        }
-        // sum = sum_b (b - lo + 1) B_b ; add lo * running to get weights (b + 1)
-        R = sum.add(running.mul_small((uint32_t)lo));
-    }
-    block_sum_xyzz(R, sh, block_out + blockIdx.x);
+    const uint32_t L = 1u << lo_bits, H = 1u << hi_bits;
+    const g1_xyzz_t* src = buckets + ((size_t)blockIdx.y << (lo_bits + hi_bits)) + ((size_t)blockIdx.x << lo_bits);
+    g1_xyzz_t acc = g1_xyzz_t::infinity();
+    for (uint32_t i = threadIdx.x; i < L; i += blockDim.x) acc = acc.add(ld_xyzz(src + i));
+    block_sum_xyzz(acc, sh, super + (size_t)blockIdx.y * (H + L) + blockIdx.x);
 }
-__global__ void __launch_bounds__(128) msm_final_reduce_kernel(const g1_xyzz_t* in, uint32_t n, g1_xyzz_t* out) {
+// G0[set][lo] = sum_hi B[set][hi * L + lo]; block = 32 consecutive lo x 4 hi-groups
+__global__ void __launch_bounds__(128) msm_super_lo_kernel(const g1_xyzz_t* buckets, int lo_bits, int hi_bits, g1_xyzz_t* super) {
+    __shared__ g1_xyzz_t sh[128];
+    const uint32_t L = 1u << lo_bits, H = 1u << hi_bits;
+    const uint32_t lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const uint32_t lo = blockIdx.x * 32 + lane;
+    const g1_xyzz_t* src = buckets + ((size_t)blockIdx.y << (lo_bits + hi_bits));
+    g1_xyzz_t acc = g1_xyzz_t::infinity();
+    if (lo < L)
+        for (uint32_t hi = grp; hi < H; hi += 4) acc = acc.add(ld_xyzz(src + ((size_t)hi << lo_bits) + lo));
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    if (grp < 2) sh[threadIdx.x] = sh[threadIdx.x].add(sh[threadIdx.x + 64]);
+    __syncthreads();
+    if (grp == 0 && lo < L) st_xyzz(super + (size_t)blockIdx.y * (H + L) + H + lo, sh[lane].add(sh[lane + 32]));
+}
+// sum_hi (L * hi + 1) G1[hi] + sum_lo lo * G0[lo], block partials
+__global__ void __launch_bounds__(128) msm_weighted_kernel(const g1_xyzz_t* super, int lo_bits, int hi_bits, g1_xyzz_t* red, uint32_t red_stride) {
+    __shared__ g1_xyzz_t sh[128];
+    const uint32_t L = 1u << lo_bits, H = 1u << hi_bits;
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    g1_xyzz_t R = g1_xyzz_t::infinity();
+    if (j < H + L) {
+        uint32_t weight = j < H ? (j << lo_bits) + 1 : j - H;
+        R = ld_xyzz(super + (size_t)blockIdx.y * (H + L) + j).mul_small(weight);
+    }
+    block_sum_xyzz(R, sh, red + (size_t)blockIdx.y * red_stride + blockIdx.x);
+}
+__global__ void __launch_bounds__(128) msm_fold_kernel(const g1_xyzz_t* red, uint32_t n, uint32_t red_stride, g1_xyzz_t* out) {
     __shared__ g1_xyzz_t sh[128];
     g1_xyzz_t acc = g1_xyzz_t::infinity();
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) acc = acc.add(ld_xyzz(in + i));
-    block_sum_xyzz(acc, sh, out);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) acc = acc.add(ld_xyzz(red + (size_t)blockIdx.x * red_stride + i));
+    block_sum_xyzz(acc, sh, out + blockIdx.x);
 }
 
 void affine_to_abi(const g1_affine_t& p, uint64_t out[8]) {
@@ -285,23 +344,26 @@ void affine_to_abi(const g1_affine_t& p, uint64_t out[8]) {
     memcpy(out + 4, y.v, 32);
 }
 
-g1_affine_t msm_run(pk_ctx* ctx, const fr_t* scalars, uint64_t n, uint64_t base_offset) {
+static void msm_run_group(pk_ctx* ctx, const fr_t* const* scalars, int nb, uint64_t n, uint64_t base_offset, g1_affine_t* out) {
     SrsTables* s = ctx->srs;
-    PK_REQUIRE(s != nullptr, PK_ERR_DEGREE_TOO_LARGE, "no SRS loaded (pk_srs_load_g1)");
-    PK_REQUIRE(base_offset + n <= s->n, PK_ERR_DEGREE_TOO_LARGE, "MSM longer than the resident SRS");
-    if (n == 0) return g1_affine_t::infinity();
     cudaStream_t st = ctx->stream;
     const uint32_t B = s->B;
-    PK_CUDA(cudaMemsetAsync(s->hist.p, 0, (B + 1) * sizeof(uint32_t), st));
-    PK_CUDA(cudaMemsetAsync(s->buckets.p, 0, (size_t)B * sizeof(g1_xyzz_t), st));
-    msm_digits_kernel<0><<<grid1d(n, 256), 256, 0, st>>>(scalars, (uint32_t)n, (uint32_t)s->n, (uint32_t)base_offset, s->c, s->W,
-                                                         s->hist.p, nullptr, nullptr);
-    msm_offsets_kernel<<<1, 1024, 0, st>>>(s->hist.p, s->offsets.p, s->cursor.p, B, s->counts.p);
-    msm_digits_kernel<1><<<grid1d(n, 256), 256, 0, st>>>(scalars, (uint32_t)n, (uint32_t)s->n, (uint32_t)base_offset, s->c, s->W,
-                                                         s->cursor.p, s->keys.p, s->items.p);
-    ctx->prof.kernel_launches += 3;
+    const uint32_t NB = (uint32_t)nb * B;
+    ScalarSets sets;
+    for (int k = 0; k < MSM_MAX_BATCH; ++k) sets.s[k] = scalars[k < nb ? k : 0];
+    PK_CUDA(cudaMemsetAsync(s->hist.p, 0, (size_t)NB * sizeof(uint32_t), st));
+    PK_CUDA(cudaMemsetAsync(s->buckets.p, 0, (size_t)NB * sizeof(g1_xyzz_t), st));
+    dim3 dgrid((unsigned)((n + 255) / 256), nb);
+    msm_digits_kernel<0><<<dgrid, 256, 0, st>>>(sets, (uint32_t)n, (uint32_t)s->n, (uint32_t)base_offset, s->c, s->W, s->hist.p, nullptr, nullptr);
+    const uint32_t tiles = (NB + 4095) / 4096;
+    u32_scan_tile_sums_kernel<<<tiles, 1024, 0, st>>>(s->hist.p, s->scan_sums.p, NB);
+    u32_scan_spine_kernel<<<1, 1024, 0, st>>>(s->scan_sums.p, tiles, s->counts.p, s->offsets.p + NB);
+    u32_scan_apply_kernel<<<tiles, 1024, 0, st>>>(s->hist.p, s->scan_sums.p, s->offsets.p, s->cursor.p, NB);
+    msm_digits_kernel<1><<<dgrid, 256, 0, st>>>(sets, (uint32_t)n, (uint32_t)s->n, (uint32_t)base_offset, s->c, s->W, s->cursor.p, s->keys.p,
+                                                s->items.p);
+    ctx->prof.kernel_launches += 5;
     // accumulation levels (worst-case grids; the device-side counts bound the real work)
-    size_t max_entries = (size_t)n * s->W;
+    size_t max_entries = (size_t)nb * n * s->W;
     AccumParams p;
     memset(&p, 0, sizeof(p));
     p.table = s->table.p;
@@ -320,7 +382,7 @@ g1_affine_t msm_run(pk_ctx* ctx, const fr_t* scalars, uint64_t n, uint64_t base_
         p.out_keys = s->pkeys[level & 1].p;
         p.out_pts = s->ppts[level & 1].p;
         if (level == 0) {
-            ScopedKernelTimer timer(ctx, 0, n);
+            ScopedKernelTimer timer(ctx, 0, (uint64_t)nb * n);
             msm_accum_kernel<true><<<grid1d(nchunks, 128), 128, 0, st>>>(p);
             ctx->prof.msm_accum_launches++;
         } else {
@@ -335,18 +397,41 @@ g1_affine_t msm_run(pk_ctx* ctx, const fr_t* scalars, uint64_t n, uint64_t base_
         PK_REQUIRE(level < 14, PK_ERR_INVALID, "MSM level overflow");
     }
     // bucket reduction
-    uint32_t seg = 32;
-    while ((B + seg - 1) / seg > 128u * 4096u) seg *= 2;
-    uint32_t nthreads = (B + seg - 1) / seg;
-    uint32_t nblocks = (nthreads + 127) / 128;
-    msm_bucket_reduce_kernel<<<nblocks, 128, 0, st>>>(s->buckets.p, B, seg, s->red.p);
-    msm_final_reduce_kernel<<<1, 128, 0, st>>>(s->red.p, nblocks, s->red.p + 4096);
-    ctx->prof.kernel_launches += 2;
+    const uint32_t H = 1u << s->hi_bits, L = 1u << s->lo_bits;
+    msm_super_hi_kernel<<<dim3(H, nb), 128, 0, st>>>(s->buckets.p, s->lo_bits, s->hi_bits, s->super.p);
+    msm_super_lo_kernel<<<dim3((L + 31) / 32, nb), 128, 0, st>>>(s->buckets.p, s->lo_bits, s->hi_bits, s->super.p);
+    const uint32_t wblocks = (H + L + 127) / 128;
+    PK_REQUIRE(wblocks <= 1024, PK_ERR_INVALID, "bucket reduction partial buffer too small");
+    g1_xyzz_t* result = s->red.p + (size_t)MSM_MAX_BATCH * 1024;
+    msm_weighted_kernel<<<dim3(wblocks, nb), 128, 0, st>>>(s->super.p, s->lo_bits, s->hi_bits, s->red.p, 1024);
+    msm_fold_kernel<<<nb, 128, 0, st>>>(s->red.p, wblocks, 1024, result);
+    ctx->prof.kernel_launches += 4;
     PK_CUDA(cudaGetLastError());
     g1_xyzz_t* host_pt = reinterpret_cast<g1_xyzz_t*>(ctx->pinned);
-    PK_CUDA(cudaMemcpyAsync(host_pt, s->red.p + 4096, sizeof(g1_xyzz_t), cudaMemcpyDeviceToHost, st));
+    PK_CUDA(cudaMemcpyAsync(host_pt, result, nb * sizeof(g1_xyzz_t), cudaMemcpyDeviceToHost, st));
     PK_CUDA(cudaStreamSynchronize(st));
-    return host_pt->to_affine();
+    for (int k = 0; k < nb; ++k) out[k] = host_pt[k].to_affine();
+}
+
+void msm_run_batch(pk_ctx* ctx, const fr_t* const* scalars, int nb, uint64_t n, uint64_t base_offset, g1_affine_t* out) {
+    SrsTables* s = ctx->srs;
+    PK_REQUIRE(s != nullptr, PK_ERR_DEGREE_TOO_LARGE, "no SRS loaded (pk_srs_load_g1)");
+    PK_REQUIRE(base_offset + n <= s->n, PK_ERR_DEGREE_TOO_LARGE, "MSM longer than the resident SRS");
+    if (n == 0) {
+        for (int k = 0; k < nb; ++k) out[k] = g1_affine_t::infinity();
+        return;
+    }
+    const int group = max_batch_for(s);
+    for (int k = 0; k < nb; k += group) {
+        int g = nb - k < group ? nb - k : group;
+        msm_run_group(ctx, scalars + k, g, n, base_offset, out + k);
+    }
+}
+
+g1_affine_t msm_run(pk_ctx* ctx, const fr_t* scalars, uint64_t n, uint64_t base_offset) {
+    g1_affine_t out;
+    msm_run_batch(ctx, &scalars, 1, n, base_offset, &out);
+    return out;
 }
 
 }  // namespace pk

@@ -4,29 +4,36 @@
 
 namespace pk {
 
+static const int MSM_MAX_BATCH = 4;
+
 struct SrsTables {
     uint64_t n = 0;          // resident bases
     int c = 0;               // window bits (signed digits in (-2^(c-1), 2^(c-1)])
     int W = 0;               // windows = ceil(255 / c)
-    uint32_t B = 0;          // buckets = 2^(c-1)
+    uint32_t B = 0;          // buckets per scalar set = 2^(c-1)
+    int lo_bits = 0, hi_bits = 0;  // bucket id = hi * 2^lo_bits + lo (two-level bucket reduction)
     DevBuf<g1_affine_t> table;   // [W][n]: table[w][i] = 2^(c*w) * base_i, affine, Montgomery form
 
-    // scratch, sized for n pairs
-    DevBuf<uint32_t> hist;       // [B + 1]
-    DevBuf<uint32_t> offsets;    // [B + 1]
-    DevBuf<uint32_t> cursor;     // [B]
-    DevBuf<uint32_t> keys, items;        // [n * W]
-    DevBuf<g1_xyzz_t> buckets;           // [B]
+    // scratch, sized for MSM_MAX_BATCH scalar sets of n pairs
+    DevBuf<uint32_t> hist;       // [nb*B]
+    DevBuf<uint32_t> offsets;    // [nb*B + 1]
+    DevBuf<uint32_t> cursor;     // [nb*B]
+    DevBuf<uint32_t> scan_sums;  // block sums of the offsets scan
+    DevBuf<uint32_t> keys, items;        // [nb * n * W]
+    DevBuf<g1_xyzz_t> buckets;           // [nb*B]
     DevBuf<uint32_t> pkeys[2];           // partial-run lists (ping-pong between levels)
     DevBuf<g1_xyzz_t> ppts[2];
     DevBuf<uint32_t> counts;             // [16] per-level entry counts (device)
-    DevBuf<g1_xyzz_t> red;               // bucket-reduction partials
-    uint32_t chunk1 = 64;                // entries per thread at level 1
+    DevBuf<g1_xyzz_t> super;             // [nb][2^hi_bits + 2^lo_bits] super-bucket sums
+    DevBuf<g1_xyzz_t> red;               // reduction partials + [nb] results
+    uint32_t chunk1 = 64;                // entries per thread at level 1 (for a single scalar set)
 };
 
 // loads n affine bases (canonical limbs, host) and builds the window tables
 void srs_load(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits);
-// sum_i scalars[i] * base[base_offset + i]; scalars on the device in Montgomery form; result affine (Montgomery) on the host
+// out[k] = sum_i scalars[k][i] * base[base_offset + i] for k < nb <= MSM_MAX_BATCH; scalars on the device in
+// Montgomery form; results affine (Montgomery) on the host.  One pass over the shared kernels for the whole batch.
+void msm_run_batch(pk_ctx* ctx, const fr_t* const* scalars, int nb, uint64_t n, uint64_t base_offset, g1_affine_t* out);
 g1_affine_t msm_run(pk_ctx* ctx, const fr_t* scalars, uint64_t n, uint64_t base_offset);
 // host helper: affine Montgomery point -> canonical u64[8] ((0,0) for infinity)
 void affine_to_abi(const g1_affine_t& p, uint64_t out[8]);

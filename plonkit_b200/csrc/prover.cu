@@ -147,8 +147,12 @@ void setup_create(pk_ctx* ctx, const pk_assembly* as, pk_setup** out) {
 }
 
 void setup_commitments(pk_ctx* ctx, pk_setup* s, uint64_t out_xy[11][8]) {
-    for (int k = 0; k < 7; ++k) affine_to_abi(msm_run(ctx, s->sel_coef.p + k * s->n, s->n, 0), out_xy[k]);
-    for (int k = 0; k < 4; ++k) affine_to_abi(msm_run(ctx, s->sigma_coef.p + k * s->n, s->n, 0), out_xy[7 + k]);
+    const fr_t* polys[11];
+    for (int k = 0; k < 7; ++k) polys[k] = s->sel_coef.p + k * s->n;
+    for (int k = 0; k < 4; ++k) polys[7 + k] = s->sigma_coef.p + k * s->n;
+    g1_affine_t out[11];
+    msm_run_batch(ctx, polys, 11, s->n, 0, out);
+    for (int k = 0; k < 11; ++k) affine_to_abi(out[k], out_xy[k]);
 }
 
 void witness_upload(pk_ctx* ctx, pk_setup* s, const uint64_t* var_values, uint64_t nvars) {
@@ -208,10 +212,14 @@ void prove(pk_ctx* ctx, pk_setup* s, const uint64_t* var_values, uint64_t nvars,
 
     // ---- round 1: wire polynomials and commitments
     g1_affine_t Cw[4];
-    for (int c = 0; c < 4; ++c) {
-        ntt_inverse_from_bitrev(ctx, s->w_br.p + c * n, s->w_coef.p + c * n, log_n);
-        Cw[c] = msm_run(ctx, s->w_coef.p + c * n, n, 0);
-        tr_commit_g1(tr, Cw[c]);
+    {
+        const fr_t* polys[4];
+        for (int c = 0; c < 4; ++c) {
+            ntt_inverse_from_bitrev(ctx, s->w_br.p + c * n, s->w_coef.p + c * n, log_n);
+            polys[c] = s->w_coef.p + c * n;
+        }
+        msm_run_batch(ctx, polys, 4, n, 0, Cw);  // the 4 wire commitments share one pass over the MSM kernels
+        for (int c = 0; c < 4; ++c) tr_commit_g1(tr, Cw[c]);
     }
     const fr_t beta = tr_challenge(tr), gamma = tr_challenge(tr);
     clk.mark();  // phase 1
@@ -254,9 +262,10 @@ void prove(pk_ctx* ctx, pk_setup* s, const uint64_t* var_values, uint64_t nvars,
         PK_REQUIRE(top[0].is_zero() && top[1].is_zero() && top[2].is_zero(), PK_ERR_UNSATISFIED, "quotient is not a polynomial");
     }
     g1_affine_t Ct[4];
-    for (int i = 0; i < 4; ++i) {
-        Ct[i] = msm_run(ctx, s->t4.p + i * n, n, 0);
-        tr_commit_g1(tr, Ct[i]);
+    {
+        const fr_t* polys[4] = {s->t4.p, s->t4.p + n, s->t4.p + 2 * n, s->t4.p + 3 * n};
+        msm_run_batch(ctx, polys, 4, n, 0, Ct);
+        for (int i = 0; i < 4; ++i) tr_commit_g1(tr, Ct[i]);
     }
     const fr_t zeta = tr_challenge(tr);
     clk.mark();  // phase 3
@@ -335,9 +344,13 @@ void prove(pk_ctx* ctx, pk_setup* s, const uint64_t* var_values, uint64_t nvars,
     poly_powers(ctx, s->zwinvpow.p, zeta_omega.inverse(), n);
     // W_z = (agg(X) - agg(z)) / (X - z);  W_zw = (agg2(X) - agg2(z w)) / (X - z w)
     poly_divide_linear(ctx, s->tmp_a.p, s->zpow.p, s->zinvpow.p, s->r_coef.p, s->tmp_c.p, n);
-    const g1_affine_t W1 = msm_run(ctx, s->r_coef.p, n, 0);
     poly_divide_linear(ctx, s->tmp_b.p, s->zwpow.p, s->zwinvpow.p, s->tmp_a.p, s->tmp_c.p, n);
-    const g1_affine_t W2 = msm_run(ctx, s->tmp_a.p, n, 0);
+    g1_affine_t Wz[2];
+    {
+        const fr_t* polys[2] = {s->r_coef.p, s->tmp_a.p};
+        msm_run_batch(ctx, polys, 2, n, 0, Wz);
+    }
+    const g1_affine_t W1 = Wz[0], W2 = Wz[1];
     clk.mark();  // phase 5
     clk.finish();
 
