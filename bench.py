@@ -101,12 +101,27 @@ def barrier(td, local):
         torch.cuda.synchronize(local)
 
 
+def effective_cores():
+    """Host cores this process may really use: min(visible CPUs, affinity mask, cgroup CPU quota).  On the GPU boxes
+    nproc reports 128 but the container's cgroup quota is 16 CPUs; oversubscribing it makes the CPU leg slower."""
+    cores = os.cpu_count() or 1
+    try:
+        cores = min(cores, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            cores = max(1, min(cores, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return cores
+
+
 def cpu_sample_log_n(cores, log_n):
-    if cores >= 64:
-        return log_n
     if cores >= 16:
-        return min(log_n, 18)
-    return min(log_n, 16)
+        return log_n
+    return min(log_n, 17)
 
 
 def run_cpu_prove(log_n_s, threads, repeats, warm):
@@ -131,7 +146,7 @@ def bench_reference(args):
     world, rank, local, td = 1, int(os.environ.get("RANK", "0")), 0, None
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
+    cores = effective_cores()
     ls = cpu_sample_log_n(cores, args.log_n)
     times = run_cpu_prove(ls, cores, args.steps, args.warmup)
     scale = float(1 << (args.log_n - ls))
@@ -251,7 +266,7 @@ def bench_ours(args):
         "prep_s": prep_s,
     }
     if world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
+        cores = effective_cores()
         ls = cpu_sample_log_n(cores, args.log_n)
         t = run_cpu_prove(ls, cores, 1, 1 if ls < 20 else 0)
         scale = float(1 << (args.log_n - ls))
@@ -260,7 +275,7 @@ def bench_ours(args):
             sample += ", time scaled x%d to 2^%d" % (int(scale), args.log_n)
         out["cpu_baseline"] = {"value": 1.0 / (t[0][0] * scale), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     else:
-        out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+        out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": effective_cores(), "kind": "port",
                                "sample": "not run at N > 1 (rank 0 at N = 1 only)"}
     print(json.dumps(out), flush=True)
     if td is not None:

@@ -5,6 +5,7 @@ raises.  Loading the library needs no GPU (tests check the exported symbols on C
 """
 import ctypes
 import os
+import weakref
 
 import numpy as np
 
@@ -137,9 +138,12 @@ class Context:
         self._h = h
         self.device = device
         self.srs_size = 0
+        self._children = weakref.WeakSet()  # device-side objects that must be released before the context
 
     def close(self):
         if getattr(self, "_h", None):
+            for child in list(self._children):
+                child.close()
             self._lib.pk_destroy(self._h)
             self._h = None
 

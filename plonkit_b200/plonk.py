@@ -82,6 +82,7 @@ class SetupForProver:
         h = ctypes.c_void_p()
         self.ctx._check(self.ctx._lib.pk_setup_create(self.ctx._h, ctypes.byref(a), ctypes.byref(h)))
         self._h = h
+        self.ctx._children.add(self)
         return self
 
     def _ensure_srs(self):
@@ -93,7 +94,8 @@ class SetupForProver:
 
     def close(self):
         if getattr(self, "_h", None):
-            self.ctx._lib.pk_setup_destroy(self._h)
+            if getattr(self.ctx, "_h", None):  # the context owns the device; once it is gone so is this setup
+                self.ctx._lib.pk_setup_destroy(self._h)
             self._h = None
 
     def __del__(self):
