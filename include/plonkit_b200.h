@@ -63,6 +63,10 @@ int pk_lde4(pk_ctx* ctx, const uint64_t* coeffs, uint32_t log_n, uint64_t* out_4
 /* multiexp::dense_multiexp / commit_using_monomials: sum_i scalars[i] * SRS[base_offset + i], normalised to affine. */
 int pk_msm_g1(pk_ctx* ctx, const uint64_t* scalars, uint64_t n, uint64_t base_offset, uint64_t out_xy[8], int* is_infinity,
               int fmt);
+/* Sum of n affine points (host arithmetic, no device needed).  This is the local fold of the multi-GPU MSM: every
+ * rank computes the partial sum over its chunk of (scalar, base) pairs, the 64-byte partials are all-gathered, and
+ * each rank adds them up — the "all-reduce" of SURVEY.md section 8(e) (EC addition is not an NCCL reduce-op). */
+int pk_g1_sum(const uint64_t* points_xy, uint64_t n, uint64_t out_xy[8]);
 /* Crs::<_, CrsForLagrangeForm>::from_powers (src/plonk.rs:179-185): EC inverse FFT of the first 2^log_n resident
  * monomial bases: out[i] = [L_i(tau)] G, natural order. */
 int pk_ec_intt_g1(pk_ctx* ctx, uint32_t log_n, uint64_t* out_xy);

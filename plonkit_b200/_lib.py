@@ -27,7 +27,7 @@ EXPORTS = [
     "pk_create", "pk_destroy", "pk_last_error", "pk_constants", "pk_srs_load_g1", "pk_srs_gen", "pk_ntt", "pk_lde4",
     "pk_msm_g1", "pk_ec_intt_g1", "pk_setup_create", "pk_setup_destroy", "pk_setup_commitments", "pk_witness_upload",
     "pk_prove", "pk_profile_enable", "pk_profile_reset", "pk_profile_get", "pk_bench_ntt", "pk_bench_msm",
-    "pk_bench_fieldmul", "pk_timer_begin", "pk_timer_end",
+    "pk_bench_fieldmul", "pk_timer_begin", "pk_timer_end", "pk_g1_sum",
 ]
 
 
@@ -116,6 +116,7 @@ def load():
     lib.pk_bench_ntt.argtypes = [vp, u32, i32, ctypes.POINTER(ctypes.c_double)]
     lib.pk_bench_msm.argtypes = [vp, u64, i32, ctypes.POINTER(ctypes.c_double)]
     lib.pk_bench_fieldmul.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double)]
+    lib.pk_g1_sum.argtypes = [vp, u64, vp]
     lib.pk_timer_begin.argtypes = [vp]
     lib.pk_timer_end.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     _lib = lib
@@ -235,6 +236,16 @@ class Context:
         g = ctypes.c_double()
         self._check(self._lib.pk_bench_fieldmul(self._h, which, ctypes.byref(g)))
         return g.value
+
+
+def g1_sum(points) -> np.ndarray:
+    """Sum of affine points on the host (pk_g1_sum): the local fold of the sharded MSM.  Needs no GPU."""
+    pts = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, 8)
+    out = np.zeros(8, dtype=np.uint64)
+    rc = load().pk_g1_sum(_ptr(pts) if pts.shape[0] else None, pts.shape[0], _ptr(out))
+    if rc != PK_OK:
+        raise SynthesisError(rc, "pk_g1_sum")
+    return out
 
 
 def constants():

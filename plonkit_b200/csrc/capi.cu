@@ -193,6 +193,23 @@ int pk_msm_g1(pk_ctx* ctx, const uint64_t* scalars, uint64_t n, uint64_t base_of
     PK_API_END(ctx)
 }
 
+int pk_g1_sum(const uint64_t* points_xy, uint64_t n, uint64_t out_xy[8]) {
+    if (!out_xy || (n && !points_xy)) return PK_ERR_INVALID;
+    g1_xyzz_t acc = g1_xyzz_t::infinity();
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t* s = points_xy + 8 * i;
+        bool inf = true;
+        for (int k = 0; k < 8; ++k) inf = inf && s[k] == 0;
+        if (inf) continue;
+        g1_affine_t p;
+        p.x = host_load_canonical<fq_t>(s);
+        p.y = host_load_canonical<fq_t>(s + 4);
+        acc = acc.add_mixed(p);
+    }
+    affine_to_abi(acc.to_affine(), out_xy);
+    return PK_OK;
+}
+
 int pk_ec_intt_g1(pk_ctx* ctx, uint32_t log_n, uint64_t* out_xy) {
     PK_API_BEGIN(ctx)
     PK_REQUIRE(out_xy != nullptr, PK_ERR_INVALID, "null output");

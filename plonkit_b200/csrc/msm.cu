@@ -145,22 +145,38 @@ __global__ void msm_digits_kernel(ScalarSets sets, uint32_t n, uint32_t table_n,
     fr_t k = ld_fp(sets.s[blockIdx.y] + i).from_mont();
     if (k.is_zero()) return;
     uint32_t carry = 0;
-    const uint32_t half = 1u << (c - 1);
+    const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1;
     const uint32_t set_base = blockIdx.y * half;
-    for (int w = 0; w < W; ++w) {
-        uint32_t d = raw_window(k.v, w, c) + carry;
+    // sliding bit window over the limbs: registers only (no dynamically indexed limb array)
+    uint64_t acc = 0;
+    int nbits = 0, w = 0;
+    auto emit = [&](uint32_t raw) {
+        uint32_t d = raw + carry;
         uint32_t neg = 0;
         if (d > half) { d = (1u << c) - d; neg = 1; carry = 1; } else carry = 0;
-        if (d == 0) continue;
-        uint32_t b = set_base + d - 1;
-        if (MODE == 0) {
-            atomicAdd(hist_or_cursor + b, 1u);
-        } else {
-            uint32_t pos = atomicAdd(hist_or_cursor + b, 1u);
-            keys[pos] = b;
-            items[pos] = ((uint32_t)w * table_n + base_offset + i) | (neg << 31);
+        if (d != 0) {
+            uint32_t b = set_base + d - 1;
+            if (MODE == 0) {
+                atomicAdd(hist_or_cursor + b, 1u);
+            } else {
+                uint32_t pos = atomicAdd(hist_or_cursor + b, 1u);
+                keys[pos] = b;
+                items[pos] = ((uint32_t)w * table_n + base_offset + i) | (neg << 31);
+            }
+        }
+        ++w;
+    };
+#pragma unroll
+    for (int limb = 0; limb < 8; ++limb) {
+        acc |= (uint64_t)k.v[limb] << nbits;
+        nbits += 32;
+        while (nbits >= c && w < W) {
+            emit((uint32_t)acc & mask);
+            acc >>= c;
+            nbits -= c;
         }
     }
+    if (w < W) emit((uint32_t)acc & mask);  // top window: the remaining (< c) bits
 }
 
 // ---------------------------------------------------------------- exclusive scan of the histogram (tiles of 4096)

@@ -364,8 +364,15 @@ __global__ void __launch_bounds__(256) quotient_kernel(QuotKernelArgs q) {
 
     fr_t a = ld_fp(q.a.w[0] + idx), b = ld_fp(q.a.w[1] + idx), c = ld_fp(q.a.w[2] + idx), d = ld_fp(q.a.w[3] + idx);
     fr_t gate = ld_fp(q.a.sel[0] + idx) * a + ld_fp(q.a.sel[1] + idx) * b + ld_fp(q.a.sel[2] + idx) * c + ld_fp(q.a.sel[3] + idx) * d +
-                ld_fp(q.a.sel[4] + idx) * (a * b) + ld_fp(q.a.sel[5] + idx) + ld_fp(q.a.sel[6] + idx) * ld_fp(q.a.w[3] + idn) +
-                ld_fp(q.a.pi + idx);
+                ld_fp(q.a.sel[4] + idx) * (a * b) + ld_fp(q.a.sel[5] + idx) + ld_fp(q.a.sel[6] + idx) * ld_fp(q.a.w[3] + idn);
+    if (q.a.num_direct_inputs < 0) {
+        gate = gate + ld_fp(q.a.pi + idx);
+    } else {
+        for (int i = 0; i < q.a.num_direct_inputs; ++i) {
+            const uint32_t pj = brev_n((j - (uint32_t)i) & (uint32_t)(n - 1), log_n);
+            gate = gate + q.a.inputs[i] * ld_fp(q.a.l0 + ((size_t)s << log_n) + pj);
+        }
+    }
     fr_t zv = ld_fp(q.a.z + idx), zn = ld_fp(q.a.z + idn);
     fr_t bx = q.bg[s] * omega_pow(q.tw, q.tw_shift, log_n, j);
     fr_t ag = a + q.a.gamma, bgm = b + q.a.gamma, cg = c + q.a.gamma, dg = d + q.a.gamma;

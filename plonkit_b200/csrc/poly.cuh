@@ -45,7 +45,11 @@ struct QuotientArgs {
     const fr_t* z;
     const fr_t* sel[7];
     const fr_t* sig[4];
-    const fr_t* pi;
+    const fr_t* pi;        // LDE of the public-input polynomial; only read when num_direct_inputs < 0
+    // PI(X) = sum_i in_i L_i(X) with L_i(X) = L_0(X w^-i): for a handful of inputs it is evaluated straight from
+    // the resident L_0 table (index shift inside the slot) and needs no NTT at all
+    int num_direct_inputs; // >= 0: use inputs[]; < 0: use the pi array
+    fr_t inputs[8];
     const fr_t* l0;
     fr_t* out;
     fr_t beta, gamma, alpha;

@@ -242,12 +242,19 @@ void prove(pk_ctx* ctx, pk_setup* s, const uint64_t* var_values, uint64_t nvars,
     // ---- round 3: quotient on the coset 7*H_4n
     for (int c = 0; c < 4; ++c) lde4_slots(ctx, s->w_coef.p + c * n, s->w_lde.p + 4 * c * n, log_n);
     lde4_slots(ctx, s->z_coef.p, s->z_lde.p, log_n);
-    PK_CUDA(cudaMemsetAsync(s->tmp_c.p, 0, n * sizeof(fr_t), st));
-    pi_scatter(ctx, s->w_nat.p, s->tmp_c.p, ni, log_n);
-    ntt_inverse_from_bitrev(ctx, s->tmp_c.p, s->pi_coef.p, log_n);
-    lde4_slots(ctx, s->pi_coef.p, s->pi_lde.p, log_n);
     CosetTables* ct = get_coset_tables(ctx, log_n);
     QuotientArgs qa;
+    if (ni <= 8) {
+        // PI(X) = sum_i in_i L_0(X w^-i): read off the resident L_0 table inside the quotient kernel, no NTT
+        qa.num_direct_inputs = (int)ni;
+        for (uint32_t i = 0; i < ni; ++i) qa.inputs[i] = inputs[i];
+    } else {
+        qa.num_direct_inputs = -1;
+        PK_CUDA(cudaMemsetAsync(s->tmp_c.p, 0, n * sizeof(fr_t), st));
+        pi_scatter(ctx, s->w_nat.p, s->tmp_c.p, ni, log_n);
+        ntt_inverse_from_bitrev(ctx, s->tmp_c.p, s->pi_coef.p, log_n);
+        lde4_slots(ctx, s->pi_coef.p, s->pi_lde.p, log_n);
+    }
     for (int c = 0; c < 4; ++c) { qa.w[c] = s->w_lde.p + 4 * c * n; qa.sig[c] = s->sigma_lde.p + 4 * c * n; }
     for (int k = 0; k < 7; ++k) qa.sel[k] = s->sel_lde.p + 4 * k * n;
     qa.z = s->z_lde.p; qa.pi = s->pi_lde.p; qa.l0 = ct->l0.p; qa.out = s->t4.p;

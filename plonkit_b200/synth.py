@@ -147,16 +147,18 @@ def _evaluate_chain(pattern, perms, body, inputs):
     return vals
 
 
-def random_gate_assembly(log_n: int, seed: int = SEED, reuse: float = 0.5) -> Assembly:
+def random_gate_assembly(log_n: int, seed: int = SEED, reuse: float = 0.5, num_inputs: int = 1) -> Assembly:
     """BASELINE config 3 shape: 2^log_n - 1 gates, half multiplication gates c = a*b, half addition gates c = a + b + k;
-    every operand re-uses an earlier variable with probability `reuse` (non-trivial copy permutation).  1 public input."""
+    every operand re-uses an earlier variable with probability `reuse` (non-trivial copy permutation).
+    `num_inputs` public inputs (variables 1..num_inputs, one input gate each)."""
     import random
     rnd = random.Random(seed)
     n = 1 << log_n
     n_gates = n - 1
     rows = []
-    vals = [0, rnd.randrange(R_MOD)]
-    rows.append((1, 0, 0, 0, [R_MOD - 1, 0, 0, 0, 0, 0, 0]))
+    vals = [0] + [rnd.randrange(R_MOD) for _ in range(num_inputs)]
+    for i in range(1, num_inputs + 1):
+        rows.append((i, 0, 0, 0, [R_MOD - 1, 0, 0, 0, 0, 0, 0]))
 
     def operand():
         if len(vals) > 2 and rnd.random() < reuse:
@@ -174,4 +176,4 @@ def random_gate_assembly(log_n: int, seed: int = SEED, reuse: float = 0.5) -> As
             vals.append((vals[a] + vals[b] + k) % R_MOD)
             rows.append((a, b, len(vals) - 1, 0, [1, 1, M1, 0, 0, k, 0]))
     from .circuit import assembly_from_rows
-    return assembly_from_rows(rows, vals, 1)
+    return assembly_from_rows(rows, vals, num_inputs)

@@ -1,0 +1,71 @@
+"""CPU tests (gloo, world_size 2 and 3) of the multi-GPU host logic: chunking, all-gather of partial sums and the
+local fold through the product's own pk_g1_sum.  The device MSM of each chunk is replaced by the checker here; the
+GPU test in tests/test_gpu_dist.py runs the same class with the CUDA MSM."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, SIMPLE
+from plonkit_b200 import _lib, dist, reader, synth
+
+
+def test_chunk_bounds_partition_everything():
+    for n in (1, 7, 8, 1000, 1 << 20):
+        for world in (1, 2, 3, 8):
+            edges = [dist.chunk_bounds(n, world, r) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in edges]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_g1_sum_host_fold(orc, simple_key):
+    g = simple_key.g1_bases
+    assert (_lib.g1_sum(g[:5]) == orc.msm(np.tile(np.array([1, 0, 0, 0], dtype=np.uint64), (5, 1)), g[:5])).all()
+    inf = np.zeros(8, dtype=np.uint64)
+    assert (_lib.g1_sum(np.stack([inf, g[3], inf])) == g[3]).all()
+    assert not _lib.g1_sum(np.zeros((0, 8), dtype=np.uint64)).any()
+    neg = g[4].copy()
+    from plonkit_b200.bn254 import Q_MOD, ints_to_limbs, limbs_to_ints
+    neg[4:] = ints_to_limbs([Q_MOD - limbs_to_ints(g[4][4:])[0]])[0]
+    assert not _lib.g1_sum(np.stack([g[4], neg])).any()
+    assert (_lib.g1_sum(np.stack([g[4], g[4]])) == orc.g1_add(g[4], g[4])).all()
+
+
+def _worker(rank, world, port, ret):
+    import torch.distributed as td
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    td.init_process_group(backend="gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, ROOT)
+        from oracle import oracle as orc
+        key = reader.load_key_monomial_form(os.path.join(SIMPLE, "setup_2^10.key"))
+        n = 1000  # not divisible by 3: uneven chunks
+        bases = key.g1_bases[:n]
+        committer = dist.ShardedCommitter(bases, rank, world, local_msm=lambda s, b: orc.msm(s, b, threads=2))
+        s = synth.random_field_elements(n, seed=77)
+        s[::9] = 0
+        got = committer.commit(s)
+        want = orc.msm(s, bases, threads=2)
+        ret[rank] = bool((got == want).all())
+        # wrong length -> AssignmentMissing on every rank, before any collective is entered
+        try:
+            committer.commit(s[:10])
+            ret[rank] = False
+        except _lib.SynthesisError as e:
+            ret[rank] = ret[rank] and e.code == 1
+    finally:
+        td.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_commit_over_gloo(world):
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29610 + world
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert [ret[r] for r in range(world)] == [True] * world

@@ -64,6 +64,19 @@ def test_proofs_equal_oracle_on_synthetic_circuits(ctx, orc, kind, log_n):
     assert orc.verify_trapdoor(proof.to_bytes(), com, 42)
 
 
+@pytest.mark.parametrize("num_inputs", [0, 3, 8, 9, 20])
+def test_public_input_polynomial_paths(ctx, orc, num_inputs):
+    """<= 8 inputs: PI(X) is read off the resident L_0 table; more: iNTT + LDE.  Both must give the oracle's bytes."""
+    asm = synth.random_gate_assembly(8, seed=40 + num_inputs, num_inputs=num_inputs)
+    assert asm.num_inputs == num_inputs and circuit.is_satisfied(asm)
+    srs = orc.srs_gen(asm.n, 42, threads=4)
+    from plonkit_b200.reader import Crs
+    setup = plonk.SetupForProver.prepare_setup_for_prover(asm, Crs(srs, b""), None, ctx=ctx)
+    proof = setup.prove(asm)
+    assert proof.to_bytes() == orc.prove(asm.n, asm.num_inputs, asm.wire_idx, asm.var_values, asm.selectors, srs, threads=4)
+    assert len(proof.input_values) == num_inputs
+
+
 def test_error_behaviour_mirrors_reference(ctx, orc, simple_circuit, simple_key):
     setup = plonk.SetupForProver.prepare_setup_for_prover(simple_circuit, simple_key, None, ctx=ctx)
     # wrong witness: the reference panics in is_satisfied_using_one_shot_check ("must satisfy", src/plonk.rs:137)
