@@ -77,6 +77,7 @@ def dist_setup(n_gpus):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     td = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("PK_NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout
         import torch
         import torch.distributed as td_
         torch.cuda.set_device(local)

@@ -13,9 +13,10 @@
 //     through the kernels together: bucket ids are (set, bucket), so one sort, one accumulation and one reduction
 //     serve up to 4 scalar sets and the latency-bound tail kernels are paid once per round instead of once per MSM.
 //   * kernels (each its own launch, as named in BASELINE.json's north star):
-//       window scan      msm_digits_kernel<0>     scalar -> signed base-2^c digits, bucket histogram
-//       offsets          u32_scan_*               exclusive scan of the histogram (3 small launches)
-//       scatter          msm_digits_kernel<1>     counting sort of (table index, sign) by bucket
+//       window scan      msm_coarse_kernel<false> scalar -> signed base-2^c digits, coarse-bin histogram (shared memory)
+//       offsets          u32_scan_*               exclusive scan of the coarse histogram
+//       scatter          msm_coarse_kernel<true>  partition of (bucket, table index | sign) entries by coarse bin
+//                        msm_fine_sort_kernel     per-bin counting sort by bucket, histogram in shared memory
 //       bucket accum     msm_accum_kernel<true>   mixed XYZZ additions; load-balanced segmented reduction:
 //                                                 every thread owns a fixed-length chunk of the sorted list,
 //                                                 whole runs go straight to their bucket, runs cut by a chunk
@@ -101,12 +102,17 @@ void srs_load(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits
     const int nb = max_batch_for(s);
     size_t M = (size_t)n * W;
     size_t NB = (size_t)nb * s->B;
-    s->hist.alloc(NB);
-    s->offsets.alloc(NB + 1);
-    s->cursor.alloc(NB);
-    s->scan_sums.alloc((NB + 4095) / 4096 + 1);
-    s->keys.alloc(nb * M);
-    s->items.alloc(nb * M);
+    {
+        int lg = ilog2(NB);
+        s->fine_bits_max = lg < 12 ? lg : (lg - 12 > 12 ? lg - 12 : 12);
+        size_t ncmax = (NB >> s->fine_bits_max) + 2;
+        s->coarse_count.alloc(ncmax);
+        s->coarse_offset.alloc(ncmax);
+        s->coarse_cursor.alloc(ncmax);
+        s->scan_sums.alloc(ncmax / 4096 + 2);
+    }
+    s->entries.alloc(nb * M);
+    s->tmp_entries.alloc(nb * M);
     s->buckets.alloc(NB);
     // level-1 chunk: keep the chunk count of one scalar set <= 2^19 so the partial lists stay small
     uint32_t chunk = 64;
@@ -123,47 +129,24 @@ void srs_load(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits
     PK_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
-// ---------------------------------------------------------------- window scan: signed digits
-// digit w of canonical scalar k (8 x 32-bit LE limbs), before carry handling
-__device__ __forceinline__ uint32_t raw_window(const uint32_t* k, int w, int c) {
-    int pos = w * c;
-    if (pos >= 256) return 0;
-    int limb = pos >> 5, off = pos & 31;
-    uint32_t v = k[limb] >> off;
-    if (off && limb < 7) v |= k[limb + 1] << (32 - off);
-    return v & ((1u << c) - 1);
-}
-
+// ---------------------------------------------------------------- window scan + sort by bucket (two-level radix partition)
+// Entries are (bucket id, table index | sign << 31).  Bucket ids are global: set * B + bucket.  They are sorted by a
+// coarse partition on the high bits (block-local shared-memory histograms, one global atomic per (block, bin)) followed
+// by a per-bin counting sort on the low `fine_bits` bits held entirely in shared memory.  Global atomics per batch drop
+// from one per digit (54 M at N = 2^20 x 4 sets) to one per (block, coarse bin).
 struct ScalarSets { const fr_t* s[MSM_MAX_BATCH]; };
 
-// MODE 0: histogram; MODE 1: scatter.  blockIdx.y = scalar set; bucket ids are set * B + bucket.
-template <int MODE>
-__global__ void msm_digits_kernel(ScalarSets sets, uint32_t n, uint32_t table_n, uint32_t base_offset, int c, int W,
-                                  uint32_t* hist_or_cursor, uint32_t* keys, uint32_t* items) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    fr_t k = ld_fp(sets.s[blockIdx.y] + i).from_mont();
-    if (k.is_zero()) return;
+// calls f(w, global_bucket, neg) for every non-zero signed base-2^c digit of the canonical scalar k
+template <class F> __device__ __forceinline__ void for_each_digit(const fr_t& k, int c, int W, uint32_t set_base, F f) {
     uint32_t carry = 0;
     const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1;
-    const uint32_t set_base = blockIdx.y * half;
-    // sliding bit window over the limbs: registers only (no dynamically indexed limb array)
-    uint64_t acc = 0;
+    uint64_t acc = 0;  // sliding bit window over the limbs: registers only
     int nbits = 0, w = 0;
     auto emit = [&](uint32_t raw) {
         uint32_t d = raw + carry;
         uint32_t neg = 0;
         if (d > half) { d = (1u << c) - d; neg = 1; carry = 1; } else carry = 0;
-        if (d != 0) {
-            uint32_t b = set_base + d - 1;
-            if (MODE == 0) {
-                atomicAdd(hist_or_cursor + b, 1u);
-            } else {
-                uint32_t pos = atomicAdd(hist_or_cursor + b, 1u);
-                keys[pos] = b;
-                items[pos] = ((uint32_t)w * table_n + base_offset + i) | (neg << 31);
-            }
-        }
+        if (d != 0) f((uint32_t)w, set_base + d - 1, neg);
         ++w;
     };
 #pragma unroll
@@ -177,6 +160,91 @@ __global__ void msm_digits_kernel(ScalarSets sets, uint32_t n, uint32_t table_n,
         }
     }
     if (w < W) emit((uint32_t)acc & mask);  // top window: the remaining (< c) bits
+}
+
+// SCATTER = false: coarse_counts[bin] += digits of this block in bin.
+// SCATTER = true : reserves a range per (block, bin) in coarse_cursor and writes the entries there.
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) msm_coarse_kernel(ScalarSets sets, uint32_t n, uint32_t table_n, uint32_t base_offset, int c, int W,
+                                                         int fine_bits, uint32_t NC, uint32_t* coarse, uint2* tmp) {
+    extern __shared__ uint32_t sh[];  // cnt[NC] (+ base[NC] when scattering)
+    uint32_t* cnt = sh;
+    uint32_t* base = sh + NC;
+    for (uint32_t b = threadIdx.x; b < NC; b += blockDim.x) cnt[b] = 0;
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t set_base = blockIdx.y << (c - 1);
+    fr_t k = fr_t::zero();
+    if (i < n) k = ld_fp(sets.s[blockIdx.y] + i).from_mont();
+    const bool live = !k.is_zero();
+    if (live) for_each_digit(k, c, W, set_base, [&](uint32_t, uint32_t g, uint32_t) { atomicAdd(&cnt[g >> fine_bits], 1u); });
+    __syncthreads();
+    if (!SCATTER) {
+        for (uint32_t b = threadIdx.x; b < NC; b += blockDim.x)
+            if (cnt[b]) atomicAdd(coarse + b, cnt[b]);
+        return;
+    }
+    for (uint32_t b = threadIdx.x; b < NC; b += blockDim.x) {
+        if (cnt[b]) base[b] = atomicAdd(coarse + b, cnt[b]);
+        cnt[b] = 0;
+    }
+    __syncthreads();
+    if (live)
+        for_each_digit(k, c, W, set_base, [&](uint32_t w, uint32_t g, uint32_t neg) {
+            const uint32_t bin = g >> fine_bits;
+            const uint32_t slot = atomicAdd(&cnt[bin], 1u);
+            tmp[base[bin] + slot] = make_uint2(g, (w * table_n + base_offset + i) | (neg << 31));
+        });
+}
+
+// counting sort of one coarse bin by the low fine_bits of the bucket id, histogram in shared memory; same-key lanes of
+// a warp are aggregated so heavily repeated digits (all-equal scalars) do not serialise on one counter
+__global__ void __launch_bounds__(512) msm_fine_sort_kernel(const uint2* tmp, uint2* entries, const uint32_t* coarse_offset, int fine_bits) {
+    extern __shared__ uint32_t hist[];  // [2^fine_bits] then 512 scan partials
+    const uint32_t F = 1u << fine_bits, fmask = F - 1;
+    uint32_t* part = hist + F;
+    const uint32_t lo = coarse_offset[blockIdx.x], hi = coarse_offset[blockIdx.x + 1];
+    if (lo == hi) return;
+    for (uint32_t b = threadIdx.x; b < F; b += blockDim.x) hist[b] = 0;
+    __syncthreads();
+    const uint32_t span = hi - lo, rounds = (span + blockDim.x - 1) / blockDim.x;
+    const unsigned lane = threadIdx.x & 31;
+    for (uint32_t r = 0; r < rounds; ++r) {
+        const uint32_t e = lo + r * blockDim.x + threadIdx.x;
+        const bool ok = e < hi;
+        const uint32_t key = ok ? (tmp[e].x & fmask) : 0xffffffffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (ok && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[key], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    // exclusive scan of hist[0..F): each thread owns F / blockDim consecutive counters
+    const uint32_t per = (F + blockDim.x - 1) / blockDim.x;
+    const uint32_t b0 = threadIdx.x * per, b1 = (b0 + per < F) ? b0 + per : F;
+    uint32_t sum = 0;
+    for (uint32_t b = b0; b < b1; ++b) sum += hist[b];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (unsigned d = 1; d < blockDim.x; d <<= 1) {
+        uint32_t t = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
+        __syncthreads();
+        part[threadIdx.x] += t;
+        __syncthreads();
+    }
+    uint32_t run = part[threadIdx.x] - sum;
+    for (uint32_t b = b0; b < b1; ++b) { uint32_t x = hist[b]; hist[b] = run; run += x; }
+    __syncthreads();
+    for (uint32_t r = 0; r < rounds; ++r) {
+        const uint32_t e = lo + r * blockDim.x + threadIdx.x;
+        const bool ok = e < hi;
+        uint2 ent = ok ? tmp[e] : make_uint2(0xffffffffu, 0);
+        const uint32_t key = ok ? (ent.x & fmask) : 0xffffffffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const unsigned leader = __ffs(peers) - 1;
+        uint32_t basepos = 0;
+        if (ok && lane == leader) basepos = atomicAdd(&hist[key], (uint32_t)__popc(peers));
+        basepos = __shfl_sync(0xffffffffu, basepos, leader);
+        if (ok) entries[lo + basepos + __popc(peers & ((1u << lane) - 1))] = ent;
+    }
 }
 
 // ---------------------------------------------------------------- exclusive scan of the histogram (tiles of 4096)
@@ -230,8 +298,8 @@ __global__ void __launch_bounds__(1024) u32_scan_apply_kernel(const uint32_t* in
 
 // ---------------------------------------------------------------- bucket accumulation (segmented reduction over the sorted list)
 struct AccumParams {
-    const uint32_t* keys;       // sorted bucket ids of this level's entries
-    const uint32_t* items;      // level 1: table index | sign << 31
+    const uint32_t* keys;       // level >= 2: sorted bucket ids of this level's entries
+    const uint2* ent;           // level 1: sorted (bucket id, table index | sign << 31)
     const g1_xyzz_t* pts;       // level >= 2: partial sums
     const g1_affine_t* table;
     const uint32_t* count_in;   // number of entries of this level (device)
@@ -250,15 +318,18 @@ template <bool LEVEL1> __global__ void __launch_bounds__(128) msm_accum_kernel(A
     if (t >= nchunks) return;
     const uint32_t s = t * p.chunk;
     const uint32_t e = (s + p.chunk < count) ? s + p.chunk : count;
-    const bool head_partial = s > 0 && p.keys[s - 1] == p.keys[s];
-    const bool tail_partial = e < count && p.keys[e] == p.keys[e - 1];
-    const uint32_t first_key = p.keys[s];
+    auto key_at = [&](uint32_t i) -> uint32_t { return LEVEL1 ? p.ent[i].x : p.keys[i]; };
+    const bool head_partial = s > 0 && key_at(s - 1) == key_at(s);
+    const bool tail_partial = e < count && key_at(e) == key_at(e - 1);
+    const uint32_t first_key = key_at(s);
     uint32_t cur = first_key;
     bool in_head = true;
     g1_xyzz_t acc = g1_xyzz_t::infinity();
     const g1_xyzz_t inf = g1_xyzz_t::infinity();
     for (uint32_t i = s; i < e; ++i) {
-        const uint32_t k = p.keys[i];
+        uint2 en = make_uint2(0, 0);
+        if (LEVEL1) en = p.ent[i];
+        const uint32_t k = LEVEL1 ? en.x : p.keys[i];
         if (k != cur) {
             if (in_head && head_partial) st_xyzz(p.out_pts + 2 * (size_t)t, acc);
             else if (!acc.is_inf()) st_xyzz(p.buckets + cur, acc);
@@ -267,7 +338,7 @@ template <bool LEVEL1> __global__ void __launch_bounds__(128) msm_accum_kernel(A
             cur = k;
         }
         if (LEVEL1) {
-            const uint32_t it = p.items[i];
+            const uint32_t it = en.y;
             g1_affine_t pt = ldg_affine(p.table + (it & 0x7fffffffu));
             if (it >> 31) pt.y = pt.y.neg();
             acc = acc.add_mixed(pt);
@@ -367,17 +438,23 @@ static void msm_run_group(pk_ctx* ctx, const fr_t* const* scalars, int nb, uint6
     const uint32_t NB = (uint32_t)nb * B;
     ScalarSets sets;
     for (int k = 0; k < MSM_MAX_BATCH; ++k) sets.s[k] = scalars[k < nb ? k : 0];
-    PK_CUDA(cudaMemsetAsync(s->hist.p, 0, (size_t)NB * sizeof(uint32_t), st));
+    const int lg = ilog2(NB);
+    const int fine_bits = lg < 12 ? lg : (lg - 12 > 12 ? lg - 12 : 12);
+    const uint32_t NC = NB >> fine_bits;
+    PK_CUDA(cudaMemsetAsync(s->coarse_count.p, 0, (size_t)(NC + 1) * sizeof(uint32_t), st));
     PK_CUDA(cudaMemsetAsync(s->buckets.p, 0, (size_t)NB * sizeof(g1_xyzz_t), st));
     dim3 dgrid((unsigned)((n + 255) / 256), nb);
-    msm_digits_kernel<0><<<dgrid, 256, 0, st>>>(sets, (uint32_t)n, (uint32_t)s->n, (uint32_t)base_offset, s->c, s->W, s->hist.p, nullptr, nullptr);
-    const uint32_t tiles = (NB + 4095) / 4096;
-    u32_scan_tile_sums_kernel<<<tiles, 1024, 0, st>>>(s->hist.p, s->scan_sums.p, NB);
-    u32_scan_spine_kernel<<<1, 1024, 0, st>>>(s->scan_sums.p, tiles, s->counts.p, s->offsets.p + NB);
-    u32_scan_apply_kernel<<<tiles, 1024, 0, st>>>(s->hist.p, s->scan_sums.p, s->offsets.p, s->cursor.p, NB);
-    msm_digits_kernel<1><<<dgrid, 256, 0, st>>>(sets, (uint32_t)n, (uint32_t)s->n, (uint32_t)base_offset, s->c, s->W, s->cursor.p, s->keys.p,
-                                                s->items.p);
-    ctx->prof.kernel_launches += 5;
+    msm_coarse_kernel<false><<<dgrid, 256, NC * sizeof(uint32_t), st>>>(sets, (uint32_t)n, (uint32_t)s->n, (uint32_t)base_offset, s->c, s->W,
+                                                                      fine_bits, NC, s->coarse_count.p, nullptr);
+    const uint32_t tiles = (NC + 4095) / 4096;
+    u32_scan_tile_sums_kernel<<<tiles, 1024, 0, st>>>(s->coarse_count.p, s->scan_sums.p, NC);
+    u32_scan_spine_kernel<<<1, 1024, 0, st>>>(s->scan_sums.p, tiles, s->counts.p, s->coarse_offset.p + NC);
+    u32_scan_apply_kernel<<<tiles, 1024, 0, st>>>(s->coarse_count.p, s->scan_sums.p, s->coarse_offset.p, s->coarse_cursor.p, NC);
+    msm_coarse_kernel<true><<<dgrid, 256, 2 * NC * sizeof(uint32_t), st>>>(sets, (uint32_t)n, (uint32_t)s->n, (uint32_t)base_offset, s->c, s->W,
+                                                                         fine_bits, NC, s->coarse_cursor.p, s->tmp_entries.p);
+    msm_fine_sort_kernel<<<NC, 512, ((size_t(1) << fine_bits) + 512) * sizeof(uint32_t), st>>>(s->tmp_entries.p, s->entries.p,
+                                                                                            s->coarse_offset.p, fine_bits);
+    ctx->prof.kernel_launches += 6;
     // accumulation levels (worst-case grids; the device-side counts bound the real work)
     size_t max_entries = (size_t)nb * n * s->W;
     AccumParams p;
@@ -386,11 +463,11 @@ static void msm_run_group(pk_ctx* ctx, const fr_t* const* scalars, int nb, uint6
     p.buckets = s->buckets.p;
     int level = 0;
     uint32_t chunk = s->chunk1;
-    const uint32_t* keys = s->keys.p;
+    const uint32_t* keys = nullptr;
     while (true) {
         size_t nchunks = (max_entries + chunk - 1) / chunk;
         p.keys = keys;
-        p.items = s->items.p;
+        p.ent = s->entries.p;
         p.pts = level == 0 ? nullptr : s->ppts[(level - 1) & 1].p;
         p.count_in = s->counts.p + level;
         p.count_out = s->counts.p + level + 1;

@@ -15,11 +15,10 @@ struct SrsTables {
     DevBuf<g1_affine_t> table;   // [W][n]: table[w][i] = 2^(c*w) * base_i, affine, Montgomery form
 
     // scratch, sized for MSM_MAX_BATCH scalar sets of n pairs
-    DevBuf<uint32_t> hist;       // [nb*B]
-    DevBuf<uint32_t> offsets;    // [nb*B + 1]
-    DevBuf<uint32_t> cursor;     // [nb*B]
+    int fine_bits_max = 0;
+    DevBuf<uint32_t> coarse_count, coarse_offset, coarse_cursor;  // [NC + 1] coarse-bin histogram / offsets / cursors
     DevBuf<uint32_t> scan_sums;  // block sums of the offsets scan
-    DevBuf<uint32_t> keys, items;        // [nb * n * W]
+    DevBuf<uint2> entries, tmp_entries;  // [nb * n * W] (bucket id, table index | sign << 31): sorted / partitioned
     DevBuf<g1_xyzz_t> buckets;           // [nb*B]
     DevBuf<uint32_t> pkeys[2];           // partial-run lists (ping-pong between levels)
     DevBuf<g1_xyzz_t> ppts[2];
