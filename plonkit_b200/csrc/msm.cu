@@ -197,8 +197,7 @@ __global__ void __launch_bounds__(256) msm_coarse_kernel(ScalarSets sets, uint32
         });
 }
 
-// counting sort of one coarse bin by the low fine_bits of the bucket id, histogram in shared memory; same-key lanes of
-// a warp are aggregated so heavily repeated digits (all-equal scalars) do not serialise on one counter
+// counting sort of one coarse bin by the low fine_bits of the bucket id; histogram and cursors live in shared memory
 __global__ void __launch_bounds__(512) msm_fine_sort_kernel(const uint2* tmp, uint2* entries, const uint32_t* coarse_offset, int fine_bits) {
     extern __shared__ uint32_t hist[];  // [2^fine_bits] then 512 scan partials
     const uint32_t F = 1u << fine_bits, fmask = F - 1;
@@ -207,19 +206,11 @@ __global__ void __launch_bounds__(512) msm_fine_sort_kernel(const uint2* tmp, ui
     if (lo == hi) return;
     for (uint32_t b = threadIdx.x; b < F; b += blockDim.x) hist[b] = 0;
     __syncthreads();
-    const uint32_t span = hi - lo, rounds = (span + blockDim.x - 1) / blockDim.x;
-    const unsigned lane = threadIdx.x & 31;
-    for (uint32_t r = 0; r < rounds; ++r) {
-        const uint32_t e = lo + r * blockDim.x + threadIdx.x;
-        const bool ok = e < hi;
-        const uint32_t key = ok ? (tmp[e].x & fmask) : 0xffffffffu;
-        const unsigned peers = __match_any_sync(0xffffffffu, key);
-        if (ok && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[key], (uint32_t)__popc(peers));
-    }
+    for (uint32_t e = lo + threadIdx.x; e < hi; e += blockDim.x) atomicAdd(&hist[tmp[e].x & fmask], 1u);
     __syncthreads();
     // exclusive scan of hist[0..F): each thread owns F / blockDim consecutive counters
     const uint32_t per = (F + blockDim.x - 1) / blockDim.x;
-    const uint32_t b0 = threadIdx.x * per, b1 = (b0 + per < F) ? b0 + per : F;
+    const uint32_t b0 = threadIdx.x * per < F ? threadIdx.x * per : F, b1 = (b0 + per < F) ? b0 + per : F;
     uint32_t sum = 0;
     for (uint32_t b = b0; b < b1; ++b) sum += hist[b];
     part[threadIdx.x] = sum;
@@ -233,17 +224,10 @@ __global__ void __launch_bounds__(512) msm_fine_sort_kernel(const uint2* tmp, ui
     uint32_t run = part[threadIdx.x] - sum;
     for (uint32_t b = b0; b < b1; ++b) { uint32_t x = hist[b]; hist[b] = run; run += x; }
     __syncthreads();
-    for (uint32_t r = 0; r < rounds; ++r) {
-        const uint32_t e = lo + r * blockDim.x + threadIdx.x;
-        const bool ok = e < hi;
-        uint2 ent = ok ? tmp[e] : make_uint2(0xffffffffu, 0);
-        const uint32_t key = ok ? (ent.x & fmask) : 0xffffffffu;
-        const unsigned peers = __match_any_sync(0xffffffffu, key);
-        const unsigned leader = __ffs(peers) - 1;
-        uint32_t basepos = 0;
-        if (ok && lane == leader) basepos = atomicAdd(&hist[key], (uint32_t)__popc(peers));
-        basepos = __shfl_sync(0xffffffffu, basepos, leader);
-        if (ok) entries[lo + basepos + __popc(peers & ((1u << lane) - 1))] = ent;
+    for (uint32_t e = lo + threadIdx.x; e < hi; e += blockDim.x) {
+        const uint2 ent = tmp[e];
+        const uint32_t pos = atomicAdd(&hist[ent.x & fmask], 1u);
+        entries[lo + pos] = ent;
     }
 }
 
@@ -440,7 +424,7 @@ static void msm_run_group(pk_ctx* ctx, const fr_t* const* scalars, int nb, uint6
     for (int k = 0; k < MSM_MAX_BATCH; ++k) sets.s[k] = scalars[k < nb ? k : 0];
     const int lg = ilog2(NB);
     const int fine_bits = lg < 12 ? lg : (lg - 12 > 12 ? lg - 12 : 12);
-    const uint32_t NC = NB >> fine_bits;
+    const uint32_t NC = (NB + (1u << fine_bits) - 1) >> fine_bits;
     PK_CUDA(cudaMemsetAsync(s->coarse_count.p, 0, (size_t)(NC + 1) * sizeof(uint32_t), st));
     PK_CUDA(cudaMemsetAsync(s->buckets.p, 0, (size_t)NB * sizeof(g1_xyzz_t), st));
     dim3 dgrid((unsigned)((n + 255) / 256), nb);
