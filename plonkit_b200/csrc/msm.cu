@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(256) msm_coarse_kernel(ScalarSets sets, uint32
 }
 
 // counting sort of one coarse bin by the low fine_bits of the bucket id; histogram and cursors live in shared memory
+#define FS_UNROLL 8
 __global__ void __launch_bounds__(512) msm_fine_sort_kernel(const uint2* tmp, uint2* entries, const uint32_t* coarse_offset, int fine_bits) {
     extern __shared__ uint32_t hist[];  // [2^fine_bits] then 512 scan partials
     const uint32_t F = 1u << fine_bits, fmask = F - 1;
@@ -206,7 +207,18 @@ __global__ void __launch_bounds__(512) msm_fine_sort_kernel(const uint2* tmp, ui
     if (lo == hi) return;
     for (uint32_t b = threadIdx.x; b < F; b += blockDim.x) hist[b] = 0;
     __syncthreads();
-    for (uint32_t e = lo + threadIdx.x; e < hi; e += blockDim.x) atomicAdd(&hist[tmp[e].x & fmask], 1u);
+    // the loops are latency-bound on the global loads: keep FS_UNROLL independent loads in flight per thread
+    for (uint32_t e0 = lo + threadIdx.x; e0 < hi; e0 += FS_UNROLL * blockDim.x) {
+        uint32_t key[FS_UNROLL];
+#pragma unroll
+        for (int u = 0; u < FS_UNROLL; ++u) {
+            const uint32_t e = e0 + u * blockDim.x;
+            key[u] = e < hi ? (tmp[e].x & fmask) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int u = 0; u < FS_UNROLL; ++u)
+            if (key[u] != 0xffffffffu) atomicAdd(&hist[key[u]], 1u);
+    }
     __syncthreads();
     // exclusive scan of hist[0..F): each thread owns F / blockDim consecutive counters
     const uint32_t per = (F + blockDim.x - 1) / blockDim.x;
@@ -224,10 +236,20 @@ __global__ void __launch_bounds__(512) msm_fine_sort_kernel(const uint2* tmp, ui
     uint32_t run = part[threadIdx.x] - sum;
     for (uint32_t b = b0; b < b1; ++b) { uint32_t x = hist[b]; hist[b] = run; run += x; }
     __syncthreads();
-    for (uint32_t e = lo + threadIdx.x; e < hi; e += blockDim.x) {
-        const uint2 ent = tmp[e];
-        const uint32_t pos = atomicAdd(&hist[ent.x & fmask], 1u);
-        entries[lo + pos] = ent;
+    for (uint32_t e0 = lo + threadIdx.x; e0 < hi; e0 += FS_UNROLL * blockDim.x) {
+        uint2 ent[FS_UNROLL];
+        uint32_t pos[FS_UNROLL];
+#pragma unroll
+        for (int u = 0; u < FS_UNROLL; ++u) {
+            const uint32_t e = e0 + u * blockDim.x;
+            ent[u] = e < hi ? tmp[e] : make_uint2(0xffffffffu, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < FS_UNROLL; ++u)
+            pos[u] = ent[u].x != 0xffffffffu ? atomicAdd(&hist[ent[u].x & fmask], 1u) : 0;
+#pragma unroll
+        for (int u = 0; u < FS_UNROLL; ++u)
+            if (ent[u].x != 0xffffffffu) entries[lo + pos[u]] = ent[u];
     }
 }
 
