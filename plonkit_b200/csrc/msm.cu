@@ -71,6 +71,14 @@ static int pick_window_bits(uint64_t n) {
     return best;
 }
 
+// coarse bins hold 2^fine_bits buckets: small enough that one bin's entries (~13 K at N = 2^20) stay in L2 while a block
+// sorts them, and at most 8192 bins so the per-block bin counters fit in shared memory
+static int msm_fine_bits(int lg_total_buckets) {
+    int fb = lg_total_buckets < 9 ? lg_total_buckets : 9;
+    if (lg_total_buckets - fb > 13) fb = lg_total_buckets - 13;
+    return fb;
+}
+
 static int max_batch_for(const SrsTables* s) {
     size_t M = (size_t)s->n * s->W;
     int nb = MSM_MAX_BATCH;
@@ -104,8 +112,11 @@ void srs_load(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits
     size_t NB = (size_t)nb * s->B;
     {
         int lg = ilog2(NB);
-        s->fine_bits_max = lg < 12 ? lg : (lg - 12 > 12 ? lg - 12 : 12);
+        s->fine_bits_max = msm_fine_bits(lg);
         size_t ncmax = (NB >> s->fine_bits_max) + 2;
+        // the coarse kernels keep two counters per bin in shared memory (up to 128 KB for the largest window sizes)
+        PK_CUDA(cudaFuncSetAttribute(msm_coarse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        PK_CUDA(cudaFuncSetAttribute(msm_coarse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         s->coarse_count.alloc(ncmax);
         s->coarse_offset.alloc(ncmax);
         s->coarse_cursor.alloc(ncmax);
@@ -162,6 +173,7 @@ template <class F> __device__ __forceinline__ void for_each_digit(const fr_t& k,
     if (w < W) emit((uint32_t)acc & mask);  // top window: the remaining (< c) bits
 }
 
+#define COARSE_PER_THREAD 16
 // SCATTER = false: coarse_counts[bin] += digits of this block in bin.
 // SCATTER = true : reserves a range per (block, bin) in coarse_cursor and writes the entries there.
 template <bool SCATTER>
@@ -172,12 +184,18 @@ __global__ void __launch_bounds__(256) msm_coarse_kernel(ScalarSets sets, uint32
     uint32_t* base = sh + NC;
     for (uint32_t b = threadIdx.x; b < NC; b += blockDim.x) cnt[b] = 0;
     __syncthreads();
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    // a block owns COARSE_PER_THREAD * blockDim consecutive scalars: many entries per (block, bin) keep the global
+    // atomics rare and the scattered runs long
+    const uint32_t i0 = blockIdx.x * (blockDim.x * COARSE_PER_THREAD) + threadIdx.x;
     const uint32_t set_base = blockIdx.y << (c - 1);
-    fr_t k = fr_t::zero();
-    if (i < n) k = ld_fp(sets.s[blockIdx.y] + i).from_mont();
-    const bool live = !k.is_zero();
-    if (live) for_each_digit(k, c, W, set_base, [&](uint32_t, uint32_t g, uint32_t) { atomicAdd(&cnt[g >> fine_bits], 1u); });
+    const fr_t* src = sets.s[blockIdx.y];
+    for (int r = 0; r < COARSE_PER_THREAD; ++r) {
+        const uint32_t i = i0 + r * blockDim.x;
+        if (i >= n) break;
+        fr_t k = ld_fp(src + i).from_mont();
+        if (k.is_zero()) continue;
+        for_each_digit(k, c, W, set_base, [&](uint32_t, uint32_t g, uint32_t) { atomicAdd(&cnt[g >> fine_bits], 1u); });
+    }
     __syncthreads();
     if (!SCATTER) {
         for (uint32_t b = threadIdx.x; b < NC; b += blockDim.x)
@@ -189,12 +207,17 @@ __global__ void __launch_bounds__(256) msm_coarse_kernel(ScalarSets sets, uint32
         cnt[b] = 0;
     }
     __syncthreads();
-    if (live)
+    for (int r = 0; r < COARSE_PER_THREAD; ++r) {
+        const uint32_t i = i0 + r * blockDim.x;
+        if (i >= n) break;
+        fr_t k = ld_fp(src + i).from_mont();
+        if (k.is_zero()) continue;
         for_each_digit(k, c, W, set_base, [&](uint32_t w, uint32_t g, uint32_t neg) {
             const uint32_t bin = g >> fine_bits;
             const uint32_t slot = atomicAdd(&cnt[bin], 1u);
             tmp[base[bin] + slot] = make_uint2(g, (w * table_n + base_offset + i) | (neg << 31));
         });
+    }
 }
 
 // counting sort of one coarse bin by the low fine_bits of the bucket id; histogram and cursors live in shared memory
@@ -445,11 +468,11 @@ static void msm_run_group(pk_ctx* ctx, const fr_t* const* scalars, int nb, uint6
     ScalarSets sets;
     for (int k = 0; k < MSM_MAX_BATCH; ++k) sets.s[k] = scalars[k < nb ? k : 0];
     const int lg = ilog2(NB);
-    const int fine_bits = lg < 12 ? lg : (lg - 12 > 12 ? lg - 12 : 12);
+    const int fine_bits = msm_fine_bits(lg);
     const uint32_t NC = (NB + (1u << fine_bits) - 1) >> fine_bits;
     PK_CUDA(cudaMemsetAsync(s->coarse_count.p, 0, (size_t)(NC + 1) * sizeof(uint32_t), st));
     PK_CUDA(cudaMemsetAsync(s->buckets.p, 0, (size_t)NB * sizeof(g1_xyzz_t), st));
-    dim3 dgrid((unsigned)((n + 255) / 256), nb);
+    dim3 dgrid((unsigned)((n + 256 * COARSE_PER_THREAD - 1) / (256 * COARSE_PER_THREAD)), nb);
     msm_coarse_kernel<false><<<dgrid, 256, NC * sizeof(uint32_t), st>>>(sets, (uint32_t)n, (uint32_t)s->n, (uint32_t)base_offset, s->c, s->W,
                                                                       fine_bits, NC, s->coarse_count.p, nullptr);
     const uint32_t tiles = (NC + 4095) / 4096;
