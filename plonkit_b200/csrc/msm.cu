@@ -35,6 +35,11 @@ namespace pk {
 
 static inline dim3 grid1d(size_t n, int block) { return dim3((unsigned)((n + block - 1) / block)); }
 
+struct ScalarSets { const fr_t* s[MSM_MAX_BATCH]; };
+template <bool SCATTER>
+__global__ void msm_coarse_kernel(ScalarSets sets, uint32_t n, uint32_t table_n, uint32_t base_offset, int c, int W, int fine_bits,
+                                  uint32_t NC, uint32_t* coarse, uint2* tmp);
+
 // ---------------------------------------------------------------- SRS upload + window tables
 __global__ void bases_to_mont_kernel(g1_affine_t* pts, size_t n) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -145,7 +150,6 @@ void srs_load(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits
 // coarse partition on the high bits (block-local shared-memory histograms, one global atomic per (block, bin)) followed
 // by a per-bin counting sort on the low `fine_bits` bits held entirely in shared memory.  Global atomics per batch drop
 // from one per digit (54 M at N = 2^20 x 4 sets) to one per (block, coarse bin).
-struct ScalarSets { const fr_t* s[MSM_MAX_BATCH]; };
 
 // calls f(w, global_bucket, neg) for every non-zero signed base-2^c digit of the canonical scalar k
 template <class F> __device__ __forceinline__ void for_each_digit(const fr_t& k, int c, int W, uint32_t set_base, F f) {
