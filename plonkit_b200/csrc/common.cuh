@@ -101,16 +101,17 @@ struct ScopedKernelTimer {
     int kind;
     uint64_t units;
     cudaEvent_t a = nullptr, b = nullptr;
-    ScopedKernelTimer(pk_ctx* c, int k, uint64_t u) : ctx(c), kind(k), units(u) {
+    cudaStream_t stream;
+    ScopedKernelTimer(pk_ctx* c, int k, uint64_t u, cudaStream_t st = nullptr) : ctx(c), kind(k), units(u), stream(st ? st : c->stream) {
         if (ctx->prof.enabled) {
             cudaEventCreate(&a);
             cudaEventCreate(&b);
-            cudaEventRecord(a, ctx->stream);
+            cudaEventRecord(a, stream);
         }
     }
     ~ScopedKernelTimer() {
         if (a) {
-            cudaEventRecord(b, ctx->stream);
+            cudaEventRecord(b, stream);
             ctx->prof.pending.push_back({a, b, kind, units});
         }
     }

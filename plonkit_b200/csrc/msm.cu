@@ -91,6 +91,29 @@ static int max_batch_for(const SrsTables* s) {
     return nb;
 }
 
+static void alloc_scratch(const SrsTables* s, MsmScratch& sc, int nb) {
+    const size_t M = (size_t)s->n * s->W;
+    const size_t NB = (size_t)nb * s->B;
+    const int fb = msm_fine_bits(ilog2(NB));
+    const size_t ncmax = 2 * (NB >> fb) + 2;  // a 3-set group has a coarser floor(log2) than the 4-set one it shares with
+    sc.max_sets = nb;
+    sc.coarse_count.alloc(ncmax);
+    sc.coarse_offset.alloc(ncmax);
+    sc.coarse_cursor.alloc(ncmax);
+    sc.scan_sums.alloc(ncmax / 4096 + 2);
+    sc.entries.alloc(nb * M);
+    sc.tmp_entries.alloc(nb * M);
+    sc.buckets.alloc(NB);
+    const size_t nchunks = (nb * M + s->chunk1 - 1) / s->chunk1;
+    for (int k = 0; k < 2; ++k) {
+        sc.pkeys[k].alloc(2 * nchunks + 2);
+        sc.ppts[k].alloc(2 * nchunks + 2);
+    }
+    sc.counts.alloc(16);
+    sc.super.alloc((size_t)nb * ((size_t(1) << s->hi_bits) + (size_t(1) << s->lo_bits)));
+    sc.red.alloc((size_t)MSM_MAX_BATCH * 1024 + MSM_MAX_BATCH);
+}
+
 void srs_load(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits) {
     PK_REQUIRE(n >= 1, PK_ERR_INVALID, "empty SRS");
     PK_REQUIRE(n <= (uint64_t(1) << 26), PK_ERR_DEGREE_TOO_LARGE, "SRS larger than 2^26 bases (SETUP_MAX_POW2, src/plonk.rs:27)");
@@ -112,36 +135,23 @@ void srs_load(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits
     srs_window_kernel<<<grid1d(n, 128), 128, 0, ctx->stream>>>(s->table.p, n, c, W);
     ctx->prof.kernel_launches += 2;
     PK_CUDA(cudaGetLastError());
+    PK_CUDA(cudaFuncSetAttribute(msm_coarse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    PK_CUDA(cudaFuncSetAttribute(msm_coarse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     const int nb = max_batch_for(s);
     size_t M = (size_t)n * W;
-    size_t NB = (size_t)nb * s->B;
-    {
-        int lg = ilog2(NB);
-        s->fine_bits_max = msm_fine_bits(lg);
-        size_t ncmax = (NB >> s->fine_bits_max) + 2;
-        // the coarse kernels keep two counters per bin in shared memory (up to 128 KB for the largest window sizes)
-        PK_CUDA(cudaFuncSetAttribute(msm_coarse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        PK_CUDA(cudaFuncSetAttribute(msm_coarse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        s->coarse_count.alloc(ncmax);
-        s->coarse_offset.alloc(ncmax);
-        s->coarse_cursor.alloc(ncmax);
-        s->scan_sums.alloc(ncmax / 4096 + 2);
-    }
-    s->entries.alloc(nb * M);
-    s->tmp_entries.alloc(nb * M);
-    s->buckets.alloc(NB);
     // level-1 chunk: keep the chunk count of one scalar set <= 2^19 so the partial lists stay small
     uint32_t chunk = 64;
     while (M / chunk > (size_t(1) << 19)) chunk *= 2;
     s->chunk1 = chunk;
-    size_t nchunks = (nb * M + chunk - 1) / chunk;
-    for (int k = 0; k < 2; ++k) {
-        s->pkeys[k].alloc(2 * nchunks + 2);
-        s->ppts[k].alloc(2 * nchunks + 2);
+    // scratch 0 serves a full batch, scratch 1 the second half of a split batch (see msm_run_batch)
+    alloc_scratch(s, s->scratch[0], nb);
+    if (nb >= 2) alloc_scratch(s, s->scratch[1], nb / 2);
+    if (!s->stream2) {
+        PK_CUDA(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+        PK_CUDA(cudaEventCreateWithFlags(&s->ev_ready, cudaEventDisableTiming));
+        PK_CUDA(cudaEventCreateWithFlags(&s->ev_sorted, cudaEventDisableTiming));
+        PK_CUDA(cudaEventCreateWithFlags(&s->ev_done2, cudaEventDisableTiming));
     }
-    s->counts.alloc(16);
-    s->super.alloc((size_t)nb * ((size_t(1) << s->hi_bits) + (size_t(1) << s->lo_bits)));
-    s->red.alloc((size_t)MSM_MAX_BATCH * 1024 + MSM_MAX_BATCH);
     PK_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
@@ -464,9 +474,10 @@ void affine_to_abi(const g1_affine_t& p, uint64_t out[8]) {
     memcpy(out + 4, y.v, 32);
 }
 
-static void msm_run_group(pk_ctx* ctx, const fr_t* const* scalars, int nb, uint64_t n, uint64_t base_offset, g1_affine_t* out) {
+// enqueues one group of <= sc.max_sets scalar sets on stream st; the nb XYZZ results land in host_pt (pinned) once st drains
+static void msm_enqueue_group(pk_ctx* ctx, MsmScratch& sc, cudaStream_t st, const fr_t* const* scalars, int nb, uint64_t n,
+                              uint64_t base_offset, g1_xyzz_t* host_pt, cudaEvent_t sorted_event) {
     SrsTables* s = ctx->srs;
-    cudaStream_t st = ctx->stream;
     const uint32_t B = s->B;
     const uint32_t NB = (uint32_t)nb * B;
     ScalarSets sets;
@@ -474,41 +485,42 @@ static void msm_run_group(pk_ctx* ctx, const fr_t* const* scalars, int nb, uint6
     const int lg = ilog2(NB);
     const int fine_bits = msm_fine_bits(lg);
     const uint32_t NC = (NB + (1u << fine_bits) - 1) >> fine_bits;
-    PK_CUDA(cudaMemsetAsync(s->coarse_count.p, 0, (size_t)(NC + 1) * sizeof(uint32_t), st));
-    PK_CUDA(cudaMemsetAsync(s->buckets.p, 0, (size_t)NB * sizeof(g1_xyzz_t), st));
+    PK_CUDA(cudaMemsetAsync(sc.coarse_count.p, 0, (size_t)(NC + 1) * sizeof(uint32_t), st));
+    PK_CUDA(cudaMemsetAsync(sc.buckets.p, 0, (size_t)NB * sizeof(g1_xyzz_t), st));
     dim3 dgrid((unsigned)((n + 256 * COARSE_PER_THREAD - 1) / (256 * COARSE_PER_THREAD)), nb);
     msm_coarse_kernel<false><<<dgrid, 256, NC * sizeof(uint32_t), st>>>(sets, (uint32_t)n, (uint32_t)s->n, (uint32_t)base_offset, s->c, s->W,
-                                                                      fine_bits, NC, s->coarse_count.p, nullptr);
+                                                                      fine_bits, NC, sc.coarse_count.p, nullptr);
     const uint32_t tiles = (NC + 4095) / 4096;
-    u32_scan_tile_sums_kernel<<<tiles, 1024, 0, st>>>(s->coarse_count.p, s->scan_sums.p, NC);
-    u32_scan_spine_kernel<<<1, 1024, 0, st>>>(s->scan_sums.p, tiles, s->counts.p, s->coarse_offset.p + NC);
-    u32_scan_apply_kernel<<<tiles, 1024, 0, st>>>(s->coarse_count.p, s->scan_sums.p, s->coarse_offset.p, s->coarse_cursor.p, NC);
+    u32_scan_tile_sums_kernel<<<tiles, 1024, 0, st>>>(sc.coarse_count.p, sc.scan_sums.p, NC);
+    u32_scan_spine_kernel<<<1, 1024, 0, st>>>(sc.scan_sums.p, tiles, sc.counts.p, sc.coarse_offset.p + NC);
+    u32_scan_apply_kernel<<<tiles, 1024, 0, st>>>(sc.coarse_count.p, sc.scan_sums.p, sc.coarse_offset.p, sc.coarse_cursor.p, NC);
     msm_coarse_kernel<true><<<dgrid, 256, 2 * NC * sizeof(uint32_t), st>>>(sets, (uint32_t)n, (uint32_t)s->n, (uint32_t)base_offset, s->c, s->W,
-                                                                         fine_bits, NC, s->coarse_cursor.p, s->tmp_entries.p);
-    msm_fine_sort_kernel<<<NC, 512, ((size_t(1) << fine_bits) + 512) * sizeof(uint32_t), st>>>(s->tmp_entries.p, s->entries.p,
-                                                                                            s->coarse_offset.p, fine_bits);
+                                                                         fine_bits, NC, sc.coarse_cursor.p, sc.tmp_entries.p);
+    msm_fine_sort_kernel<<<NC, 512, ((size_t(1) << fine_bits) + 512) * sizeof(uint32_t), st>>>(sc.tmp_entries.p, sc.entries.p,
+                                                                                            sc.coarse_offset.p, fine_bits);
     ctx->prof.kernel_launches += 6;
+    if (sorted_event) PK_CUDA(cudaEventRecord(sorted_event, st));
     // accumulation levels (worst-case grids; the device-side counts bound the real work)
     size_t max_entries = (size_t)nb * n * s->W;
     AccumParams p;
     memset(&p, 0, sizeof(p));
     p.table = s->table.p;
-    p.buckets = s->buckets.p;
+    p.buckets = sc.buckets.p;
     int level = 0;
     uint32_t chunk = s->chunk1;
     const uint32_t* keys = nullptr;
     while (true) {
         size_t nchunks = (max_entries + chunk - 1) / chunk;
         p.keys = keys;
-        p.ent = s->entries.p;
-        p.pts = level == 0 ? nullptr : s->ppts[(level - 1) & 1].p;
-        p.count_in = s->counts.p + level;
-        p.count_out = s->counts.p + level + 1;
+        p.ent = sc.entries.p;
+        p.pts = level == 0 ? nullptr : sc.ppts[(level - 1) & 1].p;
+        p.count_in = sc.counts.p + level;
+        p.count_out = sc.counts.p + level + 1;
         p.chunk = chunk;
-        p.out_keys = s->pkeys[level & 1].p;
-        p.out_pts = s->ppts[level & 1].p;
+        p.out_keys = sc.pkeys[level & 1].p;
+        p.out_pts = sc.ppts[level & 1].p;
         if (level == 0) {
-            ScopedKernelTimer timer(ctx, 0, (uint64_t)nb * n);
+            ScopedKernelTimer timer(ctx, 0, (uint64_t)nb * n, st);
             msm_accum_kernel<true><<<grid1d(nchunks, 128), 128, 0, st>>>(p);
             ctx->prof.msm_accum_launches++;
         } else {
@@ -516,7 +528,7 @@ static void msm_run_group(pk_ctx* ctx, const fr_t* const* scalars, int nb, uint6
         }
         ctx->prof.kernel_launches++;
         if (nchunks <= 1) break;
-        keys = s->pkeys[level & 1].p;
+        keys = sc.pkeys[level & 1].p;
         max_entries = 2 * nchunks;
         chunk = 16;
         ++level;
@@ -524,19 +536,16 @@ static void msm_run_group(pk_ctx* ctx, const fr_t* const* scalars, int nb, uint6
     }
     // bucket reduction
     const uint32_t H = 1u << s->hi_bits, L = 1u << s->lo_bits;
-    msm_super_hi_kernel<<<dim3(H, nb), 128, 0, st>>>(s->buckets.p, s->lo_bits, s->hi_bits, s->super.p);
-    msm_super_lo_kernel<<<dim3((L + 31) / 32, nb), 128, 0, st>>>(s->buckets.p, s->lo_bits, s->hi_bits, s->super.p);
+    msm_super_hi_kernel<<<dim3(H, nb), 128, 0, st>>>(sc.buckets.p, s->lo_bits, s->hi_bits, sc.super.p);
+    msm_super_lo_kernel<<<dim3((L + 31) / 32, nb), 128, 0, st>>>(sc.buckets.p, s->lo_bits, s->hi_bits, sc.super.p);
     const uint32_t wblocks = (H + L + 127) / 128;
     PK_REQUIRE(wblocks <= 1024, PK_ERR_INVALID, "bucket reduction partial buffer too small");
-    g1_xyzz_t* result = s->red.p + (size_t)MSM_MAX_BATCH * 1024;
-    msm_weighted_kernel<<<dim3(wblocks, nb), 128, 0, st>>>(s->super.p, s->lo_bits, s->hi_bits, s->red.p, 1024);
-    msm_fold_kernel<<<nb, 128, 0, st>>>(s->red.p, wblocks, 1024, result);
+    g1_xyzz_t* result = sc.red.p + (size_t)MSM_MAX_BATCH * 1024;
+    msm_weighted_kernel<<<dim3(wblocks, nb), 128, 0, st>>>(sc.super.p, s->lo_bits, s->hi_bits, sc.red.p, 1024);
+    msm_fold_kernel<<<nb, 128, 0, st>>>(sc.red.p, wblocks, 1024, result);
     ctx->prof.kernel_launches += 4;
     PK_CUDA(cudaGetLastError());
-    g1_xyzz_t* host_pt = reinterpret_cast<g1_xyzz_t*>(ctx->pinned);
     PK_CUDA(cudaMemcpyAsync(host_pt, result, nb * sizeof(g1_xyzz_t), cudaMemcpyDeviceToHost, st));
-    PK_CUDA(cudaStreamSynchronize(st));
-    for (int k = 0; k < nb; ++k) out[k] = host_pt[k].to_affine();
 }
 
 void msm_run_batch(pk_ctx* ctx, const fr_t* const* scalars, int nb, uint64_t n, uint64_t base_offset, g1_affine_t* out) {
@@ -547,10 +556,29 @@ void msm_run_batch(pk_ctx* ctx, const fr_t* const* scalars, int nb, uint64_t n, 
         for (int k = 0; k < nb; ++k) out[k] = g1_affine_t::infinity();
         return;
     }
-    const int group = max_batch_for(s);
+    const int group = s->scratch[0].max_sets;
+    g1_xyzz_t* host_pt = reinterpret_cast<g1_xyzz_t*>(ctx->pinned);
+    // While profiling, groups run one after the other on the main stream so that per-kernel event times are clean.
+    // Otherwise a group of >= 2 sets is split in two halves on two streams, staggered by the first half's sort: the
+    // sort / partial-run / bucket-reduction kernels (memory- and latency-bound) of one half then overlap the bucket
+    // accumulation (integer-multiply-bound) of the other.
+    const bool overlap = !ctx->prof.enabled && s->scratch[1].max_sets > 0 && n >= 4096;
     for (int k = 0; k < nb; k += group) {
-        int g = nb - k < group ? nb - k : group;
-        msm_run_group(ctx, scalars + k, g, n, base_offset, out + k);
+        const int g = nb - k < group ? nb - k : group;
+        const int ga = overlap && g >= 2 ? (g + 1) / 2 : g, gb = g - ga;
+        if (gb > 0) {
+            PK_CUDA(cudaEventRecord(s->ev_ready, ctx->stream));  // the scalars are produced on the main stream
+            PK_CUDA(cudaStreamWaitEvent(s->stream2, s->ev_ready, 0));
+        }
+        msm_enqueue_group(ctx, s->scratch[0], ctx->stream, scalars + k, ga, n, base_offset, host_pt, gb > 0 ? s->ev_sorted : nullptr);
+        if (gb > 0) {
+            PK_CUDA(cudaStreamWaitEvent(s->stream2, s->ev_sorted, 0));
+            msm_enqueue_group(ctx, s->scratch[1], s->stream2, scalars + k + ga, gb, n, base_offset, host_pt + ga, nullptr);
+            PK_CUDA(cudaEventRecord(s->ev_done2, s->stream2));
+            PK_CUDA(cudaStreamWaitEvent(ctx->stream, s->ev_done2, 0));
+        }
+        PK_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int j = 0; j < g; ++j) out[k + j] = host_pt[j].to_affine();
     }
 }
 

@@ -6,6 +6,20 @@ namespace pk {
 
 static const int MSM_MAX_BATCH = 4;
 
+// per-stream working set of one MSM group
+struct MsmScratch {
+    int max_sets = 0;
+    DevBuf<uint32_t> coarse_count, coarse_offset, coarse_cursor;  // [NC + 1] coarse-bin histogram / offsets / cursors
+    DevBuf<uint32_t> scan_sums;          // block sums of the offsets scan
+    DevBuf<uint2> entries, tmp_entries;  // [sets * n * W] (bucket id, table index | sign << 31): sorted / partitioned
+    DevBuf<g1_xyzz_t> buckets;           // [sets * B]
+    DevBuf<uint32_t> pkeys[2];           // partial-run lists (ping-pong between levels)
+    DevBuf<g1_xyzz_t> ppts[2];
+    DevBuf<uint32_t> counts;             // [16] per-level entry counts (device)
+    DevBuf<g1_xyzz_t> super;             // [sets][2^hi_bits + 2^lo_bits] super-bucket sums
+    DevBuf<g1_xyzz_t> red;               // reduction partials + [sets] results
+};
+
 struct SrsTables {
     uint64_t n = 0;          // resident bases
     int c = 0;               // window bits (signed digits in (-2^(c-1), 2^(c-1)])
@@ -14,18 +28,16 @@ struct SrsTables {
     int lo_bits = 0, hi_bits = 0;  // bucket id = hi * 2^lo_bits + lo (two-level bucket reduction)
     DevBuf<g1_affine_t> table;   // [W][n]: table[w][i] = 2^(c*w) * base_i, affine, Montgomery form
 
-    // scratch, sized for MSM_MAX_BATCH scalar sets of n pairs
-    int fine_bits_max = 0;
-    DevBuf<uint32_t> coarse_count, coarse_offset, coarse_cursor;  // [NC + 1] coarse-bin histogram / offsets / cursors
-    DevBuf<uint32_t> scan_sums;  // block sums of the offsets scan
-    DevBuf<uint2> entries, tmp_entries;  // [nb * n * W] (bucket id, table index | sign << 31): sorted / partitioned
-    DevBuf<g1_xyzz_t> buckets;           // [nb*B]
-    DevBuf<uint32_t> pkeys[2];           // partial-run lists (ping-pong between levels)
-    DevBuf<g1_xyzz_t> ppts[2];
-    DevBuf<uint32_t> counts;             // [16] per-level entry counts (device)
-    DevBuf<g1_xyzz_t> super;             // [nb][2^hi_bits + 2^lo_bits] super-bucket sums
-    DevBuf<g1_xyzz_t> red;               // reduction partials + [nb] results
+    MsmScratch scratch[2];               // [0]: a full batch; [1]: the second half of a split batch
+    cudaStream_t stream2 = nullptr;      // second stream + events for the split
+    cudaEvent_t ev_ready = nullptr, ev_sorted = nullptr, ev_done2 = nullptr;
     uint32_t chunk1 = 64;                // entries per thread at level 1 (for a single scalar set)
+    ~SrsTables() {
+        if (stream2) cudaStreamDestroy(stream2);
+        if (ev_ready) cudaEventDestroy(ev_ready);
+        if (ev_sorted) cudaEventDestroy(ev_sorted);
+        if (ev_done2) cudaEventDestroy(ev_done2);
+    }
 };
 
 // loads n affine bases (canonical limbs, host) and builds the window tables
