@@ -207,7 +207,7 @@ def bench_ours(args):
         sampler.start()
     # ---- timed region 1: witness resident in HBM
     setup.upload_witness(wit_np)
-    ctx.profile_enable(True)
+    ctx.profile_enable(False)
     ctx.profile_reset()
     barrier(td, local)
     ctx.timer_begin()
@@ -215,9 +215,19 @@ def bench_ours(args):
         proof = setup.prove(None)
     ms_dev = ctx.timer_end()
     barrier(td, local)
+    launches_timed = ctx.profile()["kernel_launches"]
+    ms_dev = max_over_ranks(td, local, ms_dev)
+    # ---- per-kernel pass (not part of `value`): the same K steps with CUDA events around the dominant kernel.  With
+    # event timing on, the library runs the two halves of an MSM batch back to back instead of on two overlapping
+    # streams, so the kernel is timed alone; ms_per_step_profiled below is this pass's step time.
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    ctx.timer_begin()
+    for _ in range(args.steps):
+        proof = setup.prove(None)
+    ms_prof = ctx.timer_end()
     prof = ctx.profile()
     ctx.profile_enable(False)
-    ms_dev = max_over_ranks(td, local, ms_dev)
     # ---- timed region 2: end to end through the public API, host buffers
     barrier(td, local)
     ctx.timer_begin()
@@ -255,12 +265,12 @@ def bench_ours(args):
         "config": workload_config(args, world),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(prof["kernel_launches"]),
+        "gpu_launches": int(launches_timed),
         "roofline": {"bound": "hbm", "kernel": "msm_accum_kernel<true> (bucket accumulation; 4 batched launches cover the 11 MSMs of a proof)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes, "ms_per_launch": accum_ms,
-                     "share_of_step": (prof["msm_accum_ms"] / args.steps) / (ms_dev / args.steps),
-                     "note": "integer-ALU bound (10 x 254-bit Montgomery products per pair and window); see DESIGN.md"},
+                     "share_of_step": prof["msm_accum_ms"] / ms_prof, "ms_per_step_profiled": ms_prof / args.steps,
+                     "note": "integer-ALU bound (10 x 254-bit Montgomery products per pair and window); kernel timed by CUDA events in a separate K-step pass with the MSM streams serialised (the timed value pass overlaps them); see DESIGN.md"},
         "ntt": {"ms_per_step": prof["ntt_ms"] / args.steps, "launches_per_step": prof["ntt_launches"] / args.steps},
         "phase_ms": prof["phase_ms"],
         "clocks": clocks,
