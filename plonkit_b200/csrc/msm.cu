@@ -558,11 +558,13 @@ void msm_run_batch(pk_ctx* ctx, const fr_t* const* scalars, int nb, uint64_t n, 
     }
     const int group = s->scratch[0].max_sets;
     g1_xyzz_t* host_pt = reinterpret_cast<g1_xyzz_t*>(ctx->pinned);
-    // While profiling, groups run one after the other on the main stream so that per-kernel event times are clean.
-    // Otherwise a group of >= 2 sets is split in two halves on two streams, staggered by the first half's sort: the
-    // sort / partial-run / bucket-reduction kernels (memory- and latency-bound) of one half then overlap the bucket
-    // accumulation (integer-multiply-bound) of the other.
-    const bool overlap = !ctx->prof.enabled && s->scratch[1].max_sets > 0 && n >= 4096;
+    // Optional (PK_MSM_OVERLAP=1): split a group of >= 2 sets in two halves on two streams, staggered by the first
+    // half's sort, so that the memory/latency-bound kernels of one half overlap the integer-bound accumulation of the
+    // other.  Measured on B200 at N = 2^20 this LOSES 4 % (52.8 vs 50.9 ms per proof): the halves pay the latency-bound
+    // tail kernels twice and the accumulation kernels already fill the machine.  Off by default; never used while
+    // per-kernel event timing is on.
+    static const bool want_overlap = [] { const char* e = getenv("PK_MSM_OVERLAP"); return e && e[0] == '1'; }();
+    const bool overlap = want_overlap && !ctx->prof.enabled && s->scratch[1].max_sets > 0 && n >= 4096;
     for (int k = 0; k < nb; k += group) {
         const int g = nb - k < group ? nb - k : group;
         const int ga = overlap && g >= 2 ? (g + 1) / 2 : g, gb = g - ga;
