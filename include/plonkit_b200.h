@@ -71,6 +71,17 @@ int pk_g1_sum(const uint64_t* points_xy, uint64_t n, uint64_t out_xy[8]);
  * monomial bases: out[i] = [L_i(tau)] G, natural order. */
 int pk_ec_intt_g1(pk_ctx* ctx, uint32_t log_n, uint64_t* out_xy);
 
+/* ---- device-pointer primitives for the multi-GPU path ------------------------------ */
+/* These operate in place on CALLER-OWNED device memory (e.g. torch tensors that NCCL collectives also touch), hold
+ * Montgomery-form elements, and return after the library's stream has drained.
+ * pk_dev_fr_convert : canonical <-> Montgomery over n elements.
+ * pk_dev_ntt_rows   : `rows` independent (i)NTTs of length 2^log_len over consecutive rows, natural order in and out.
+ * pk_dev_twiddle    : a[r][c] *= w_N^(+-(row0 + r) * c), N = 2^log_total — the twiddle step between the local
+ *                     column transforms and the all-to-all of a four-step distributed NTT. */
+int pk_dev_fr_convert(pk_ctx* ctx, void* dev, uint64_t n, int to_mont);
+int pk_dev_ntt_rows(pk_ctx* ctx, void* dev, uint32_t log_len, uint64_t rows, int inverse);
+int pk_dev_twiddle(pk_ctx* ctx, void* dev, uint64_t rows, uint64_t cols, uint32_t log_total, uint64_t row0, int inverse);
+
 /* ---- prover -------------------------------------------------------------------------------------------- */
 /* Gate tables of a width-4 circuit with d_next (PlonkCsWidth4WithNextStepParams).  n is the domain size (power of
  * two); rows 0..num_inputs-1 are the public-input gates; row n-1 is never a gate.  Variable 0 is the dummy

@@ -27,7 +27,8 @@ EXPORTS = [
     "pk_create", "pk_destroy", "pk_last_error", "pk_constants", "pk_srs_load_g1", "pk_srs_gen", "pk_ntt", "pk_lde4",
     "pk_msm_g1", "pk_ec_intt_g1", "pk_setup_create", "pk_setup_destroy", "pk_setup_commitments", "pk_witness_upload",
     "pk_prove", "pk_profile_enable", "pk_profile_reset", "pk_profile_get", "pk_bench_ntt", "pk_bench_msm",
-    "pk_bench_fieldmul", "pk_timer_begin", "pk_timer_end", "pk_g1_sum",
+    "pk_bench_fieldmul", "pk_timer_begin", "pk_timer_end", "pk_g1_sum", "pk_dev_fr_convert", "pk_dev_ntt_rows",
+    "pk_dev_twiddle",
 ]
 
 
@@ -117,6 +118,9 @@ def load():
     lib.pk_bench_msm.argtypes = [vp, u64, i32, ctypes.POINTER(ctypes.c_double)]
     lib.pk_bench_fieldmul.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double)]
     lib.pk_g1_sum.argtypes = [vp, u64, vp]
+    lib.pk_dev_fr_convert.argtypes = [vp, vp, u64, i32]
+    lib.pk_dev_ntt_rows.argtypes = [vp, vp, u32, u64, i32]
+    lib.pk_dev_twiddle.argtypes = [vp, vp, u64, u64, u32, u64, i32]
     lib.pk_timer_begin.argtypes = [vp]
     lib.pk_timer_end.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     _lib = lib
@@ -199,6 +203,16 @@ class Context:
         out = np.zeros((1 << log_n, 8), dtype=np.uint64)
         self._check(self._lib.pk_ec_intt_g1(self._h, log_n, _ptr(out)))
         return out
+
+    # ---- device-pointer primitives (caller-owned device memory; `ptr` is a raw CUDA device address)
+    def dev_fr_convert(self, ptr, n, to_mont):
+        self._check(self._lib.pk_dev_fr_convert(self._h, ctypes.c_void_p(ptr), n, int(to_mont)))
+
+    def dev_ntt_rows(self, ptr, log_len, rows, inverse=False):
+        self._check(self._lib.pk_dev_ntt_rows(self._h, ctypes.c_void_p(ptr), log_len, rows, int(inverse)))
+
+    def dev_twiddle(self, ptr, rows, cols, log_total, row0, inverse=False):
+        self._check(self._lib.pk_dev_twiddle(self._h, ctypes.c_void_p(ptr), rows, cols, log_total, row0, int(inverse)))
 
     # ---- profiling / micro-benchmarks
     def profile_enable(self, on=True):

@@ -210,6 +210,36 @@ int pk_g1_sum(const uint64_t* points_xy, uint64_t n, uint64_t out_xy[8]) {
     return PK_OK;
 }
 
+// ---- device-pointer primitives (caller-owned device memory, e.g. torch tensors shared with NCCL collectives)
+int pk_dev_fr_convert(pk_ctx* ctx, void* dev, uint64_t n, int to_mont) {
+    PK_API_BEGIN(ctx)
+    PK_REQUIRE(dev != nullptr || n == 0, PK_ERR_INVALID, "null device pointer");
+    if (to_mont) fr_to_mont(ctx, static_cast<fr_t*>(dev), n);
+    else fr_from_mont(ctx, static_cast<fr_t*>(dev), static_cast<fr_t*>(dev), n);
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    PK_CUDA(cudaGetLastError());
+    PK_API_END(ctx)
+}
+int pk_dev_ntt_rows(pk_ctx* ctx, void* dev, uint32_t log_len, uint64_t rows, int inverse) {
+    PK_API_BEGIN(ctx)
+    PK_REQUIRE(dev != nullptr && rows >= 1, PK_ERR_INVALID, "bad argument");
+    PK_REQUIRE(log_len <= 28, PK_ERR_DEGREE_TOO_LARGE, "domain larger than 2^28");
+    DevBuf<fr_t> tmp((size_t)rows << log_len);
+    ntt_rows_natural(ctx, static_cast<fr_t*>(dev), tmp.p, (int)log_len, rows, inverse != 0);
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    PK_CUDA(cudaGetLastError());
+    PK_API_END(ctx)
+}
+int pk_dev_twiddle(pk_ctx* ctx, void* dev, uint64_t rows, uint64_t cols, uint32_t log_total, uint64_t row0, int inverse) {
+    PK_API_BEGIN(ctx)
+    PK_REQUIRE(dev != nullptr && rows >= 1 && cols >= 1, PK_ERR_INVALID, "bad argument");
+    PK_REQUIRE(log_total <= 28, PK_ERR_DEGREE_TOO_LARGE, "domain larger than 2^28");
+    twiddle_rows(ctx, static_cast<fr_t*>(dev), rows, cols, (int)log_total, row0, inverse != 0);
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    PK_CUDA(cudaGetLastError());
+    PK_API_END(ctx)
+}
+
 int pk_ec_intt_g1(pk_ctx* ctx, uint32_t log_n, uint64_t* out_xy) {
     PK_API_BEGIN(ctx)
     PK_REQUIRE(out_xy != nullptr, PK_ERR_INVALID, "null output");

@@ -57,11 +57,20 @@ __global__ void from_mont_kernel(const fr_t* src, fr_t* dst, size_t n) {
     size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (k < n) st_fp(dst + k, ld_fp(src + k).from_mont());
 }
-__global__ void bitrev_kernel(const fr_t* src, fr_t* dst, int log_n) {
+__global__ void bitrev_kernel(const fr_t* src, fr_t* dst, int log_n) {  // blockIdx.y = row of a batch
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >> log_n) return;
     size_t r = log_n ? (size_t)(__brev((unsigned)i) >> (32 - log_n)) : 0;
-    st_fp(dst + r, ld_fp(src + i));
+    const size_t row = (size_t)blockIdx.y << log_n;
+    st_fp(dst + row + r, ld_fp(src + row + i));
+}
+// a[r][c] *= w^{(row0 + r) * c}  (w = primitive 2^log_total-th root, or its inverse): the four-step twiddle
+__global__ void twiddle_rows_kernel(fr_t* a, size_t rows, size_t cols, fr_t w, size_t row0) {
+    size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t r = blockIdx.y;
+    if (c >= cols || r >= rows) return;
+    const fr_t base = w.pow_u64(row0 + r);  // w^(row0 + r); then raised to c
+    st_fp(a + r * cols + c, ld_fp(a + r * cols + c) * base.pow_u64(c));
 }
 
 static inline dim3 grid1d(size_t n, int block) { return dim3((unsigned)((n + block - 1) / block)); }
@@ -76,12 +85,12 @@ void fr_from_mont(pk_ctx* ctx, const fr_t* src, fr_t* dst, size_t n) {
     from_mont_kernel<<<grid1d(n, 256), 256, 0, ctx->stream>>>(src, dst, n);
     ctx->prof.kernel_launches++;
 }
-void bitrev_permute(pk_ctx* ctx, const fr_t* src, fr_t* dst, int log_n) {
+void bitrev_permute(pk_ctx* ctx, const fr_t* src, fr_t* dst, int log_n, size_t rows) {
     size_t n = size_t(1) << log_n;
-    bitrev_kernel<<<grid1d(n, 256), 256, 0, ctx->stream>>>(src, dst, log_n);
+    PK_REQUIRE(rows >= 1 && rows <= 65535, PK_ERR_INVALID, "bitrev batch too large");
+    bitrev_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)rows), 256, 0, ctx->stream>>>(src, dst, log_n);
     ctx->prof.kernel_launches++;
 }
-
 void ensure_twiddles(pk_ctx* ctx, int log_n) {
     PK_REQUIRE(log_n <= 28, PK_ERR_DEGREE_TOO_LARGE, "domain larger than 2^28 (Fr two-adicity)");
     if (!ctx->domains) ctx->domains = new DomainCache();
@@ -328,5 +337,26 @@ void icoset4n_from_slots(pk_ctx* ctx, const fr_t* vals4n, fr_t* coeffs4n, int lo
     CosetTables* ct = get_coset_tables(ctx, log_n);
     ntt_inverse_from_bitrev(ctx, vals4n, coeffs4n, log_n + 2, ct->iscale4n.p);
 }
+
+void ntt_rows_natural(pk_ctx* ctx, fr_t* data, fr_t* tmp, int log_len, size_t rows, bool inverse) {
+    const size_t len = size_t(1) << log_len;
+    PK_REQUIRE(rows >= 1 && rows <= 65535, PK_ERR_INVALID, "row batch too large");
+    if (!inverse) {
+        ntt_forward_bitrev(ctx, data, tmp, log_len, nullptr, (int)rows, len, len, 0);
+        bitrev_permute(ctx, tmp, data, log_len, rows);
+    } else {
+        bitrev_permute(ctx, data, tmp, log_len, rows);
+        fr_t ninv = fr_t::from_u32(2).inverse().pow_u64(log_len);
+        run_passes<true>(ctx, tmp, data, log_len, nullptr, nullptr, &ninv, (int)rows, len, len, 0);
+    }
+}
+void twiddle_rows(pk_ctx* ctx, fr_t* a, size_t rows, size_t cols, int log_total, size_t row0, bool inverse) {
+    PK_REQUIRE(rows >= 1 && rows <= 65535, PK_ERR_INVALID, "row batch too large");
+    fr_t w = host_root_of_unity(log_total);
+    if (inverse) w = w.inverse();
+    twiddle_rows_kernel<<<dim3((unsigned)((cols + 255) / 256), (unsigned)rows), 256, 0, ctx->stream>>>(a, rows, cols, w, row0);
+    ctx->prof.kernel_launches++;
+}
+
 
 }  // namespace pk

@@ -32,7 +32,11 @@ void ntt_forward_bitrev(pk_ctx* ctx, const fr_t* src, fr_t* dst, int log_n, cons
 // inverse NTT, bit-reversed order in -> natural order out (decimation in time), result multiplied by post[i] if given,
 // else by 1/n.
 void ntt_inverse_from_bitrev(pk_ctx* ctx, const fr_t* src, fr_t* dst, int log_n, const fr_t* post = nullptr);
-void bitrev_permute(pk_ctx* ctx, const fr_t* src, fr_t* dst, int log_n);  // out of place, src != dst
+void bitrev_permute(pk_ctx* ctx, const fr_t* src, fr_t* dst, int log_n, size_t rows = 1);  // out of place, src != dst
+// rows independent (i)NTTs of length 2^log_len, natural order in and out, in place (tmp: same size scratch)
+void ntt_rows_natural(pk_ctx* ctx, fr_t* data, fr_t* tmp, int log_len, size_t rows, bool inverse);
+// a[r][c] *= w_N^{+-(row0 + r) * c}: the twiddle step between the two halves of a four-step NTT of size N = 2^log_total
+void twiddle_rows(pk_ctx* ctx, fr_t* a, size_t rows, size_t cols, int log_total, size_t row0, bool inverse);
 // coefficients (N, natural) -> evaluations on 7*H_4N in slot layout (4N)
 void lde4_slots(pk_ctx* ctx, const fr_t* coeffs, fr_t* out4n, int log_n);
 // evaluations on 7*H_4N in slot layout -> 4N coefficients (natural), in place allowed

@@ -57,3 +57,87 @@ class ShardedCommitter:
         out = [torch.empty_like(t) for _ in range(self.world)]
         td.all_gather(out, t, group=self.group)
         return np.stack([o.cpu().numpy().view(np.uint64) for o in out])
+
+
+class CudaNttOps:
+    """Local steps of the distributed NTT on caller-owned CUDA tensors through the library's device-pointer entry points
+    (pk_dev_fr_convert / pk_dev_ntt_rows / pk_dev_twiddle).  Tensors are (rows, cols, 4) int64 views of u64 limbs."""
+
+    def __init__(self, ctx, device):
+        self.ctx, self.device = ctx, device
+
+    def _sync(self):
+        import torch
+        torch.cuda.synchronize(self.device)  # the library runs on its own stream
+
+    def enter(self, t):
+        self._sync()
+        self.ctx.dev_fr_convert(t.data_ptr(), t.shape[0] * t.shape[1], True)
+
+    def leave(self, t):
+        self._sync()
+        self.ctx.dev_fr_convert(t.data_ptr(), t.shape[0] * t.shape[1], False)
+
+    def ntt_rows(self, t):
+        self._sync()
+        self.ctx.dev_ntt_rows(t.data_ptr(), t.shape[1].bit_length() - 1, t.shape[0], False)
+
+    def twiddle(self, t, log_total, row0):
+        self._sync()
+        self.ctx.dev_twiddle(t.data_ptr(), t.shape[0], t.shape[1], log_total, row0, False)
+
+
+class DistributedNtt:
+    """Four-step forward NTT of size N = N1 * N2 over `world` ranks with ONE all-to-all (SURVEY.md §8e, row "NTT").
+
+    Input  (column blocks): rank r holds x[N2*n1 + r*C + j] for n1 < N1, j < C = N2/world, as an (N1, C, 4) array.
+    Output (row blocks)   : rank q holds X[(q*K + i) + N1*k2] for i < K = N1/world, k2 < N2, as a (K, N2, 4) array.
+    Steps: local column NTTs of size N1 -> twiddle w_N^(n2*k1) -> all-to-all transpose (N*32/world bytes leave each
+    rank) -> local row NTTs of size N2.  `ops` supplies the local steps (CudaNttOps on the GPU; the CPU tests plug in
+    the checker); torch moves the data (transposes, packing, all_to_all_single over NCCL or gloo).
+    """
+
+    def __init__(self, log_n, rank, world, ops, group=None, log_n1=None):
+        self.log_n, self.rank, self.world, self.ops, self.group = log_n, rank, world, ops, group
+        self.log_n1 = log_n1 if log_n1 is not None else (log_n + 1) // 2
+        self.n1, self.n2 = 1 << self.log_n1, 1 << (log_n - self.log_n1)
+        if self.n1 % world or self.n2 % world:
+            raise _lib.SynthesisError(6, "both NTT factors must be divisible by the number of ranks")
+        self.c, self.k = self.n2 // world, self.n1 // world
+
+    def local_input(self, x_full):
+        """The (N1, C, 4) block of this rank, cut from a full natural-order vector (helper for tests / bench)."""
+        x = np.ascontiguousarray(x_full, dtype=np.uint64).reshape(self.n1, self.n2, 4)
+        return np.ascontiguousarray(x[:, self.rank * self.c:(self.rank + 1) * self.c])
+
+    def forward(self, local):
+        import torch
+        import torch.distributed as td
+        t = local if isinstance(local, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(local).view(np.int64))
+        n2, c, k, w = self.n2, self.c, self.k, self.world
+        cols = t.transpose(0, 1).contiguous()                  # (C, N1): this rank's columns as rows
+        self.ops.enter(cols)
+        self.ops.ntt_rows(cols)                                 # over n1 -> k1
+        self.ops.twiddle(cols, self.log_n, self.rank * c)       # * w_N^(n2 * k1)
+        send = cols.view(c, w, k, 4).permute(1, 0, 2, 3).contiguous()   # (world, C, K): block q goes to rank q
+        recv = torch.empty_like(send)
+        if w == 1:
+            recv.copy_(send)
+        else:
+            td.all_to_all_single(recv, send, group=self.group)
+        rows = recv.view(n2, k, 4).transpose(0, 1).contiguous()         # (K, N2): my k1 rows, all n2
+        self.ops.ntt_rows(rows)                                 # over n2 -> k2
+        self.ops.leave(rows)
+        return rows
+
+    def gather_natural(self, rows):
+        """All ranks' outputs reassembled into the natural-order vector X (test helper; O(N) traffic)."""
+        import torch
+        import torch.distributed as td
+        parts = [torch.empty_like(rows) for _ in range(self.world)]
+        if self.world == 1:
+            parts[0].copy_(rows)
+        else:
+            td.all_gather(parts, rows, group=self.group)
+        full = torch.cat(parts, dim=0)                          # (N1, N2): [k1][k2]
+        return full.transpose(0, 1).contiguous().cpu().numpy().view(np.uint64).reshape(-1, 4)  # index k1 + N1*k2

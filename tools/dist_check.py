@@ -1,0 +1,57 @@
+"""torchrun --nproc-per-node G tools/dist_check.py : multi-GPU checks + timings of the sharded MSM (all-gather + fold)
+and of the four-step distributed NTT (one all-to-all) against the single-GPU results.  Prints one line per rank 0 item."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as td
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    os.environ["NCCL_DEBUG"] = "WARN"
+    torch.cuda.set_device(local)
+    td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from plonkit_b200 import _lib, dist, synth
+    ctx = _lib.Context(local)
+    log_n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+    n = 1 << log_n
+    # ---- sharded MSM: every rank generates the same SRS/scalars, keeps its chunk of the window tables
+    srs = ctx.srs_gen(n, 42)
+    s = synth.random_field_elements(n, seed=11)
+    c = dist.ShardedCommitter(srs, rank, world, ctx=ctx, device="cuda:%d" % local)
+    got = c.commit(s)
+    td.barrier(device_ids=[local])
+    t0 = time.perf_counter()
+    for _ in range(3):
+        got = c.commit(s)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / 3
+    if rank == 0:
+        ctx.srs_load_g1(srs)
+        ref = ctx.msm_g1(s)
+        print("sharded MSM 2^%d over %d GPUs: %.2f ms per commitment (incl. H2D of the scalar chunk), == single GPU: %s"
+              % (log_n, world, dt * 1e3, bool((got == ref).all())), flush=True)
+    td.barrier(device_ids=[local])
+    # ---- four-step distributed NTT
+    x = synth.random_field_elements(n, seed=12)
+    d = dist.DistributedNtt(log_n, rank, world, dist.CudaNttOps(ctx, local))
+    loc = torch.from_numpy(d.local_input(x).view(np.int64)).cuda()
+    out = d.forward(loc)
+    td.barrier(device_ids=[local])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        out = d.forward(loc)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / 3
+    full = d.gather_natural(out)
+    if rank == 0:
+        ref = ctx.ntt(x)
+        print("four-step NTT 2^%d over %d GPUs: %.2f ms (device-resident, one all-to-all), == single GPU: %s"
+              % (log_n, world, dt * 1e3, bool((full == ref).all())), flush=True)
+    td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
