@@ -81,7 +81,19 @@ def dist_setup(n_gpus):
         import torch
         import torch.distributed as td_
         torch.cuda.set_device(local)
-        td_.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+        # NCCL / c10d print a version banner on stdout when the communicator is created; stdout must carry exactly one
+        # JSON line, so fd 1 points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            td_.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+            td_.barrier(device_ids=[local])
+            torch.cuda.synchronize(local)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
         td = td_
     return world, rank, local, td
 
