@@ -123,3 +123,20 @@ def test_full_size_2pow20_poseidon_proof_verifies(ctx, orc):
     vals[1000] = ints_to_limbs([(int(vals[1000][0]) + 1) % R_MOD])[0]
     with pytest.raises(_lib.SynthesisError):
         setup.prove(vals)
+
+
+def test_cli_prove_and_export_vk_write_the_golden_files(tmp_path):
+    """`plonkit export-verification-key` / `plonkit prove` (src/bin/main.rs:384-424,484-504) through the CLI mirror"""
+    from plonkit_b200 import __main__ as cli
+    key = os.path.join(SIMPLE, "setup_2^10.key")
+    circ = os.path.join(SIMPLE, "circuit.r1cs.json")
+    vk, proof = tmp_path / "vk.bin", tmp_path / "proof.bin"
+    cli.main(["export-verification-key", "-m", key, "-c", circ, "-v", str(vk)])
+    assert vk.read_bytes() == open(os.path.join(SIMPLE, "vk.bin"), "rb").read()
+    cli.main(["prove", "-m", key, "-c", circ, "-w", os.path.join(SIMPLE, "witness.json"), "-p", str(proof),
+              "-j", str(tmp_path / "proof.json"), "-i", str(tmp_path / "public.json")])
+    assert proof.read_bytes() == open(os.path.join(SIMPLE, "proof.bin"), "rb").read()
+    import json
+    assert json.load(open(tmp_path / "public.json")) == ["0x23"] and len(json.load(open(tmp_path / "proof.json"))) == 33
+    with pytest.raises(SystemExit, match="duplicate proof file"):
+        cli.main(["prove", "-m", key, "-c", circ, "-w", os.path.join(SIMPLE, "witness.json"), "-p", str(proof)])

@@ -233,3 +233,27 @@ def test_host_keccak_and_transcript_match_oracle(hc, orc):
     got = limbs_to_ints(ch.view(np.uint64))
     assert got[0] == 0x0f72cf563829c88d02442b32aa5bc8b0aff226697faa846756e813710804a058
     assert got[1] == 0x19f776d072bc5715a7fb2a727344f31eda1aa1b214c0b8b7f0bf9a8fed192264
+
+
+# ---------------------------------------------------------------- CLI surface (src/bin/main.rs:20-256)
+def test_cli_analyse_and_flag_surface(tmp_path):
+    from plonkit_b200 import __main__ as cli
+    out = tmp_path / "analyse.json"
+    cli.main(["analyse", "-c", os.path.join(SIMPLE, "circuit.r1cs.json"), "-o", str(out)])
+    got = __import__("json").load(open(out))
+    assert got["num_gates"] == 3 and got["num_hints"] == 2 and got["constraint_stats"][1] == {"name": "1", "num_gates": 2}
+    p = cli.build_parser()
+    o = p.parse_args(["prove", "-m", "k.key", "-c", "c.r1cs"])
+    assert (o.witness, o.proof, o.proofjson, o.publicjson, o.transcript, o.overwrite) == \
+        ("witness.wtns", "proof.bin", "proof.json", "public.json", "keccak", False)
+    o = p.parse_args(["export-verification-key", "-m", "k.key"])
+    assert o.vk == "vk.bin" and o.circuit is None
+    assert cli.resolve_circuit_file(None) in ("circuit.r1cs", "circuit.json") and cli.resolve_circuit_file("x.json") == "x.json"
+    with pytest.raises(SystemExit):
+        cli.main(["recursive-prove"])
+    # overwrite guard (main.rs:336-339)
+    existing = tmp_path / "exists.key"
+    existing.write_bytes(b"x")
+    with pytest.raises(SystemExit, match="duplicate srs_monomial_form file"):
+        cli._guard(str(existing), "srs_monomial_form", False)
+    cli._guard(str(existing), "srs_monomial_form", True)
