@@ -39,6 +39,7 @@ struct ScalarSets { const fr_t* s[MSM_MAX_BATCH]; };
 template <bool SCATTER>
 __global__ void msm_coarse_kernel(ScalarSets sets, uint32_t n, uint32_t table_n, uint32_t base_offset, int c, int W, int fine_bits,
                                   uint32_t NC, uint32_t* coarse, uint2* tmp);
+__global__ void msm_fine_sort_kernel(const uint2* tmp, uint2* entries, const uint32_t* coarse_offset, int fine_bits);
 
 // ---------------------------------------------------------------- SRS upload + window tables
 __global__ void bases_to_mont_kernel(g1_affine_t* pts, size_t n) {
@@ -76,11 +77,11 @@ static int pick_window_bits(uint64_t n) {
     return best;
 }
 
-// coarse bins hold 2^fine_bits buckets: small enough that one bin's entries (~13 K at N = 2^20) stay in L2 while a block
-// sorts them, and at most 8192 bins so the per-block bin counters fit in shared memory
+// coarse bins hold 2^fine_bits buckets: small enough that one bin's entries (~6.6 K at N = 2^20) fit the fine sort's
+// shared-memory staging area, and at most 2^14 bins so the per-block bin counters of the coarse kernels fit too (128 KB)
 static int msm_fine_bits(int lg_total_buckets) {
-    int fb = lg_total_buckets < 9 ? lg_total_buckets : 9;
-    if (lg_total_buckets - fb > 13) fb = lg_total_buckets - 13;
+    int fb = lg_total_buckets < 8 ? lg_total_buckets : 8;
+    if (lg_total_buckets - fb > 14) fb = lg_total_buckets - 14;
     return fb;
 }
 
@@ -137,6 +138,7 @@ void srs_load(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits
     PK_CUDA(cudaGetLastError());
     PK_CUDA(cudaFuncSetAttribute(msm_coarse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     PK_CUDA(cudaFuncSetAttribute(msm_coarse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    PK_CUDA(cudaFuncSetAttribute(msm_fine_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
     const int nb = max_batch_for(s);
     size_t M = (size_t)n * W;
     // level-1 chunk: keep the chunk count of one scalar set <= 2^19 so the partial lists stay small
@@ -234,37 +236,36 @@ __global__ void __launch_bounds__(256) msm_coarse_kernel(ScalarSets sets, uint32
     }
 }
 
-// counting sort of one coarse bin by the low fine_bits of the bucket id; histogram and cursors live in shared memory
-#define FS_UNROLL 8
-__global__ void __launch_bounds__(512) msm_fine_sort_kernel(const uint2* tmp, uint2* entries, const uint32_t* coarse_offset, int fine_bits) {
-    extern __shared__ uint32_t hist[];  // [2^fine_bits] then 512 scan partials
+// Counting sort of one coarse bin by the low fine_bits of the bucket id.  The bin's entries are staged in shared
+// memory (one global read per entry; bins hold ~6.6 K entries at N = 2^20), counted and ranked there, and written
+// to their final place; entries beyond the staging capacity (skewed inputs) are re-read from global memory instead.
+#define FS_THREADS 256
+#define FS_CAP 7168  // staged entries per block (56 KB)
+__global__ void __launch_bounds__(FS_THREADS) msm_fine_sort_kernel(const uint2* tmp, uint2* entries, const uint32_t* coarse_offset, int fine_bits) {
+    extern __shared__ uint2 stage[];                                    // [FS_CAP] entries, then hist[2^fine_bits], part[FS_THREADS]
     const uint32_t F = 1u << fine_bits, fmask = F - 1;
+    uint32_t* hist = reinterpret_cast<uint32_t*>(stage + FS_CAP);
     uint32_t* part = hist + F;
     const uint32_t lo = coarse_offset[blockIdx.x], hi = coarse_offset[blockIdx.x + 1];
     if (lo == hi) return;
-    for (uint32_t b = threadIdx.x; b < F; b += blockDim.x) hist[b] = 0;
+    const uint32_t size = hi - lo;
+    const uint32_t staged = size < FS_CAP ? size : FS_CAP;
+    for (uint32_t b = threadIdx.x; b < F; b += FS_THREADS) hist[b] = 0;
+    for (uint32_t i = threadIdx.x; i < staged; i += FS_THREADS) stage[i] = tmp[lo + i];
     __syncthreads();
-    // the loops are latency-bound on the global loads: keep FS_UNROLL independent loads in flight per thread
-    for (uint32_t e0 = lo + threadIdx.x; e0 < hi; e0 += FS_UNROLL * blockDim.x) {
-        uint32_t key[FS_UNROLL];
-#pragma unroll
-        for (int u = 0; u < FS_UNROLL; ++u) {
-            const uint32_t e = e0 + u * blockDim.x;
-            key[u] = e < hi ? (tmp[e].x & fmask) : 0xffffffffu;
-        }
-#pragma unroll
-        for (int u = 0; u < FS_UNROLL; ++u)
-            if (key[u] != 0xffffffffu) atomicAdd(&hist[key[u]], 1u);
+    for (uint32_t i = threadIdx.x; i < size; i += FS_THREADS) {
+        const uint32_t key = (i < staged ? stage[i].x : tmp[lo + i].x) & fmask;
+        atomicAdd(&hist[key], 1u);
     }
     __syncthreads();
-    // exclusive scan of hist[0..F): each thread owns F / blockDim consecutive counters
-    const uint32_t per = (F + blockDim.x - 1) / blockDim.x;
+    // exclusive scan of hist[0..F): each thread owns F / FS_THREADS consecutive counters
+    const uint32_t per = (F + FS_THREADS - 1) / FS_THREADS;
     const uint32_t b0 = threadIdx.x * per < F ? threadIdx.x * per : F, b1 = (b0 + per < F) ? b0 + per : F;
     uint32_t sum = 0;
     for (uint32_t b = b0; b < b1; ++b) sum += hist[b];
     part[threadIdx.x] = sum;
     __syncthreads();
-    for (unsigned d = 1; d < blockDim.x; d <<= 1) {
+    for (unsigned d = 1; d < FS_THREADS; d <<= 1) {
         uint32_t t = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
         __syncthreads();
         part[threadIdx.x] += t;
@@ -273,20 +274,10 @@ __global__ void __launch_bounds__(512) msm_fine_sort_kernel(const uint2* tmp, ui
     uint32_t run = part[threadIdx.x] - sum;
     for (uint32_t b = b0; b < b1; ++b) { uint32_t x = hist[b]; hist[b] = run; run += x; }
     __syncthreads();
-    for (uint32_t e0 = lo + threadIdx.x; e0 < hi; e0 += FS_UNROLL * blockDim.x) {
-        uint2 ent[FS_UNROLL];
-        uint32_t pos[FS_UNROLL];
-#pragma unroll
-        for (int u = 0; u < FS_UNROLL; ++u) {
-            const uint32_t e = e0 + u * blockDim.x;
-            ent[u] = e < hi ? tmp[e] : make_uint2(0xffffffffu, 0);
-        }
-#pragma unroll
-        for (int u = 0; u < FS_UNROLL; ++u)
-            pos[u] = ent[u].x != 0xffffffffu ? atomicAdd(&hist[ent[u].x & fmask], 1u) : 0;
-#pragma unroll
-        for (int u = 0; u < FS_UNROLL; ++u)
-            if (ent[u].x != 0xffffffffu) entries[lo + pos[u]] = ent[u];
+    for (uint32_t i = threadIdx.x; i < size; i += FS_THREADS) {
+        const uint2 ent = i < staged ? stage[i] : tmp[lo + i];
+        const uint32_t pos = atomicAdd(&hist[ent.x & fmask], 1u);
+        entries[lo + pos] = ent;
     }
 }
 
@@ -496,8 +487,8 @@ static void msm_enqueue_group(pk_ctx* ctx, MsmScratch& sc, cudaStream_t st, cons
     u32_scan_apply_kernel<<<tiles, 1024, 0, st>>>(sc.coarse_count.p, sc.scan_sums.p, sc.coarse_offset.p, sc.coarse_cursor.p, NC);
     msm_coarse_kernel<true><<<dgrid, 256, 2 * NC * sizeof(uint32_t), st>>>(sets, (uint32_t)n, (uint32_t)s->n, (uint32_t)base_offset, s->c, s->W,
                                                                          fine_bits, NC, sc.coarse_cursor.p, sc.tmp_entries.p);
-    msm_fine_sort_kernel<<<NC, 512, ((size_t(1) << fine_bits) + 512) * sizeof(uint32_t), st>>>(sc.tmp_entries.p, sc.entries.p,
-                                                                                            sc.coarse_offset.p, fine_bits);
+    msm_fine_sort_kernel<<<NC, FS_THREADS, FS_CAP * sizeof(uint2) + ((size_t(1) << fine_bits) + FS_THREADS) * sizeof(uint32_t), st>>>(
+        sc.tmp_entries.p, sc.entries.p, sc.coarse_offset.p, fine_bits);
     ctx->prof.kernel_launches += 6;
     if (sorted_event) PK_CUDA(cudaEventRecord(sorted_event, st));
     // accumulation levels (worst-case grids; the device-side counts bound the real work)
