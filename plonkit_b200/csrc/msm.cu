@@ -251,7 +251,20 @@ __global__ void __launch_bounds__(FS_THREADS) msm_fine_sort_kernel(const uint2* 
     const uint32_t size = hi - lo;
     const uint32_t staged = size < FS_CAP ? size : FS_CAP;
     for (uint32_t b = threadIdx.x; b < F; b += FS_THREADS) hist[b] = 0;
-    for (uint32_t i = threadIdx.x; i < staged; i += FS_THREADS) stage[i] = tmp[lo + i];
+    {
+        // all of this thread's loads are issued before the first one is consumed (the kernel is latency-bound)
+        uint2 r[FS_CAP / FS_THREADS];
+#pragma unroll
+        for (int k = 0; k < FS_CAP / FS_THREADS; ++k) {
+            const uint32_t i = threadIdx.x + k * FS_THREADS;
+            if (i < staged) r[k] = tmp[lo + i];
+        }
+#pragma unroll
+        for (int k = 0; k < FS_CAP / FS_THREADS; ++k) {
+            const uint32_t i = threadIdx.x + k * FS_THREADS;
+            if (i < staged) stage[i] = r[k];
+        }
+    }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < size; i += FS_THREADS) {
         const uint32_t key = (i < staged ? stage[i].x : tmp[lo + i].x) & fmask;
