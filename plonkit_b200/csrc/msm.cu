@@ -37,7 +37,7 @@ static inline dim3 grid1d(size_t n, int block) { return dim3((unsigned)((n + blo
 
 struct ScalarSets { const fr_t* s[MSM_MAX_BATCH]; };
 template <bool SCATTER>
-__global__ void msm_coarse_kernel(ScalarSets sets, uint32_t n, uint32_t table_n, uint32_t base_offset, int c, int W, int fine_bits,
+__global__ void msm_coarse_kernel(ScalarSets sets, uint32_t n, uint32_t table_n, uint32_t base_offset, WindowPlan plan, int fine_bits,
                                   uint32_t NC, uint32_t* coarse, uint2* tmp);
 __global__ void msm_fine_sort_kernel(const uint2* tmp, uint2* entries, const uint32_t* coarse_offset, int fine_bits);
 
@@ -51,14 +51,14 @@ __global__ void bases_to_mont_kernel(g1_affine_t* pts, size_t n) {
     p.y = p.y.to_mont();
     st_affine(pts + i, p);
 }
-// table[w][i] = 2^c * table[w-1][i]
-__global__ void srs_window_kernel(g1_affine_t* table, size_t n, int c, int W) {
+// table[w][i] = 2^(width of window w-1) * table[w-1][i]  =  2^(start bit of window w) * base_i
+__global__ void srs_window_kernel(g1_affine_t* table, size_t n, WindowPlan plan) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     g1_affine_t p = ldg_affine(table + i);
-    for (int w = 1; w < W; ++w) {
+    for (int w = 1; w < plan.W; ++w) {
         g1_xyzz_t a = g1_xyzz_t::dbl_affine(p);
-        for (int k = 1; k < c; ++k) a = a.dbl();
+        for (int k = 1; k < plan.width[w - 1]; ++k) a = a.dbl();
         p = a.to_affine();
         st_affine(table + (size_t)w * n + i, p);
     }
@@ -127,13 +127,31 @@ void srs_load(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits
     ctx->srs = nullptr;
     SrsTables* s = new SrsTables();
     ctx->srs = s;
+    // Window widths: the 255 scalar bits (254 + one spare for the signed-digit carry) are split as evenly as possible
+    // over W windows (e.g. c = 20: eight 20-bit and five 19-bit windows).  A plain "12 x 20 bits + 14 bits" split
+    // would pile the short top window's 2^20 entries onto 2^14 buckets and unbalance the per-bin sort 4:1.
+    WindowPlan plan;
+    memset(&plan, 0, sizeof(plan));
+    plan.W = W;
+    {
+        const int base = 255 / W, rem = 255 % W;
+        int maxw = 0;
+        for (int w = 0; w < W; ++w) {
+            plan.width[w] = (uint8_t)(base + (w >= W - rem ? 1 : 0));  // the wider windows sit at the top
+            if (plan.width[w] > maxw) maxw = plan.width[w];
+        }
+        PK_REQUIRE(maxw == c || (rem == 0 && maxw <= c), PK_ERR_INVALID, "window plan inconsistent");
+        c = maxw;
+    }
+    plan.c = c;
+    s->plan = plan;
     s->n = n; s->c = c; s->W = W; s->B = 1u << (c - 1);
     s->hi_bits = (c - 1) / 2 < 7 ? (c - 1) / 2 : 7;
     s->lo_bits = (c - 1) - s->hi_bits;
     s->table.alloc((size_t)W * n);
     PK_CUDA(cudaMemcpyAsync(s->table.p, bases_xy, n * 64, cudaMemcpyHostToDevice, ctx->stream));
     bases_to_mont_kernel<<<grid1d(n, 256), 256, 0, ctx->stream>>>(s->table.p, n);
-    srs_window_kernel<<<grid1d(n, 128), 128, 0, ctx->stream>>>(s->table.p, n, c, W);
+    srs_window_kernel<<<grid1d(n, 128), 128, 0, ctx->stream>>>(s->table.p, n, plan);
     ctx->prof.kernel_launches += 2;
     PK_CUDA(cudaGetLastError());
     PK_CUDA(cudaFuncSetAttribute(msm_coarse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -163,16 +181,15 @@ void srs_load(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits
 // by a per-bin counting sort on the low `fine_bits` bits held entirely in shared memory.  Global atomics per batch drop
 // from one per digit (54 M at N = 2^20 x 4 sets) to one per (block, coarse bin).
 
-// calls f(w, global_bucket, neg) for every non-zero signed base-2^c digit of the canonical scalar k
-template <class F> __device__ __forceinline__ void for_each_digit(const fr_t& k, int c, int W, uint32_t set_base, F f) {
+// calls f(w, global_bucket, neg) for every non-zero signed digit of the canonical scalar k under the window plan
+template <class F> __device__ __forceinline__ void for_each_digit(const fr_t& k, const WindowPlan& plan, uint32_t set_base, F f) {
     uint32_t carry = 0;
-    const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1;
     uint64_t acc = 0;  // sliding bit window over the limbs: registers only
     int nbits = 0, w = 0;
-    auto emit = [&](uint32_t raw) {
+    auto emit = [&](uint32_t raw, int width) {
         uint32_t d = raw + carry;
         uint32_t neg = 0;
-        if (d > half) { d = (1u << c) - d; neg = 1; carry = 1; } else carry = 0;
+        if (d > (1u << (width - 1))) { d = (1u << width) - d; neg = 1; carry = 1; } else carry = 0;
         if (d != 0) f((uint32_t)w, set_base + d - 1, neg);
         ++w;
     };
@@ -180,20 +197,21 @@ template <class F> __device__ __forceinline__ void for_each_digit(const fr_t& k,
     for (int limb = 0; limb < 8; ++limb) {
         acc |= (uint64_t)k.v[limb] << nbits;
         nbits += 32;
-        while (nbits >= c && w < W) {
-            emit((uint32_t)acc & mask);
-            acc >>= c;
-            nbits -= c;
+        while (w < plan.W && nbits >= (int)plan.width[w]) {
+            const int width = plan.width[w];
+            emit((uint32_t)acc & ((1u << width) - 1), width);
+            acc >>= width;
+            nbits -= width;
         }
     }
-    if (w < W) emit((uint32_t)acc & mask);  // top window: the remaining (< c) bits
+    if (w < plan.W) emit((uint32_t)acc, plan.width[w]);  // top window: the remaining bits (fewer than its width)
 }
 
 #define COARSE_PER_THREAD 16
 // SCATTER = false: coarse_counts[bin] += digits of this block in bin.
 // SCATTER = true : reserves a range per (block, bin) in coarse_cursor and writes the entries there.
 template <bool SCATTER>
-__global__ void __launch_bounds__(256) msm_coarse_kernel(ScalarSets sets, uint32_t n, uint32_t table_n, uint32_t base_offset, int c, int W,
+__global__ void __launch_bounds__(256) msm_coarse_kernel(ScalarSets sets, uint32_t n, uint32_t table_n, uint32_t base_offset, WindowPlan plan,
                                                          int fine_bits, uint32_t NC, uint32_t* coarse, uint2* tmp) {
     extern __shared__ uint32_t sh[];  // cnt[NC] (+ base[NC] when scattering)
     uint32_t* cnt = sh;
@@ -203,14 +221,14 @@ __global__ void __launch_bounds__(256) msm_coarse_kernel(ScalarSets sets, uint32
     // a block owns COARSE_PER_THREAD * blockDim consecutive scalars: many entries per (block, bin) keep the global
     // atomics rare and the scattered runs long
     const uint32_t i0 = blockIdx.x * (blockDim.x * COARSE_PER_THREAD) + threadIdx.x;
-    const uint32_t set_base = blockIdx.y << (c - 1);
+    const uint32_t set_base = blockIdx.y << (plan.c - 1);
     const fr_t* src = sets.s[blockIdx.y];
     for (int r = 0; r < COARSE_PER_THREAD; ++r) {
         const uint32_t i = i0 + r * blockDim.x;
         if (i >= n) break;
         fr_t k = ld_fp(src + i).from_mont();
         if (k.is_zero()) continue;
-        for_each_digit(k, c, W, set_base, [&](uint32_t, uint32_t g, uint32_t) { atomicAdd(&cnt[g >> fine_bits], 1u); });
+        for_each_digit(k, plan, set_base, [&](uint32_t, uint32_t g, uint32_t) { atomicAdd(&cnt[g >> fine_bits], 1u); });
     }
     __syncthreads();
     if (!SCATTER) {
@@ -228,7 +246,7 @@ __global__ void __launch_bounds__(256) msm_coarse_kernel(ScalarSets sets, uint32
         if (i >= n) break;
         fr_t k = ld_fp(src + i).from_mont();
         if (k.is_zero()) continue;
-        for_each_digit(k, c, W, set_base, [&](uint32_t w, uint32_t g, uint32_t neg) {
+        for_each_digit(k, plan, set_base, [&](uint32_t w, uint32_t g, uint32_t neg) {
             const uint32_t bin = g >> fine_bits;
             const uint32_t slot = atomicAdd(&cnt[bin], 1u);
             tmp[base[bin] + slot] = make_uint2(g, (w * table_n + base_offset + i) | (neg << 31));
@@ -492,13 +510,13 @@ static void msm_enqueue_group(pk_ctx* ctx, MsmScratch& sc, cudaStream_t st, cons
     PK_CUDA(cudaMemsetAsync(sc.coarse_count.p, 0, (size_t)(NC + 1) * sizeof(uint32_t), st));
     PK_CUDA(cudaMemsetAsync(sc.buckets.p, 0, (size_t)NB * sizeof(g1_xyzz_t), st));
     dim3 dgrid((unsigned)((n + 256 * COARSE_PER_THREAD - 1) / (256 * COARSE_PER_THREAD)), nb);
-    msm_coarse_kernel<false><<<dgrid, 256, NC * sizeof(uint32_t), st>>>(sets, (uint32_t)n, (uint32_t)s->n, (uint32_t)base_offset, s->c, s->W,
+    msm_coarse_kernel<false><<<dgrid, 256, NC * sizeof(uint32_t), st>>>(sets, (uint32_t)n, (uint32_t)s->n, (uint32_t)base_offset, s->plan,
                                                                       fine_bits, NC, sc.coarse_count.p, nullptr);
     const uint32_t tiles = (NC + 4095) / 4096;
     u32_scan_tile_sums_kernel<<<tiles, 1024, 0, st>>>(sc.coarse_count.p, sc.scan_sums.p, NC);
     u32_scan_spine_kernel<<<1, 1024, 0, st>>>(sc.scan_sums.p, tiles, sc.counts.p, sc.coarse_offset.p + NC);
     u32_scan_apply_kernel<<<tiles, 1024, 0, st>>>(sc.coarse_count.p, sc.scan_sums.p, sc.coarse_offset.p, sc.coarse_cursor.p, NC);
-    msm_coarse_kernel<true><<<dgrid, 256, 2 * NC * sizeof(uint32_t), st>>>(sets, (uint32_t)n, (uint32_t)s->n, (uint32_t)base_offset, s->c, s->W,
+    msm_coarse_kernel<true><<<dgrid, 256, 2 * NC * sizeof(uint32_t), st>>>(sets, (uint32_t)n, (uint32_t)s->n, (uint32_t)base_offset, s->plan,
                                                                          fine_bits, NC, sc.coarse_cursor.p, sc.tmp_entries.p);
     msm_fine_sort_kernel<<<NC, FS_THREADS, FS_CAP * sizeof(uint2) + ((size_t(1) << fine_bits) + FS_THREADS) * sizeof(uint32_t), st>>>(
         sc.tmp_entries.p, sc.entries.p, sc.coarse_offset.p, fine_bits);

@@ -6,6 +6,13 @@ namespace pk {
 
 static const int MSM_MAX_BATCH = 4;
 
+// signed-digit window layout: window w covers `width[w]` bits starting at the sum of the lower widths; c = max width
+struct WindowPlan {
+    int W;
+    int c;
+    uint8_t width[64];
+};
+
 // per-stream working set of one MSM group
 struct MsmScratch {
     int max_sets = 0;
@@ -25,6 +32,7 @@ struct SrsTables {
     int c = 0;               // window bits (signed digits in (-2^(c-1), 2^(c-1)])
     int W = 0;               // windows = ceil(255 / c)
     uint32_t B = 0;          // buckets per scalar set = 2^(c-1)
+    WindowPlan plan;
     int lo_bits = 0, hi_bits = 0;  // bucket id = hi * 2^lo_bits + lo (two-level bucket reduction)
     DevBuf<g1_affine_t> table;   // [W][n]: table[w][i] = 2^(c*w) * base_i, affine, Montgomery form
 
