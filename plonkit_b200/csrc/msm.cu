@@ -119,7 +119,7 @@ void srs_load(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits
     PK_REQUIRE(n >= 1, PK_ERR_INVALID, "empty SRS");
     PK_REQUIRE(n <= (uint64_t(1) << 26), PK_ERR_DEGREE_TOO_LARGE, "SRS larger than 2^26 bases (SETUP_MAX_POW2, src/plonk.rs:27)");
     int c = window_bits ? window_bits : pick_window_bits(n);
-    PK_REQUIRE(c >= 2 && c <= 24, PK_ERR_INVALID, "window_bits out of range");
+    PK_REQUIRE(c >= 4 && c <= 24, PK_ERR_INVALID, "window_bits out of range (4..24)");
     int W = (255 + c - 1) / c;
     PK_REQUIRE((uint64_t)W * n < (uint64_t(1) << 31), PK_ERR_DEGREE_TOO_LARGE, "window table index does not fit 31 bits");
     PK_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -140,7 +140,6 @@ void srs_load(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits
             plan.width[w] = (uint8_t)(base + (w >= W - rem ? 1 : 0));  // the wider windows sit at the top
             if (plan.width[w] > maxw) maxw = plan.width[w];
         }
-        PK_REQUIRE(maxw == c || (rem == 0 && maxw <= c), PK_ERR_INVALID, "window plan inconsistent");
         c = maxw;
     }
     plan.c = c;
@@ -258,7 +257,7 @@ __global__ void __launch_bounds__(256) msm_coarse_kernel(ScalarSets sets, uint32
 // memory (one global read per entry; bins hold ~6.6 K entries at N = 2^20), counted and ranked there, and written
 // to their final place; entries beyond the staging capacity (skewed inputs) are re-read from global memory instead.
 #define FS_THREADS 256
-#define FS_CAP 7168  // staged entries per block (56 KB)
+#define FS_CAP 9216  // staged entries per block (72 KB): the fullest bins of the balanced window plan hold ~8.7 K at N = 2^20
 __global__ void __launch_bounds__(FS_THREADS) msm_fine_sort_kernel(const uint2* tmp, uint2* entries, const uint32_t* coarse_offset, int fine_bits) {
     extern __shared__ uint2 stage[];                                    // [FS_CAP] entries, then hist[2^fine_bits], part[FS_THREADS]
     const uint32_t F = 1u << fine_bits, fmask = F - 1;
@@ -270,17 +269,20 @@ __global__ void __launch_bounds__(FS_THREADS) msm_fine_sort_kernel(const uint2* 
     const uint32_t staged = size < FS_CAP ? size : FS_CAP;
     for (uint32_t b = threadIdx.x; b < F; b += FS_THREADS) hist[b] = 0;
     {
-        // all of this thread's loads are issued before the first one is consumed (the kernel is latency-bound)
-        uint2 r[FS_CAP / FS_THREADS];
+        // many loads in flight per thread before the first one is consumed (the kernel is latency-bound)
+        constexpr int HALF = FS_CAP / FS_THREADS / 2;
+        for (int h = 0; h < 2; ++h) {
+            uint2 r[HALF];
 #pragma unroll
-        for (int k = 0; k < FS_CAP / FS_THREADS; ++k) {
-            const uint32_t i = threadIdx.x + k * FS_THREADS;
-            if (i < staged) r[k] = tmp[lo + i];
-        }
+            for (int k = 0; k < HALF; ++k) {
+                const uint32_t i = threadIdx.x + (h * HALF + k) * FS_THREADS;
+                if (i < staged) r[k] = tmp[lo + i];
+            }
 #pragma unroll
-        for (int k = 0; k < FS_CAP / FS_THREADS; ++k) {
-            const uint32_t i = threadIdx.x + k * FS_THREADS;
-            if (i < staged) stage[i] = r[k];
+            for (int k = 0; k < HALF; ++k) {
+                const uint32_t i = threadIdx.x + (h * HALF + k) * FS_THREADS;
+                if (i < staged) stage[i] = r[k];
+            }
         }
     }
     __syncthreads();
