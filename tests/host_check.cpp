@@ -1,6 +1,8 @@
 // Host build (g++) of the product's field / curve / transcript headers, for CPU-side checks of the exact
 // instruction sequences the device code runs (the carry-flag primitives are emulated on the host, see fp.cuh).
 #include "../plonkit_b200/csrc/ec.cuh"
+#include "../tools/micro/fp_f64.cuh"
+#include <cfenv>
 #include "../plonkit_b200/csrc/keccak_host.hpp"
 using namespace pk;
 
@@ -13,6 +15,14 @@ static void store_pt(const g1_affine_t& p, uint64_t* d) { if (p.is_inf()) { mems
 extern "C" {
 void hc_mont_mul(int which, const uint32_t* a, const uint32_t* b, uint32_t* o, int n) {
     for (int i = 0; i < n; ++i) { if (which == 0) limbs::mont_mul<FrParams>(o + 8 * i, a + 8 * i, b + 8 * i); else limbs::mont_mul<FqParams>(o + 8 * i, a + 8 * i, b + 8 * i); }
+}
+// the FP64-pipe multiplier (fp_f64.cuh): same contract as hc_mont_mul; the device uses DFMA.RZ, the host emulates it by
+// running fma() under round-toward-zero
+void hc_mont_mul_f64(int which, const uint32_t* a, const uint32_t* b, uint32_t* o, int n) {
+    const int old = fegetround();
+    fesetround(FE_TOWARDZERO);
+    for (int i = 0; i < n; ++i) { if (which == 0) f64::mont_mul<FrParams>(o + 8 * i, a + 8 * i, b + 8 * i); else f64::mont_mul<FqParams>(o + 8 * i, a + 8 * i, b + 8 * i); }
+    fesetround(old);
 }
 void hc_fr_ops(const uint64_t* a, const uint64_t* b, uint64_t* add, uint64_t* sub, uint64_t* mul, uint64_t* inv, int n) {
     for (int i = 0; i < n; ++i) {

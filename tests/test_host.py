@@ -165,7 +165,7 @@ def test_gen_key_range_check_mirrors_reference():
 @pytest.fixture(scope="module")
 def hc(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("hc") / "host_check.so")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", os.path.join(ROOT, "tests", "host_check.cpp"), "-o", so])
+    subprocess.check_call(["g++", "-O2", "-frounding-math", "-std=c++17", "-shared", "-fPIC", "-x", "c++", os.path.join(ROOT, "tests", "host_check.cpp"), "-o", so])
     return ctypes.CDLL(so)
 
 
@@ -182,6 +182,23 @@ def test_montgomery_multiplier_sequence(hc):
         A, B = ints_to_limbs(a).view(np.uint32), ints_to_limbs(b).view(np.uint32)
         out = np.zeros_like(A)
         hc.hc_mont_mul(which, _p(A), _p(B), _p(out), len(a))
+        rinv = pow(1 << 256, -1, p)
+        assert limbs_to_ints(out.view(np.uint64)) == [x * y * rinv % p for x, y in zip(a, b)]
+
+
+def test_fp64_pipe_multiplier_sequence(hc):
+    """fp_f64.cuh: the DFMA-based Montgomery product must agree with Python integers (and so with the IMAD one) on edge
+    values, limb patterns that maximise every column chain, and random inputs."""
+    rng = np.random.default_rng(9)
+    m51 = (1 << 51) - 1
+    for which, p in ((0, R_MOD), (1, Q_MOD)):
+        edge = [0, 1, 2, p - 1, p - 2, 1 << 253, (1 << 256) % p, (1 << 51) - 1, (1 << 51), ((1 << 255) - 1) % p]
+        pat = [sum(int(rng.choice([0, m51, m51 - 1, 1])) << (51 * i) for i in range(5)) % p for _ in range(200)]
+        a = edge * len(edge) + pat + [int.from_bytes(rng.bytes(32), "little") % p for _ in range(5000)]
+        b = [e for e in edge for _ in edge] + pat[::-1] + [int.from_bytes(rng.bytes(32), "little") % p for _ in range(5000)]
+        A, B = ints_to_limbs(a).view(np.uint32), ints_to_limbs(b).view(np.uint32)
+        out = np.zeros_like(A)
+        hc.hc_mont_mul_f64(which, _p(A), _p(B), _p(out), len(a))
         rinv = pow(1 << 256, -1, p)
         assert limbs_to_ints(out.view(np.uint64)) == [x * y * rinv % p for x, y in zip(a, b)]
 
