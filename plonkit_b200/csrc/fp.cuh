@@ -157,6 +157,7 @@ template <class P> PK_HD void sub_mod(uint32_t* r, const uint32_t* a, const uint
 
 // ---------------------------------------------------------------- field element
 template <class P> struct alignas(16) Fp {
+    typedef P params;
     uint32_t v[8];
 
     static PK_HD Fp zero() {

@@ -2,6 +2,7 @@
 // instruction sequences the device code runs (the carry-flag primitives are emulated on the host, see fp.cuh).
 #include "../plonkit_b200/csrc/ec.cuh"
 #include "../tools/micro/fp_f64.cuh"
+#include "../tools/micro/fp_wide.cuh"
 #include <cfenv>
 #include "../plonkit_b200/csrc/keccak_host.hpp"
 using namespace pk;
@@ -23,6 +24,18 @@ void hc_mont_mul_f64(int which, const uint32_t* a, const uint32_t* b, uint32_t* 
     fesetround(FE_TOWARDZERO);
     for (int i = 0; i < n; ++i) { if (which == 0) f64::mont_mul<FrParams>(o + 8 * i, a + 8 * i, b + 8 * i); else f64::mont_mul<FqParams>(o + 8 * i, a + 8 * i, b + 8 * i); }
     fesetround(old);
+}
+// Karatsuba + separate-reduction multiplier (fp.cuh): mode 0 = mont_mul_k(a,b), 1 = mont_sqr_k(a), 2 = mont_mul_sub_mul(a,b,c,d)
+void hc_mont_wide(int which, int mode, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, uint32_t* o, int n) {
+    for (int i = 0; i < n; ++i) {
+        const uint32_t *A = a + 8 * i, *B = b + 8 * i, *C = c + 8 * i, *D = d + 8 * i;
+        uint32_t* O = o + 8 * i;
+        if (which == 0) {
+            if (mode == 0) limbs::mont_mul_k<FrParams>(O, A, B); else if (mode == 1) limbs::mont_sqr_k<FrParams>(O, A); else limbs::mont_mul_sub_mul<FrParams>(O, A, B, C, D);
+        } else {
+            if (mode == 0) limbs::mont_mul_k<FqParams>(O, A, B); else if (mode == 1) limbs::mont_sqr_k<FqParams>(O, A); else limbs::mont_mul_sub_mul<FqParams>(O, A, B, C, D);
+        }
+    }
 }
 void hc_fr_ops(const uint64_t* a, const uint64_t* b, uint64_t* add, uint64_t* sub, uint64_t* mul, uint64_t* inv, int n) {
     for (int i = 0; i < n; ++i) {

@@ -186,6 +186,32 @@ def test_montgomery_multiplier_sequence(hc):
         assert limbs_to_ints(out.view(np.uint64)) == [x * y * rinv % p for x, y in zip(a, b)]
 
 
+def test_karatsuba_multiplier_sequences(hc):
+    """fp.cuh mont_mul_k / mont_sqr_k / mont_mul_sub_mul (Karatsuba product, separate Montgomery reduction, lazy
+    reduction of a difference of products) against Python integers: edge values, halves that are equal / ordered
+    either way (both signs of the Karatsuba cross term), all-ones limbs (every carry path), random inputs."""
+    rng = np.random.default_rng(10)
+    ones = (1 << 128) - 1
+    for which, p in ((0, R_MOD), (1, Q_MOD)):
+        edge = [0, 1, 2, p - 1, p - 2, 1 << 253, (1 << 256) % p, (1 << 128) - 1, 1 << 128, (ones << 128 | ones) % p,
+                (5 << 128) | 5, (7 << 128) | 3, (3 << 128) | 7, ((1 << 125) << 128) | ones, (1 << 253) | ones]
+        pat = [sum(int(rng.choice([0, 0xffffffff, 0xfffffffe, 1, 0x80000000])) << (32 * i) for i in range(8)) % p for _ in range(400)]
+        rnd = lambda k: [int.from_bytes(rng.bytes(32), "little") % p for _ in range(k)]
+        a = edge * len(edge) + pat + rnd(4000)
+        b = [e for e in edge for _ in edge] + pat[::-1] + rnd(4000)
+        c = b[::-1][:len(a)]
+        d = a[::-1][:len(a)]
+        A, B, C, D = (ints_to_limbs(x).view(np.uint32) for x in (a, b, c, d))
+        rinv = pow(1 << 256, -1, p)
+        out = np.zeros_like(A)
+        hc.hc_mont_wide(which, 0, _p(A), _p(B), _p(C), _p(D), _p(out), len(a))
+        assert limbs_to_ints(out.view(np.uint64)) == [x * y * rinv % p for x, y in zip(a, b)]
+        hc.hc_mont_wide(which, 1, _p(A), _p(B), _p(C), _p(D), _p(out), len(a))
+        assert limbs_to_ints(out.view(np.uint64)) == [x * x * rinv % p for x in a]
+        hc.hc_mont_wide(which, 2, _p(A), _p(B), _p(C), _p(D), _p(out), len(a))
+        assert limbs_to_ints(out.view(np.uint64)) == [(x * y - z * w) * rinv % p for x, y, z, w in zip(a, b, c, d)]
+
+
 def test_fp64_pipe_multiplier_sequence(hc):
     """fp_f64.cuh: the DFMA-based Montgomery product must agree with Python integers (and so with the IMAD one) on edge
     values, limb patterns that maximise every column chain, and random inputs."""
