@@ -131,12 +131,6 @@ def effective_cores():
     return cores
 
 
-def cpu_sample_log_n(cores, log_n):
-    if cores >= 16:
-        return log_n
-    return min(log_n, 17)
-
-
 def run_cpu_prove(log_n_s, threads, repeats, warm):
     """Times the oracle's CPU prover (restated bellman algorithms) on a poseidon-shaped circuit of 2^log_n_s gates."""
     from oracle import oracle as orc
@@ -155,12 +149,24 @@ def run_cpu_prove(log_n_s, threads, repeats, warm):
     return times
 
 
+def cpu_sample_log_n(cores, log_n, proves, budget_s):
+    """Largest sample circuit 2^L (L <= log_n) for which `proves` CPU proofs are predicted to fit in `budget_s` seconds:
+    one 2^13 proof is timed and extrapolated linearly in the gate count (SRS generation on the CPU, which also grows
+    linearly, is budgeted at one extra proof)."""
+    t13 = run_cpu_prove(13, cores, 1, 0)[0][1]
+    L = 13
+    while L < log_n and t13 * (1 << (L + 1 - 13)) * (proves + 1) <= budget_s:
+        L += 1
+    return L
+
+
 def bench_reference(args):
     world, rank, local, td = 1, int(os.environ.get("RANK", "0")), 0, None
     if rank != 0:
         return 0
     cores = effective_cores()
-    ls = cpu_sample_log_n(cores, args.log_n)
+    # each step = one proof of a bounded sample circuit, sized so that warmup + steps proofs end within ~3 minutes
+    ls = cpu_sample_log_n(cores, args.log_n, args.steps + args.warmup, 170.0)
     times = run_cpu_prove(ls, cores, args.steps, args.warmup)
     scale = float(1 << (args.log_n - ls))
     per_step = sum(t[0] for t in times) / len(times) * scale
@@ -290,8 +296,8 @@ def bench_ours(args):
     }
     if world == 1 and not args.no_cpu:
         cores = effective_cores()
-        ls = cpu_sample_log_n(cores, args.log_n)
-        t = run_cpu_prove(ls, cores, 1, 1 if ls < 20 else 0)
+        ls = cpu_sample_log_n(cores, args.log_n, 1, 25.0)  # bounded sample: ~10-30 s of CPU work
+        t = run_cpu_prove(ls, cores, 1, 0)
         scale = float(1 << (args.log_n - ls))
         sample = "one full prove of the oracle port at 2^%d gates, %d threads (setup polynomials excluded)" % (ls, cores)
         if ls != args.log_n:
