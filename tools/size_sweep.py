@@ -31,10 +31,23 @@ def main():
             ctx.msm_g1(s)
             t = time.perf_counter(); ctx.msm_g1(s); dt = time.perf_counter() - t
             print("MSM 2^20 witness-like (40%% zero, 10%% one), through host buffers: %.2f ms" % (dt * 1e3), flush=True)
-    for lg in (10, 12, 14, 16):
+    for lg in (10, 12, 14, 16, 18, 20):
         ctx.srs_load_g1(srs[: 1 << lg])
         t = time.perf_counter(); ctx.ec_intt_g1(lg); dt = time.perf_counter() - t
-        print("EC-iNTT (dump-lagrange) 2^%d: %.1f ms" % (lg, dt * 1e3), flush=True)
+        print("EC-iNTT (dump-lagrange) 2^%d: %.1f ms  (HBM-roofline frac %.6f at 128 B/point)" % (lg, dt * 1e3, 128.0 * (1 << lg) / dt / 6571.6e9), flush=True)
+    # restated CPU baseline (oracle port, all usable host cores) for the same primitives, bounded sizes
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import effective_cores
+    cores = effective_cores()
+    x = synth.random_field_elements(1 << 20, seed=5)
+    t = time.perf_counter(); orc.ntt(x, threads=cores); dt = time.perf_counter() - t
+    print("CPU (oracle port, %d threads) NTT 2^20: %.1f ms  %.4f Gelem/s" % (cores, dt * 1e3, (1 << 20) / dt / 1e9), flush=True)
+    t = time.perf_counter(); orc.lde4(x, threads=cores); dt = time.perf_counter() - t
+    print("CPU (oracle port, %d threads) LDE4 2^20: %.1f ms" % (cores, dt * 1e3), flush=True)
+    t = time.perf_counter(); orc.msm(x, srs[: 1 << 20], threads=cores); dt = time.perf_counter() - t
+    print("CPU (oracle port, %d threads) MSM 2^20: %.1f ms  %.3f Mscalar/s" % (cores, dt * 1e3, (1 << 20) / dt / 1e6), flush=True)
+    t = time.perf_counter(); orc.ec_intt(srs[: 1 << 12], threads=cores); dt = time.perf_counter() - t
+    print("CPU (oracle port, %d threads) EC-iNTT 2^12: %.1f ms" % (cores, dt * 1e3), flush=True)
     for lg in (22, 24):
         if lg > max_lg:
             break
