@@ -145,6 +145,15 @@ def test_msm_2pow16_uniform_and_skewed(ctx, orc):
     s[: n // 2] = ints_to_limbs([1])[0]          # one giant bucket
     s[n // 2: n // 2 + n // 4] = 0
     assert (ctx.msm_g1(s) == orc.msm(s, bases, threads=8)).all()
+    # many repeated bases and P / -P pairs inside the same buckets: P + P and P + (-P) inside the accumulation
+    b2 = bases.copy()
+    b2[1::2] = b2[0::2]
+    neg = limbs_to_ints(b2[2::4, 4:].reshape(-1, 4))
+    b2[2::4, 4:] = ints_to_limbs([Q_MOD - v for v in neg]).reshape(-1, 4)
+    _load(ctx, b2)
+    s2 = synth.random_field_elements(n, seed=6)
+    s2[1::2] = s2[0::2]
+    assert (ctx.msm_g1(s2) == orc.msm(s2, b2, threads=8)).all()
 
 
 def test_srs_generator_matches_reference_key(ctx, simple_key):
