@@ -60,6 +60,15 @@ int pk_ntt(pk_ctx* ctx, uint64_t* fr, uint32_t log_n, int inverse, int coset, in
 /* Polynomial::bitreversed_lde_using_bitreversed_ntt(factor = 4, coset_factor = 7): n coefficients -> 4n evaluations
  * on 7*H_4n.  bitreversed = 0: natural order; 1: the 4n-point bit-reversed order bellman's LDE returns. */
 int pk_lde4(pk_ctx* ctx, const uint64_t* coeffs, uint32_t log_n, uint64_t* out_4n, int bitreversed, int fmt);
+/* ---- polynomial primitives (a12, a14 of SURVEY.md section 8): canonical limbs in and out ------------------------------
+ * Polynomial<Fr, Coefficients>::evaluate_at(worker, z) -> sum_i coeffs[i] z^i  (call sites behind src/plonk.rs:140,152). */
+int pk_poly_evaluate_at(pk_ctx* ctx, const uint64_t* coeffs, uint64_t n, const uint64_t z[4], uint64_t out[4]);
+/* kate_commitment::divide_single(poly, z): the n coefficients of (p(X) - p(z)) / (X - z), top coefficient 0. */
+int pk_poly_divide_by_linear(pk_ctx* ctx, const uint64_t* coeffs, uint64_t n, const uint64_t z[4], uint64_t* quotient);
+/* Polynomial<Fr, Values>::calculate_shifted_grand_product: out[0] = 1, out[i] = out[i-1] * values[i-1]. */
+int pk_poly_shifted_grand_product(pk_ctx* ctx, const uint64_t* values, uint64_t n, uint64_t* out);
+/* Polynomial<Fr, Values>::batch_inversion: values[i] <- values[i]^-1 in place, zeros stay zero. */
+int pk_poly_batch_inversion(pk_ctx* ctx, uint64_t* values, uint64_t n);
 /* multiexp::dense_multiexp / commit_using_monomials: sum_i scalars[i] * SRS[base_offset + i], normalised to affine. */
 int pk_msm_g1(pk_ctx* ctx, const uint64_t* scalars, uint64_t n, uint64_t base_offset, uint64_t out_xy[8], int* is_infinity,
               int fmt);

@@ -563,6 +563,27 @@ void orc_setup_commitments(const orc_assembly* as, const uint64_t* srs, uint64_t
 static double g_last_setup_s = 0, g_last_prove_s = 0;
 // seconds spent by the last orc_prove in (a) rebuilding the setup polynomials, which the reference does once in
 // prepare_setup_for_prover (src/plonk.rs:104), and (b) everything SetupForProver::prove does per call
+// Polynomial primitives of bellman restated one by one (checkers for pk_poly_*): op 0 evaluate_at (Horner), 1 divide_single
+// by (X - z), 2 calculate_shifted_grand_product, 3 batch_inversion (zeros stay zero).  Canonical limbs in and out.
+void orc_poly_op(int op, const uint64_t* in, uint64_t n, const uint64_t* z, uint64_t* out) {
+    init_fields();
+    hvec<Fr> v(n);
+    for (uint64_t i = 0; i < n; ++i) v[i] = Fr::from_canonical(in + 4 * i);
+    if (op == 0) {
+        Fr zz = Fr::from_canonical(z), acc = Fr::zero();
+        for (uint64_t i = n; i-- > 0;) acc = acc * zz + v[i];
+        acc.to_canonical(out);
+    } else if (op == 1) {
+        hvec<Fr> q = divide_by_linear(v, Fr::from_canonical(z));
+        for (uint64_t i = 0; i < n; ++i) q[i].to_canonical(out + 4 * i);
+    } else if (op == 2) {
+        Fr acc = Fr::one();
+        for (uint64_t i = 0; i < n; ++i) { acc.to_canonical(out + 4 * i); acc = acc * v[i]; }
+    } else {
+        for (uint64_t i = 0; i < n; ++i) { Fr r = v[i].is_zero() ? Fr::zero() : v[i].inverse(); r.to_canonical(out + 4 * i); }
+    }
+}
+
 void orc_last_timings(double* out) { out[0] = g_last_setup_s; out[1] = g_last_prove_s; }
 
 int64_t orc_prove(const orc_assembly* as, const uint64_t* srs, uint8_t* proof_out, uint64_t* challenges_out, int threads) {

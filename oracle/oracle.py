@@ -112,6 +112,17 @@ def lde4(coeffs, threads=1):
     return out
 
 
+def poly_op(op, data, z=None):
+    """bellman polynomial primitives restated serially (oracle.cpp orc_poly_op): op in evaluate_at | divide_by_linear |
+    shifted_grand_product | batch_inversion"""
+    code = {"evaluate_at": 0, "divide_by_linear": 1, "shifted_grand_product": 2, "batch_inversion": 3}[op]
+    a = np.ascontiguousarray(data, dtype=np.uint64).reshape(-1, 4)
+    zz = np.ascontiguousarray(z if z is not None else np.zeros(4), dtype=np.uint64).reshape(4)
+    out = np.zeros(4, dtype=np.uint64) if code == 0 else np.zeros_like(a)
+    lib().orc_poly_op(code, _p(a), ctypes.c_uint64(a.shape[0]), _p(zz), _p(out))
+    return out
+
+
 def msm(scalars, bases, threads=1):
     s = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
     b = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)

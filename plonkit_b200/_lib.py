@@ -28,7 +28,8 @@ EXPORTS = [
     "pk_msm_g1", "pk_ec_intt_g1", "pk_setup_create", "pk_setup_destroy", "pk_setup_commitments", "pk_witness_upload",
     "pk_prove", "pk_profile_enable", "pk_profile_reset", "pk_profile_get", "pk_bench_ntt", "pk_bench_msm",
     "pk_bench_fieldmul", "pk_timer_begin", "pk_timer_end", "pk_g1_sum", "pk_dev_fr_convert", "pk_dev_ntt_rows",
-    "pk_dev_twiddle",
+    "pk_dev_twiddle", "pk_poly_evaluate_at", "pk_poly_divide_by_linear", "pk_poly_shifted_grand_product",
+    "pk_poly_batch_inversion",
 ]
 
 
@@ -121,6 +122,10 @@ def load():
     lib.pk_dev_fr_convert.argtypes = [vp, vp, u64, i32]
     lib.pk_dev_ntt_rows.argtypes = [vp, vp, u32, u64, i32]
     lib.pk_dev_twiddle.argtypes = [vp, vp, u64, u64, u32, u64, i32]
+    lib.pk_poly_evaluate_at.argtypes = [vp, vp, u64, vp, vp]
+    lib.pk_poly_divide_by_linear.argtypes = [vp, vp, u64, vp, vp]
+    lib.pk_poly_shifted_grand_product.argtypes = [vp, vp, u64, vp]
+    lib.pk_poly_batch_inversion.argtypes = [vp, vp, u64]
     lib.pk_timer_begin.argtypes = [vp]
     lib.pk_timer_end.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     _lib = lib
@@ -190,6 +195,34 @@ class Context:
         out = np.zeros((4 * a.shape[0], 4), dtype=np.uint64)
         self._check(self._lib.pk_lde4(self._h, _ptr(a), log_n, _ptr(out), int(bitreversed), fmt))
         return out
+
+    # ---- polynomial primitives (bellman's evaluate_at / divide_single / calculate_shifted_grand_product / batch_inversion)
+    def poly_evaluate_at(self, coeffs, z):
+        c = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, 4)
+        zz = np.ascontiguousarray(z, dtype=np.uint64).reshape(4)
+        out = np.zeros(4, dtype=np.uint64)
+        self._check(self._lib.pk_poly_evaluate_at(self._h, _ptr(c) if c.shape[0] else None, c.shape[0], _ptr(zz), _ptr(out)))
+        return out
+
+    def poly_divide_by_linear(self, coeffs, z):
+        c = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, 4)
+        zz = np.ascontiguousarray(z, dtype=np.uint64).reshape(4)
+        out = np.zeros_like(c)
+        self._check(self._lib.pk_poly_divide_by_linear(self._h, _ptr(c) if c.shape[0] else None, c.shape[0], _ptr(zz),
+                                                       _ptr(out) if c.shape[0] else None))
+        return out
+
+    def poly_shifted_grand_product(self, values):
+        v = np.ascontiguousarray(values, dtype=np.uint64).reshape(-1, 4)
+        out = np.zeros_like(v)
+        self._check(self._lib.pk_poly_shifted_grand_product(self._h, _ptr(v) if v.shape[0] else None, v.shape[0],
+                                                            _ptr(out) if v.shape[0] else None))
+        return out
+
+    def poly_batch_inversion(self, values):
+        v = np.ascontiguousarray(values, dtype=np.uint64).reshape(-1, 4).copy()
+        self._check(self._lib.pk_poly_batch_inversion(self._h, _ptr(v) if v.shape[0] else None, v.shape[0]))
+        return v
 
     def msm_g1(self, scalars, base_offset=0, fmt=FMT_CANONICAL):
         s = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)

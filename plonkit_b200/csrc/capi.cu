@@ -156,6 +156,77 @@ int pk_ntt(pk_ctx* ctx, uint64_t* fr, uint32_t log_n, int inverse, int coset, in
     PK_API_END(ctx)
 }
 
+// ---------------------------------------------------------------- polynomial primitives
+static void upload_fr(pk_ctx* ctx, DevBuf<fr_t>& d, const uint64_t* host, size_t n) {
+    d.alloc(n);
+    PK_CUDA(cudaMemcpyAsync(d.p, host, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    fr_to_mont(ctx, d.p, n);
+}
+static void download_fr(pk_ctx* ctx, fr_t* dev, uint64_t* host, size_t n) {
+    fr_from_mont(ctx, dev, dev, n);
+    PK_CUDA(cudaMemcpyAsync(host, dev, n * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    PK_CUDA(cudaGetLastError());
+}
+
+int pk_poly_evaluate_at(pk_ctx* ctx, const uint64_t* coeffs, uint64_t n, const uint64_t z[4], uint64_t out[4]) {
+    PK_API_BEGIN(ctx)
+    PK_REQUIRE(z != nullptr && out != nullptr && (coeffs != nullptr || n == 0), PK_ERR_INVALID, "null argument");
+    if (n == 0) { memset(out, 0, 32); return PK_OK; }
+    DevBuf<fr_t> c, pw(n);
+    upload_fr(ctx, c, coeffs, n);
+    poly_powers(ctx, pw.p, host_load_canonical<fr_t>(z), n);
+    const fr_t* polys[1] = {c.p};
+    const fr_t* pows[1] = {pw.p};
+    fr_t r;
+    poly_dot_batch(ctx, 1, polys, pows, n, &r);
+    host_store_canonical(r, out);
+    PK_API_END(ctx)
+}
+
+int pk_poly_divide_by_linear(pk_ctx* ctx, const uint64_t* coeffs, uint64_t n, const uint64_t z[4], uint64_t* quotient) {
+    PK_API_BEGIN(ctx)
+    PK_REQUIRE(z != nullptr && (n == 0 || (coeffs != nullptr && quotient != nullptr)), PK_ERR_INVALID, "null argument");
+    if (n == 0) return PK_OK;
+    const fr_t zf = host_load_canonical<fr_t>(z);
+    if (zf.is_zero()) {  // division by X: a shift
+        memmove(quotient, coeffs + 4, (n - 1) * 32);
+        memset(quotient + 4 * (n - 1), 0, 32);
+        return PK_OK;
+    }
+    DevBuf<fr_t> c, zp(n), zi(n), q(n), tmp(n);
+    upload_fr(ctx, c, coeffs, n);
+    poly_powers(ctx, zp.p, zf, n);
+    poly_powers(ctx, zi.p, zf.inverse(), n);
+    poly_divide_linear(ctx, c.p, zp.p, zi.p, q.p, tmp.p, n);
+    download_fr(ctx, q.p, quotient, n);
+    PK_API_END(ctx)
+}
+
+int pk_poly_shifted_grand_product(pk_ctx* ctx, const uint64_t* values, uint64_t n, uint64_t* out) {
+    PK_API_BEGIN(ctx)
+    PK_REQUIRE(n == 0 || (values != nullptr && out != nullptr), PK_ERR_INVALID, "null argument");
+    if (n == 0) return PK_OK;
+    DevBuf<fr_t> v, r(n);
+    upload_fr(ctx, v, values, n);
+    poly_scan(ctx, true, false, v.p, v.p, n);
+    fr_fill(ctx, r.p, fr_t::one(), 1);
+    if (n > 1) PK_CUDA(cudaMemcpyAsync(r.p + 1, v.p, (n - 1) * sizeof(fr_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    download_fr(ctx, r.p, out, n);
+    PK_API_END(ctx)
+}
+
+int pk_poly_batch_inversion(pk_ctx* ctx, uint64_t* values, uint64_t n) {
+    PK_API_BEGIN(ctx)
+    PK_REQUIRE(n == 0 || values != nullptr, PK_ERR_INVALID, "null argument");
+    if (n == 0) return PK_OK;
+    DevBuf<fr_t> v, a(n), b(n);
+    upload_fr(ctx, v, values, n);
+    poly_batch_inversion(ctx, v.p, v.p, a.p, b.p, n);
+    download_fr(ctx, v.p, values, n);
+    PK_API_END(ctx)
+}
+
 int pk_lde4(pk_ctx* ctx, const uint64_t* coeffs, uint32_t log_n, uint64_t* out_4n, int bitreversed, int fmt) {
     PK_API_BEGIN(ctx)
     PK_REQUIRE(coeffs != nullptr && out_4n != nullptr, PK_ERR_INVALID, "null data");

@@ -230,6 +230,38 @@ void poly_divide_linear(pk_ctx* ctx, const fr_t* p, const fr_t* zpow, const fr_t
     ctx->prof.kernel_launches++;
 }
 
+// ---------------------------------------------------------------- batch inversion (bellman: Polynomial<Values>::batch_inversion)
+// No per-chunk Montgomery chains: with zeros mapped to one, out_i = (prod_{j<i} v_j) * (prod_{j>i} v_j) / prod_j v_j is
+// two multiplicative scans and ONE field inversion on the host; zeros stay zero, as in bellman.
+__global__ void zero_to_one_kernel(const fr_t* in, fr_t* out, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fr_t v = ld_fp(in + i);
+    st_fp(out + i, v.is_zero() ? fr_t::one() : v);
+}
+__global__ void batch_inv_finish_kernel(const fr_t* in, const fr_t* pn, const fr_t* sd, fr_t tinv, fr_t* out, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (ld_fp(in + i).is_zero()) { st_fp(out + i, fr_t::zero()); return; }
+    fr_t r = tinv;
+    if (i) r = r * ld_fp(pn + i - 1);
+    if (i + 1 < n) r = r * ld_fp(sd + i + 1);
+    st_fp(out + i, r);
+}
+void poly_batch_inversion(pk_ctx* ctx, const fr_t* in, fr_t* out, fr_t* tmp_a, fr_t* tmp_b, size_t n) {
+    if (!n) return;
+    zero_to_one_kernel<<<grid1d(n, 256), 256, 0, ctx->stream>>>(in, tmp_a, n);
+    ctx->prof.kernel_launches++;
+    poly_scan(ctx, true, true, tmp_a, tmp_b, n);   // sd[i] = prod_{j >= i}
+    poly_scan(ctx, true, false, tmp_a, tmp_a, n);  // pn[i] = prod_{j <= i}
+    fr_t total;
+    PK_CUDA(cudaMemcpyAsync(&total, tmp_a + n - 1, sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    batch_inv_finish_kernel<<<grid1d(n, 256), 256, 0, ctx->stream>>>(in, tmp_a, tmp_b, total.inverse(), out, n);
+    ctx->prof.kernel_launches++;
+    PK_CUDA(cudaGetLastError());
+}
+
 // ---------------------------------------------------------------- witness -> wire values
 __global__ void wire_gather_kernel(const fr_t* vars, const uint32_t* idx, fr_t* nat, fr_t* br, int log_n) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;  // over 4n

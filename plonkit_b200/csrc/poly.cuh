@@ -26,6 +26,9 @@ void poly_scan(pk_ctx* ctx, bool mul, bool reverse, const fr_t* in, fr_t* out, s
 // q(X) = (p(X) - p(z)) / (X - z) given zpow[j] = z^j and zinvpow[j] = z^-j ; tmp is an n-element scratch; q != p
 void poly_divide_linear(pk_ctx* ctx, const fr_t* p, const fr_t* zpow, const fr_t* zinvpow, fr_t* q, fr_t* tmp, size_t n);
 
+// out[i] = in[i]^-1, zeros stay zero (bellman batch_inversion); tmp_a, tmp_b: n-element scratch, out may alias in
+void poly_batch_inversion(pk_ctx* ctx, const fr_t* in, fr_t* out, fr_t* tmp_a, fr_t* tmp_b, size_t n);
+
 // ---- prover-specific kernels
 // vals_nat[c][row] = vars[idx[c][row]] ; vals_br[c][brev(row)] = same
 void wire_gather(pk_ctx* ctx, const fr_t* vars, const uint32_t* idx, fr_t* vals_nat, fr_t* vals_br, int log_n);

@@ -167,3 +167,31 @@ def test_ec_intt_matches_oracle(ctx, orc, simple_key):
     for log_n in (0, 1, 4, 7):
         got = ctx.ec_intt_g1(log_n)
         assert (got == orc.ec_intt(simple_key.g1_bases[: 1 << log_n], threads=8)).all(), log_n
+
+
+@pytest.mark.parametrize("n", [1, 2, 255, 4096, 100003, 1 << 20])
+def test_polynomial_primitives_match_oracle(ctx, orc, n):
+    """pk_poly_* (bellman's evaluate_at, divide_single, calculate_shifted_grand_product, batch_inversion) == oracle;
+    at 2^20 the serial checker still finishes in seconds."""
+    c = synth.random_field_elements(n, seed=900 + n % 1000)
+    c[n // 3] = 0                                     # a zero inside the grand product / inversion
+    z = synth.random_field_elements(1, seed=77)[0]
+    assert (ctx.poly_evaluate_at(c, z) == orc.poly_op("evaluate_at", c, z)).all()
+    assert (ctx.poly_divide_by_linear(c, z) == orc.poly_op("divide_by_linear", c, z)).all()
+    zero = np.zeros(4, dtype=np.uint64)
+    assert (ctx.poly_divide_by_linear(c, zero) == orc.poly_op("divide_by_linear", c, zero)).all()
+    assert (ctx.poly_shifted_grand_product(c) == orc.poly_op("shifted_grand_product", c)).all()
+    assert (ctx.poly_batch_inversion(c) == orc.poly_op("batch_inversion", c)).all()
+    nz = c.copy()
+    nz[n // 3] = ints_to_limbs([5])[0]
+    inv = ctx.poly_batch_inversion(nz)
+    if n <= 4096:                                     # x * x^-1 == 1 checked with Python integers
+        assert all(a * b % R_MOD == 1 for a, b in zip(limbs_to_ints(nz), limbs_to_ints(inv)))
+
+
+def test_polynomial_primitives_empty_input(ctx):
+    e = np.zeros((0, 4), dtype=np.uint64)
+    z = ints_to_limbs([3])[0]
+    assert not ctx.poly_evaluate_at(e, z).any()
+    assert ctx.poly_divide_by_linear(e, z).shape == (0, 4)
+    assert ctx.poly_shifted_grand_product(e).shape == (0, 4) and ctx.poly_batch_inversion(e).shape == (0, 4)

@@ -146,3 +146,32 @@ def test_committed_fixtures_are_what_the_oracle_produces(orc, simple_key):
     x = synth.random_field_elements(1 << 10, seed=synth.SEED + 1)
     assert (orc.ntt(x, threads=2) == np.load(os.path.join(GOLDEN, "ntt10_out.npy"))).all()
     assert (orc.msm(x, simple_key.g1_bases, threads=2) == np.load(os.path.join(GOLDEN, "msm10_out.npy"))).all()
+
+
+def test_polynomial_primitives_against_python_integers(orc):
+    """orc_poly_op restates bellman's evaluate_at / divide_single / calculate_shifted_grand_product / batch_inversion;
+    small cases are checked with plain Python integers, the division through p(X) = q(X) (X - z) + p(z)."""
+    rng = np.random.default_rng(21)
+    for n in (1, 2, 7, 64, 257):
+        c = [int.from_bytes(rng.bytes(32), "little") % R_MOD for _ in range(n)]
+        c[n // 2] = 0
+        z = int.from_bytes(rng.bytes(32), "little") % R_MOD
+        C, Z = ints_to_limbs(c), ints_to_limbs([z])[0]
+        pz = sum(ci * pow(z, i, R_MOD) for i, ci in enumerate(c)) % R_MOD
+        assert limbs_to_ints(orc.poly_op("evaluate_at", C, Z).reshape(1, 4)) == [pz]
+        q = limbs_to_ints(orc.poly_op("divide_by_linear", C, Z))
+        assert q[n - 1] == 0
+        back = [0] * n
+        for i, qi in enumerate(q[: n - 1]):
+            back[i + 1] = (back[i + 1] + qi) % R_MOD
+            back[i] = (back[i] - qi * z) % R_MOD
+        back[0] = (back[0] + pz) % R_MOD
+        assert back == c
+        gp = limbs_to_ints(orc.poly_op("shifted_grand_product", C))
+        acc, want = 1, []
+        for ci in c:
+            want.append(acc)
+            acc = acc * ci % R_MOD
+        assert gp == want
+        inv = limbs_to_ints(orc.poly_op("batch_inversion", C))
+        assert inv == [pow(ci, -1, R_MOD) if ci else 0 for ci in c]
