@@ -393,9 +393,21 @@ template <bool LEVEL1> __global__ void __launch_bounds__(128) msm_accum_kernel(A
     bool in_head = true;
     g1_xyzz_t acc = g1_xyzz_t::infinity();
     const g1_xyzz_t inf = g1_xyzz_t::infinity();
+    // level 1 runs one entry ahead: the window-table gather of entry i + 1 (a random 64-byte read) is in flight while
+    // the ten products of entry i execute
+    uint2 en_next = make_uint2(0, 0);
+    g1_affine_t pt_next;
+    if (LEVEL1) {
+        en_next = p.ent[s];
+        pt_next = ldg_affine(p.table + (en_next.y & 0x7fffffffu));
+    }
     for (uint32_t i = s; i < e; ++i) {
-        uint2 en = make_uint2(0, 0);
-        if (LEVEL1) en = p.ent[i];
+        const uint2 en = en_next;
+        g1_affine_t pt = pt_next;
+        if (LEVEL1 && i + 1 < e) {
+            en_next = p.ent[i + 1];
+            pt_next = ldg_affine(p.table + (en_next.y & 0x7fffffffu));
+        }
         const uint32_t k = LEVEL1 ? en.x : p.keys[i];
         if (k != cur) {
             if (in_head && head_partial) st_xyzz(p.out_pts + 2 * (size_t)t, acc);
@@ -405,9 +417,7 @@ template <bool LEVEL1> __global__ void __launch_bounds__(128) msm_accum_kernel(A
             cur = k;
         }
         if (LEVEL1) {
-            const uint32_t it = en.y;
-            g1_affine_t pt = ldg_affine(p.table + (it & 0x7fffffffu));
-            if (it >> 31) pt.y = pt.y.neg();
+            if (en.y >> 31) pt.y = pt.y.neg();
             acc = acc.add_mixed(pt);
         } else {
             acc = acc.add(ld_xyzz(p.pts + i));
