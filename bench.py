@@ -131,13 +131,14 @@ def effective_cores():
     return cores
 
 
-def run_cpu_prove(log_n_s, threads, repeats, warm):
-    """Times the oracle's CPU prover (restated bellman algorithms) on a poseidon-shaped circuit of 2^log_n_s gates."""
+def run_cpu_prove(log_n_s, threads, repeats, warm, srs=None):
+    """Times the oracle's CPU prover (restated bellman algorithms) on a poseidon-shaped circuit of 2^log_n_s gates.
+    `srs`: an existing [42^i]G key to cut from (the timed quantity is the prove call, not key generation)."""
     from oracle import oracle as orc
     from plonkit_b200 import synth
     orc.build()
     asm = synth.poseidon_chain_assembly(log_n_s)
-    srs = orc.srs_gen(asm.n, 42, threads=threads)
+    srs = orc.srs_gen(asm.n, 42, threads=threads) if srs is None else np.ascontiguousarray(srs[: asm.n])
     times = []
     for i in range(warm + repeats):
         t0 = time.perf_counter()
@@ -149,13 +150,13 @@ def run_cpu_prove(log_n_s, threads, repeats, warm):
     return times
 
 
-def cpu_sample_log_n(cores, log_n, proves, budget_s):
+def cpu_sample_log_n(cores, log_n, proves, budget_s, srs_extra=1):
     """Largest sample circuit 2^L (L <= log_n) for which `proves` CPU proofs are predicted to fit in `budget_s` seconds:
     one 2^13 proof is timed and extrapolated linearly in the gate count (SRS generation on the CPU, which also grows
-    linearly, is budgeted at one extra proof)."""
+    linearly, is budgeted at `srs_extra` proofs)."""
     t13 = run_cpu_prove(13, cores, 1, 0)[0][1]
     L = 13
-    while L < log_n and t13 * (1 << (L + 1 - 13)) * (proves + 1) <= budget_s:
+    while L < log_n and t13 * (1 << (L + 1 - 13)) * (proves + srs_extra) <= budget_s:
         L += 1
     return L
 
@@ -345,8 +346,8 @@ def bench_ours(args):
     }
     if world == 1 and not args.no_cpu:
         cores = effective_cores()
-        ls = cpu_sample_log_n(cores, args.log_n, 1, 40.0)  # bounded sample: ~10-30 s of CPU work
-        t = run_cpu_prove(ls, cores, 1, 0)
+        ls = cpu_sample_log_n(cores, args.log_n, 1, 40.0, srs_extra=0)  # bounded sample: ~10-30 s of CPU work
+        t = run_cpu_prove(ls, cores, 1, 0, srs=srs)
         scale = float(1 << (args.log_n - ls))
         sample = "one full prove of the oracle port at 2^%d gates, %d threads (setup polynomials excluded)" % (ls, cores)
         if ls != args.log_n:
