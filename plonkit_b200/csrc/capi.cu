@@ -384,12 +384,17 @@ int pk_timer_begin(pk_ctx* ctx) {
 int pk_timer_end(pk_ctx* ctx, double* ms) {
     PK_API_BEGIN(ctx)
     PK_REQUIRE(ms != nullptr, PK_ERR_INVALID, "null output");
-    auto it = g_timers.find(ctx);
-    PK_REQUIRE(it != g_timers.end() && it->second.first, PK_ERR_INVALID, "pk_timer_begin was not called");
-    PK_CUDA(cudaEventRecord(it->second.second, ctx->stream));
-    PK_CUDA(cudaEventSynchronize(it->second.second));
+    std::pair<cudaEvent_t, cudaEvent_t> t(nullptr, nullptr);
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_timers.find(ctx);
+        if (it != g_timers.end()) t = it->second;
+    }
+    PK_REQUIRE(t.first, PK_ERR_INVALID, "pk_timer_begin was not called");
+    PK_CUDA(cudaEventRecord(t.second, ctx->stream));
+    PK_CUDA(cudaEventSynchronize(t.second));
     float f = 0;
-    PK_CUDA(cudaEventElapsedTime(&f, it->second.first, it->second.second));
+    PK_CUDA(cudaEventElapsedTime(&f, t.first, t.second));
     *ms = f;
     PK_API_END(ctx)
 }

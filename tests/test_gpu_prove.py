@@ -49,7 +49,7 @@ def test_poseidon_shaped_golden_fixture(ctx, simple_key):
 
 
 @pytest.mark.parametrize("kind,log_n", [("poseidon", 4), ("poseidon", 10), ("poseidon", 12), ("random", 6), ("random", 11),
-                                        ("poseidon", 14)])
+                                        ("poseidon", 14), ("poseidon", 16)])
 def test_proofs_equal_oracle_on_synthetic_circuits(ctx, orc, kind, log_n):
     asm = synth.poseidon_chain_assembly(log_n) if kind == "poseidon" else synth.random_gate_assembly(log_n, seed=log_n)
     srs = orc.srs_gen(asm.n, 42, threads=8)
