@@ -375,8 +375,13 @@ void pk_profile_get(const pk_ctx* cctx, pk_profile* out) {
 static std::map<pk_ctx*, std::pair<cudaEvent_t, cudaEvent_t>> g_timers;
 int pk_timer_begin(pk_ctx* ctx) {
     PK_API_BEGIN(ctx)
-    auto& t = g_timers[ctx];
-    if (!t.first) { PK_CUDA(cudaEventCreate(&t.first)); PK_CUDA(cudaEventCreate(&t.second)); }
+    std::pair<cudaEvent_t, cudaEvent_t> t;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);  // contexts are driven from different host threads
+        auto& slot = g_timers[ctx];
+        if (!slot.first) { PK_CUDA(cudaEventCreate(&slot.first)); PK_CUDA(cudaEventCreate(&slot.second)); }
+        t = slot;
+    }
     PK_CUDA(cudaStreamSynchronize(ctx->stream));
     PK_CUDA(cudaEventRecord(t.first, ctx->stream));
     PK_API_END(ctx)
