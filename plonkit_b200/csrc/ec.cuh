@@ -89,6 +89,35 @@ struct alignas(16) g1_xyzz_t {
         r.ZZZ = ZZZ * PPP;
         return r;
     }
+    // add_mixed with the coordinates of *this and of the result in lazy form ([0, 2p), fp.cuh): no conditional
+    // subtraction after any of the ten products.  b is canonical.  Used by the bucket-accumulation loop, which
+    // normalises (lnorm) only when a run's sum leaves the registers.
+    PK_HD g1_xyzz_t add_mixed_lazy(const g1_affine_t& b) const {
+        if (b.is_inf()) return *this;
+        if (ZZ.lis_zero()) return from_affine(b);
+        fq_t U2 = b.x.lmul(ZZ);
+        fq_t S2 = b.y.lmul(ZZZ);
+        fq_t Pd = U2.lsub(X);
+        fq_t Rd = S2.lsub(Y);
+        if (Pd.lis_zero()) {
+            if (Rd.lis_zero()) return dbl_affine(b);
+            return infinity();
+        }
+        fq_t PP = Pd.lmul(Pd);
+        fq_t PPP = Pd.lmul(PP);
+        fq_t Q = X.lmul(PP);
+        g1_xyzz_t r;
+        r.X = Rd.lmul(Rd).lsub(PPP).lsub(Q.ladd(Q));
+        r.Y = Rd.lmul(Q.lsub(r.X)).lsub(Y.lmul(PPP));
+        r.ZZ = ZZ.lmul(PP);
+        r.ZZZ = ZZZ.lmul(PPP);
+        return r;
+    }
+    PK_HD g1_xyzz_t lnorm() const {
+        g1_xyzz_t r;
+        r.X = X.lnormalize(); r.Y = Y.lnormalize(); r.ZZ = ZZ.lnormalize(); r.ZZZ = ZZZ.lnormalize();
+        return r;
+    }
     // add-2008-s: general addition with all special cases
     PK_HD g1_xyzz_t add(const g1_xyzz_t& b) const {
         if (b.is_inf()) return *this;

@@ -110,7 +110,10 @@ template <class P> PK_HD void cond_sub_p(uint32_t* r) {
     for (int i = 0; i < 8; ++i) r[i] = borrow ? r[i] : t[i];
 }
 
-template <class P> PK_HD void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+// REDUCE = false leaves the result in [0, 2p) ("lazy" form): for a, b < 2p the CIOS result is below
+// (4p^2 + 2^256 p) / 2^256 < 1.76 p because 4p < 2^256, so chains of products and lazy add/sub never need the final
+// conditional subtraction; only values that leave the kernel are normalised.
+template <class P, bool REDUCE = true> PK_HD void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
     uint32_t ev[8], od[8];
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
@@ -132,7 +135,35 @@ template <class P> PK_HD void mont_mul(uint32_t* r, const uint32_t* a, const uin
 #pragma unroll
     for (int k = 1; k < 7; ++k) r[k] = addc_cc(ev[k], od[k + 1]);
     r[7] = addc(ev[7], 0);
-    cond_sub_p<P>(r);
+    if (REDUCE) cond_sub_p<P>(r);
+}
+
+// ---- lazy form: values in [0, 2p)
+template <class P> PK_HD void cond_sub_2p(uint32_t* r) {
+    uint32_t t[8];
+    t[0] = sub_cc(r[0], P::p2(0));
+#pragma unroll
+    for (int i = 1; i < 8; ++i) t[i] = subc_cc(r[i], P::p2(i));
+    uint32_t borrow = subc(0, 0);  // 0xffffffff if r < 2p
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = borrow ? r[i] : t[i];
+}
+template <class P> PK_HD void add_lazy(uint32_t* r, const uint32_t* a, const uint32_t* b) {  // a + b < 4p < 2^256
+    r[0] = add_cc(a[0], b[0]);
+#pragma unroll
+    for (int i = 1; i < 7; ++i) r[i] = addc_cc(a[i], b[i]);
+    r[7] = addc(a[7], b[7]);
+    cond_sub_2p<P>(r);
+}
+template <class P> PK_HD void sub_lazy(uint32_t* r, const uint32_t* a, const uint32_t* b) {  // a - b (+ 2p on borrow)
+    r[0] = sub_cc(a[0], b[0]);
+#pragma unroll
+    for (int i = 1; i < 8; ++i) r[i] = subc_cc(a[i], b[i]);
+    uint32_t borrow = subc(0, 0);
+    r[0] = add_cc(r[0], P::p2(0) & borrow);
+#pragma unroll
+    for (int i = 1; i < 7; ++i) r[i] = addc_cc(r[i], P::p2(i) & borrow);
+    r[7] = addc(r[7], P::p2(7) & borrow);
 }
 
 template <class P> PK_HD void add_mod(uint32_t* r, const uint32_t* a, const uint32_t* b) {
@@ -189,6 +220,17 @@ template <class P> struct alignas(16) Fp {
     PK_HD Fp operator+(const Fp& b) const { Fp r; limbs::add_mod<P>(r.v, v, b.v); return r; }
     PK_HD Fp operator-(const Fp& b) const { Fp r; limbs::sub_mod<P>(r.v, v, b.v); return r; }
     PK_HD Fp sqr() const { Fp r; limbs::mont_mul<P>(r.v, v, v); return r; }
+    // lazy form ([0, 2p), see limbs::mont_mul<P, false>): used inside the bucket-accumulation loop only
+    PK_HD Fp lmul(const Fp& b) const { Fp r; limbs::mont_mul<P, false>(r.v, v, b.v); return r; }
+    PK_HD Fp ladd(const Fp& b) const { Fp r; limbs::add_lazy<P>(r.v, v, b.v); return r; }
+    PK_HD Fp lsub(const Fp& b) const { Fp r; limbs::sub_lazy<P>(r.v, v, b.v); return r; }
+    PK_HD bool lis_zero() const {  // 0 or p
+        uint32_t o = 0, q = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { o |= v[i]; q |= v[i] ^ P::p(i); }
+        return o == 0 || q == 0;
+    }
+    PK_HD Fp lnormalize() const { Fp r = *this; limbs::cond_sub_p<P>(r.v); return r; }
     PK_HD Fp dbl() const { Fp r; limbs::add_mod<P>(r.v, v, v); return r; }
     PK_HD Fp neg() const { Fp z = zero(); Fp r; limbs::sub_mod<P>(r.v, z.v, v); return r; }
 

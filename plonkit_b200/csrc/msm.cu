@@ -410,15 +410,15 @@ template <bool LEVEL1> __global__ void __launch_bounds__(128) msm_accum_kernel(A
         }
         const uint32_t k = LEVEL1 ? en.x : p.keys[i];
         if (k != cur) {
-            if (in_head && head_partial) st_xyzz(p.out_pts + 2 * (size_t)t, acc);
-            else if (!acc.is_inf()) st_xyzz(p.buckets + cur, acc);
+            if (in_head && head_partial) st_xyzz(p.out_pts + 2 * (size_t)t, LEVEL1 ? acc.lnorm() : acc);
+            else if (!acc.is_inf()) st_xyzz(p.buckets + cur, LEVEL1 ? acc.lnorm() : acc);
             in_head = false;
             acc = inf;
             cur = k;
         }
         if (LEVEL1) {
             if (en.y >> 31) pt.y = pt.y.neg();
-            acc = acc.add_mixed(pt);
+            acc = acc.add_mixed_lazy(pt);  // coordinates stay in [0, 2p) inside a run
         } else {
             acc = acc.add(ld_xyzz(p.pts + i));
         }
@@ -426,9 +426,9 @@ template <bool LEVEL1> __global__ void __launch_bounds__(128) msm_accum_kernel(A
     // the last run: the tail run, or the only run of the chunk
     if (in_head) {
         const bool partial = head_partial || tail_partial;
-        if (partial) st_xyzz(p.out_pts + 2 * (size_t)t, acc);
+        if (partial) st_xyzz(p.out_pts + 2 * (size_t)t, LEVEL1 ? acc.lnorm() : acc);
         else {
-            if (!acc.is_inf()) st_xyzz(p.buckets + cur, acc);
+            if (!acc.is_inf()) st_xyzz(p.buckets + cur, LEVEL1 ? acc.lnorm() : acc);
             st_xyzz(p.out_pts + 2 * (size_t)t, inf);
         }
         st_xyzz(p.out_pts + 2 * (size_t)t + 1, inf);
@@ -436,9 +436,9 @@ template <bool LEVEL1> __global__ void __launch_bounds__(128) msm_accum_kernel(A
         p.out_keys[2 * (size_t)t + 1] = cur;
     } else {
         if (!head_partial) st_xyzz(p.out_pts + 2 * (size_t)t, inf);
-        if (tail_partial) st_xyzz(p.out_pts + 2 * (size_t)t + 1, acc);
+        if (tail_partial) st_xyzz(p.out_pts + 2 * (size_t)t + 1, LEVEL1 ? acc.lnorm() : acc);
         else {
-            if (!acc.is_inf()) st_xyzz(p.buckets + cur, acc);
+            if (!acc.is_inf()) st_xyzz(p.buckets + cur, LEVEL1 ? acc.lnorm() : acc);
             st_xyzz(p.out_pts + 2 * (size_t)t + 1, inf);
         }
         p.out_keys[2 * (size_t)t] = first_key;

@@ -43,7 +43,8 @@ void hc_fr_ops(const uint64_t* a, const uint64_t* b, uint64_t* add, uint64_t* su
         store_c(x + y, add + 4 * i); store_c(x - y, sub + 4 * i); store_c(x * y, mul + 4 * i); store_c(x.inverse(), inv + 4 * i);
     }
 }
-// out[0] = p + q (mixed), out[1] = p + q (full), out[2] = 2p, out[3] = k * p (mul_small)
+// out[0] = p + q (mixed), out[1] = p + q (full), out[2] = 2p, out[3] = k * p (mul_small),
+// out[4] = (((3p - 2p) + q) + q') + q'' through add_mixed_lazy chained WITHOUT normalising in between (q' = -2q.., see below)
 void hc_g1_ops(const uint64_t* p, const uint64_t* q, uint32_t k, uint64_t* out) {
     g1_affine_t P = load_pt(p), Q = load_pt(q);
     g1_xyzz_t X = g1_xyzz_t::from_affine(P), Y = g1_xyzz_t::from_affine(Q);
@@ -54,6 +55,19 @@ void hc_g1_ops(const uint64_t* p, const uint64_t* q, uint32_t k, uint64_t* out) 
     store_pt(Xn.add(Y.dbl().add(Y.neg())).to_affine(), out + 8);
     store_pt(Xn.dbl().to_affine(), out + 16);
     store_pt(Xn.mul_small(k).to_affine(), out + 24);
+    // lazy chain: Xn + Q + Q + P  (second step hits the doubling-free general path with a non-trivial ZZ; coordinates stay
+    // in [0, 2p) across the three additions and are normalised once)
+    g1_xyzz_t L = Xn.add_mixed_lazy(Q).add_mixed_lazy(Q).add_mixed_lazy(P).lnorm();
+    store_pt(L.to_affine(), out + 32);
+    // field level: lazy product chain vs canonical
+}
+void hc_lazy_field(const uint32_t* a, const uint32_t* b, uint32_t* o, int n) {
+    // o = normalise( lsub( lmul(lmul(a,b), ladd(a,b)), lmul(b,b) ) )  vs the same with canonical ops computed by the caller
+    for (int i = 0; i < n; ++i) {
+        fq_t x, y; memcpy(x.v, a + 8 * i, 32); memcpy(y.v, b + 8 * i, 32);
+        fq_t r = x.lmul(y).lmul(x.ladd(y)).lsub(y.lmul(y)).lsub(x.ladd(x).ladd(y)).lnormalize();
+        memcpy(o + 8 * i, r.v, 32);
+    }
 }
 void hc_keccak(const uint8_t* d, uint64_t n, uint8_t* out) { Keccak256 h; h.update(d, n); h.finish(out); }
 // transcript: commit `n` 32-byte big-endian values, then draw `m` challenges (canonical LE limbs out)

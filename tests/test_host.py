@@ -253,12 +253,29 @@ def test_xyzz_formulas_against_oracle_group_law(hc, orc, simple_key):
     neg5[4:] = ints_to_limbs([Q_MOD - limbs_to_ints(g[5][4:])[0]])[0]
     cases = [(g[3], g[7]), (g[5], g[5]), (g[5], neg5), (g[5], inf), (inf, g[9]), (inf, inf)]
     for p, q in cases:
-        out = np.zeros((4, 8), dtype=np.uint64)
+        out = np.zeros((5, 8), dtype=np.uint64)
         hc.hc_g1_ops(_p(np.ascontiguousarray(p)), _p(np.ascontiguousarray(q)), 11, _p(out))
         assert (out[0] == orc.g1_add(p, q)).all()
+        assert (out[4] == orc.g1_add(orc.g1_add(orc.g1_add(p, q), q), p)).all()   # lazy-form chain, normalised once
         assert (out[1] == orc.g1_add(p, q)).all()
         assert (out[2] == orc.g1_add(p, p)).all()
         assert (out[3] == orc.g1_mul(p, 11)).all()
+
+
+def test_lazy_form_field_chain(hc):
+    """fp.cuh lazy form ([0, 2p)): products without the final conditional subtraction, add/sub modulo 2p; a chain of
+    them normalised once must equal the canonical computation (Montgomery factors included)."""
+    rng = np.random.default_rng(12)
+    p = Q_MOD
+    edge = [0, 1, p - 1, p - 2, (1 << 253), (1 << 254) % p]
+    a = edge * len(edge) + [int.from_bytes(rng.bytes(32), "little") % p for _ in range(3000)]
+    b = [e for e in edge for _ in edge] + [int.from_bytes(rng.bytes(32), "little") % p for _ in range(3000)]
+    A, B = ints_to_limbs(a).view(np.uint32), ints_to_limbs(b).view(np.uint32)
+    out = np.zeros_like(A)
+    hc.hc_lazy_field(_p(A), _p(B), _p(out), len(a))
+    ri = pow(1 << 256, -1, p)
+    want = [((x * y * ri) * (x + y) * ri - y * y * ri - (2 * x + y)) % p for x, y in zip(a, b)]
+    assert limbs_to_ints(out.view(np.uint64)) == want
 
 
 def test_host_keccak_and_transcript_match_oracle(hc, orc):
