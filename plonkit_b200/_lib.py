@@ -29,7 +29,7 @@ EXPORTS = [
     "pk_prove", "pk_profile_enable", "pk_profile_reset", "pk_profile_get", "pk_bench_ntt", "pk_bench_msm",
     "pk_bench_fieldmul", "pk_timer_begin", "pk_timer_end", "pk_g1_sum", "pk_dev_fr_convert", "pk_dev_ntt_rows",
     "pk_dev_twiddle", "pk_poly_evaluate_at", "pk_poly_divide_by_linear", "pk_poly_shifted_grand_product",
-    "pk_poly_batch_inversion",
+    "pk_poly_batch_inversion", "pk_dev_ec_from_affine", "pk_dev_ec_ntt_rows", "pk_dev_ec_twiddle", "pk_dev_ec_to_affine",
 ]
 
 
@@ -122,6 +122,10 @@ def load():
     lib.pk_dev_fr_convert.argtypes = [vp, vp, u64, i32]
     lib.pk_dev_ntt_rows.argtypes = [vp, vp, u32, u64, i32]
     lib.pk_dev_twiddle.argtypes = [vp, vp, u64, u64, u32, u64, i32]
+    lib.pk_dev_ec_from_affine.argtypes = [vp, vp, vp, u64]
+    lib.pk_dev_ec_ntt_rows.argtypes = [vp, vp, u32, u64, i32]
+    lib.pk_dev_ec_twiddle.argtypes = [vp, vp, u64, u64, u32, u64, i32]
+    lib.pk_dev_ec_to_affine.argtypes = [vp, vp, vp, u64, u32]
     lib.pk_poly_evaluate_at.argtypes = [vp, vp, u64, vp, vp]
     lib.pk_poly_divide_by_linear.argtypes = [vp, vp, u64, vp, vp]
     lib.pk_poly_shifted_grand_product.argtypes = [vp, vp, u64, vp]
@@ -246,6 +250,18 @@ class Context:
 
     def dev_twiddle(self, ptr, rows, cols, log_total, row0, inverse=False):
         self._check(self._lib.pk_dev_twiddle(self._h, ctypes.c_void_p(ptr), rows, cols, log_total, row0, int(inverse)))
+
+    def dev_ec_from_affine(self, ptr_affine, ptr_xyzz, n):
+        self._check(self._lib.pk_dev_ec_from_affine(self._h, ctypes.c_void_p(ptr_affine), ctypes.c_void_p(ptr_xyzz), n))
+
+    def dev_ec_ntt_rows(self, ptr, log_len, rows, inverse=False):
+        self._check(self._lib.pk_dev_ec_ntt_rows(self._h, ctypes.c_void_p(ptr), log_len, rows, int(inverse)))
+
+    def dev_ec_twiddle(self, ptr, rows, cols, log_total, row0, inverse=False):
+        self._check(self._lib.pk_dev_ec_twiddle(self._h, ctypes.c_void_p(ptr), rows, cols, log_total, row0, int(inverse)))
+
+    def dev_ec_to_affine(self, ptr_xyzz, ptr_affine, n, log_scale):
+        self._check(self._lib.pk_dev_ec_to_affine(self._h, ctypes.c_void_p(ptr_xyzz), ctypes.c_void_p(ptr_affine), n, log_scale))
 
     # ---- profiling / micro-benchmarks
     def profile_enable(self, on=True):

@@ -15,6 +15,10 @@ void witness_upload(pk_ctx* ctx, pk_setup* s, const uint64_t* var_values, uint64
 void prove(pk_ctx* ctx, pk_setup* s, const uint64_t* var_values, uint64_t nvars, pk_proof* proof, uint64_t* inputs_out);
 void setup_free(pk_setup* s);
 void ec_intt(pk_ctx* ctx, uint32_t log_n, uint64_t* out_xy);
+void ec_dev_from_affine(pk_ctx* ctx, const g1_affine_t* in_canonical, g1_xyzz_t* out, size_t n);
+void ec_dev_ntt_rows(pk_ctx* ctx, g1_xyzz_t* data, int log_len, size_t rows, bool inverse);
+void ec_dev_twiddle_rows(pk_ctx* ctx, g1_xyzz_t* a, size_t rows, size_t cols, int log_total, size_t row0, bool inverse);
+void ec_dev_to_affine(pk_ctx* ctx, const g1_xyzz_t* in, g1_affine_t* out_canonical, size_t n, int log_scale);
 void srs_gen(pk_ctx* ctx, uint64_t n, uint64_t tau, uint64_t* out_xy);
 
 struct CtxExtras { PolyScratch poly; };
@@ -308,6 +312,36 @@ int pk_dev_twiddle(pk_ctx* ctx, void* dev, uint64_t rows, uint64_t cols, uint32_
     twiddle_rows(ctx, static_cast<fr_t*>(dev), rows, cols, (int)log_total, row0, inverse != 0);
     PK_CUDA(cudaStreamSynchronize(ctx->stream));
     PK_CUDA(cudaGetLastError());
+    PK_API_END(ctx)
+}
+
+int pk_dev_ec_from_affine(pk_ctx* ctx, const void* dev_affine, void* dev_xyzz, uint64_t n) {
+    PK_API_BEGIN(ctx)
+    PK_REQUIRE((dev_affine != nullptr && dev_xyzz != nullptr) || n == 0, PK_ERR_INVALID, "null device pointer");
+    if (n) ec_dev_from_affine(ctx, static_cast<const g1_affine_t*>(dev_affine), static_cast<g1_xyzz_t*>(dev_xyzz), n);
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    PK_API_END(ctx)
+}
+int pk_dev_ec_ntt_rows(pk_ctx* ctx, void* dev_xyzz, uint32_t log_len, uint64_t rows, int inverse) {
+    PK_API_BEGIN(ctx)
+    PK_REQUIRE(dev_xyzz != nullptr && rows >= 1, PK_ERR_INVALID, "bad argument");
+    PK_REQUIRE(log_len <= 26, PK_ERR_DEGREE_TOO_LARGE, "domain larger than 2^26");
+    ec_dev_ntt_rows(ctx, static_cast<g1_xyzz_t*>(dev_xyzz), (int)log_len, rows, inverse != 0);
+    PK_API_END(ctx)
+}
+int pk_dev_ec_twiddle(pk_ctx* ctx, void* dev_xyzz, uint64_t rows, uint64_t cols, uint32_t log_total, uint64_t row0, int inverse) {
+    PK_API_BEGIN(ctx)
+    PK_REQUIRE(dev_xyzz != nullptr && rows >= 1 && cols >= 1, PK_ERR_INVALID, "bad argument");
+    PK_REQUIRE(log_total <= 28, PK_ERR_DEGREE_TOO_LARGE, "domain larger than 2^28");
+    ec_dev_twiddle_rows(ctx, static_cast<g1_xyzz_t*>(dev_xyzz), rows, cols, (int)log_total, row0, inverse != 0);
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    PK_API_END(ctx)
+}
+int pk_dev_ec_to_affine(pk_ctx* ctx, const void* dev_xyzz, void* dev_affine, uint64_t n, uint32_t log_scale) {
+    PK_API_BEGIN(ctx)
+    PK_REQUIRE((dev_affine != nullptr && dev_xyzz != nullptr) || n == 0, PK_ERR_INVALID, "null device pointer");
+    if (n) ec_dev_to_affine(ctx, static_cast<const g1_xyzz_t*>(dev_xyzz), static_cast<g1_affine_t*>(dev_affine), n, (int)log_scale);
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
     PK_API_END(ctx)
 }
 

@@ -83,6 +83,90 @@ __global__ void __launch_bounds__(128) ec_finish_kernel(const g1_xyzz_t* a, g1_a
     st_affine(out + i, p);
 }
 
+// ---------------------------------------------------------------- device-resident pieces of a four-step EC (i)NTT across GPUs
+// (SURVEY.md §8e row "EC-iNTT": Crs::from_powers of a 2^25 key split over 8 GPUs, BASELINE configs[3]).  The caller
+// (plonkit_b200/dist.py) owns the buffers and moves them between ranks; these run the local steps.
+__global__ void ec_from_affine_kernel(const g1_affine_t* in, g1_xyzz_t* out, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g1_affine_t p = ldg_affine(in + i);
+    if (!p.is_inf()) { p.x = p.x.to_mont(); p.y = p.y.to_mont(); }
+    st_xyzz(out + i, g1_xyzz_t::from_affine(p));
+}
+__global__ void ec_rows_bitrev_kernel(const g1_xyzz_t* src, g1_xyzz_t* dst, int log_len) {  // blockIdx.y = row
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >> log_len) return;
+    size_t r = log_len ? (size_t)(__brev((unsigned)i) >> (32 - log_len)) : 0;
+    const size_t row = (size_t)blockIdx.y << log_len;
+    st_xyzz(dst + row + r, ld_xyzz(src + row + i));
+}
+// one radix-2 decimation-in-time stage of `rows` independent transforms of length 2^log_len (blockIdx.y = row);
+// forward twiddle w^e, inverse twiddle w^{-e} = -w^{len/2 - e}
+__global__ void __launch_bounds__(128) ec_rows_stage_kernel(g1_xyzz_t* a, const fr_t* tw, int tw_shift, int log_len, int s, int inverse) {
+    size_t u = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t half = size_t(1) << (log_len - 1);
+    if (u >= half) return;
+    a += (size_t)blockIdx.y << log_len;
+    const size_t m = size_t(1) << s;
+    const size_t lo = u & (m - 1);
+    const size_t i0 = ((u >> s) << (s + 1)) | lo, i1 = i0 + m;
+    const size_t e = lo << (log_len - 1 - s);
+    g1_xyzz_t x = ld_xyzz(a + i0), y = ld_xyzz(a + i1);
+    g1_xyzz_t t;
+    if (e == 0) t = y;
+    else if (inverse) t = scalar_mul(y, ldg_fp(tw + ((half - e) << tw_shift)).from_mont()).neg();
+    else t = scalar_mul(y, ldg_fp(tw + (e << tw_shift)).from_mont());
+    st_xyzz(a + i0, x.add(t));
+    st_xyzz(a + i1, x.add(t.neg()));
+}
+// a[r][c] <- w^{+-(row0 + r) * c} * a[r][c]   (w: primitive 2^log_total-th root of unity)
+__global__ void __launch_bounds__(128) ec_twiddle_rows_kernel(g1_xyzz_t* a, size_t rows, size_t cols, fr_t w, size_t row0, int log_total) {
+    size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t r = blockIdx.y;
+    if (c >= cols || r >= rows) return;
+    const uint64_t mask = (uint64_t(1) << log_total) - 1;
+    const uint64_t e = ((uint64_t)(row0 + r) * (uint64_t)c) & mask;
+    if (e == 0) return;
+    st_xyzz(a + r * cols + c, scalar_mul(ld_xyzz(a + r * cols + c), w.pow_u64(e).from_mont()));
+}
+
+void ec_dev_from_affine(pk_ctx* ctx, const g1_affine_t* in_canonical, g1_xyzz_t* out, size_t n) {
+    ec_from_affine_kernel<<<grid1d(n, 256), 256, 0, ctx->stream>>>(in_canonical, out, n);
+    ctx->prof.kernel_launches++;
+    PK_CUDA(cudaGetLastError());
+}
+void ec_dev_ntt_rows(pk_ctx* ctx, g1_xyzz_t* data, int log_len, size_t rows, bool inverse) {
+    PK_REQUIRE(rows >= 1 && rows <= 65535, PK_ERR_INVALID, "row batch too large");
+    if (log_len == 0) return;
+    const size_t len = size_t(1) << log_len;
+    ensure_twiddles(ctx, log_len);
+    DomainCache* dc = ctx->domains;
+    DevBuf<g1_xyzz_t> tmp(rows * len);
+    ec_rows_bitrev_kernel<<<dim3((unsigned)((len + 255) / 256), (unsigned)rows), 256, 0, ctx->stream>>>(data, tmp.p, log_len);
+    for (int s = 0; s < log_len; ++s)
+        ec_rows_stage_kernel<<<dim3((unsigned)((len / 2 + 127) / 128), (unsigned)rows), 128, 0, ctx->stream>>>(
+            tmp.p, dc->tw.p, dc->tw_log - log_len, log_len, s, inverse ? 1 : 0);
+    ctx->prof.kernel_launches += 1 + log_len;
+    PK_CUDA(cudaMemcpyAsync(data, tmp.p, rows * len * sizeof(g1_xyzz_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    PK_CUDA(cudaGetLastError());
+}
+void ec_dev_twiddle_rows(pk_ctx* ctx, g1_xyzz_t* a, size_t rows, size_t cols, int log_total, size_t row0, bool inverse) {
+    PK_REQUIRE(rows >= 1 && rows <= 65535, PK_ERR_INVALID, "row batch too large");
+    fr_t w = host_root_of_unity(log_total);
+    if (inverse) w = w.inverse();
+    ec_twiddle_rows_kernel<<<dim3((unsigned)((cols + 127) / 128), (unsigned)rows), 128, 0, ctx->stream>>>(a, rows, cols, w, row0, log_total);
+    ctx->prof.kernel_launches++;
+    PK_CUDA(cudaGetLastError());
+}
+// out[i] = affine(2^-log_scale * in[i]), canonical limbs
+void ec_dev_to_affine(pk_ctx* ctx, const g1_xyzz_t* in, g1_affine_t* out_canonical, size_t n, int log_scale) {
+    fr_t scale = fr_t::from_u32(2).inverse().pow_u64(log_scale).from_mont();
+    ec_finish_kernel<<<grid1d(n, 128), 128, 0, ctx->stream>>>(in, out_canonical, scale, n);
+    ctx->prof.kernel_launches++;
+    PK_CUDA(cudaGetLastError());
+}
+
 void ec_intt(pk_ctx* ctx, uint32_t log_n, uint64_t* out_xy) {
     PK_REQUIRE(log_n <= 26, PK_ERR_DEGREE_TOO_LARGE, "domain larger than 2^26");
     SrsTables* srs = ctx->srs;

@@ -141,3 +141,95 @@ class DistributedNtt:
             td.all_gather(parts, rows, group=self.group)
         full = torch.cat(parts, dim=0)                          # (N1, N2): [k1][k2]
         return full.transpose(0, 1).contiguous().cpu().numpy().view(np.uint64).reshape(-1, 4)  # index k1 + N1*k2
+
+
+class CudaEcNttOps:
+    """Local steps of the distributed EC inverse NTT on caller-owned CUDA tensors (pk_dev_ec_*).  Points travel as
+    128-byte XYZZ accumulators ((..., 16) int64 views) between `enter` (affine -> XYZZ) and `leave` (scale by 1/N,
+    normalise to affine)."""
+
+    def __init__(self, ctx, device):
+        self.ctx, self.device = ctx, device
+
+    def _sync(self):
+        import torch
+        torch.cuda.synchronize(self.device)
+
+    def enter(self, affine):
+        import torch
+        self._sync()
+        n = affine.numel() // 8
+        out = torch.empty(affine.shape[:-1] + (16,), dtype=torch.int64, device=affine.device)
+        self.ctx.dev_ec_from_affine(affine.data_ptr(), out.data_ptr(), n)
+        return out
+
+    def ntt_rows(self, t):
+        self._sync()
+        self.ctx.dev_ec_ntt_rows(t.data_ptr(), t.shape[1].bit_length() - 1, t.shape[0], True)
+
+    def twiddle(self, t, log_total, row0):
+        self._sync()
+        self.ctx.dev_ec_twiddle(t.data_ptr(), t.shape[0], t.shape[1], log_total, row0, True)
+
+    def leave(self, t, log_total):
+        import torch
+        self._sync()
+        out = torch.empty(t.shape[:-1] + (8,), dtype=torch.int64, device=t.device)
+        self.ctx.dev_ec_to_affine(t.data_ptr(), out.data_ptr(), t.numel() // 16, log_total)
+        return out
+
+
+class DistributedEcIntt:
+    """Crs::from_powers (src/plonk.rs:179-185) of a 2^log_n monomial key over `world` ranks: the four-step INVERSE NTT over
+    G1 points with ONE all-to-all (SURVEY.md §8e row "EC-iNTT", BASELINE configs[3]).
+
+    Input  (column blocks): rank r holds the monomial bases [tau^(N2*n1 + r*C + j)]G, n1 < N1, j < C = N2/world, as an
+                            (N1, C, 8) array of affine points (canonical limbs).
+    Output (row blocks)   : rank q holds [L_i(tau)]G for i = (q*K + a) + N1*k2, a < K = N1/world, k2 < N2, as (K, N2, 8).
+    Every butterfly and every twiddle is a 254-bit scalar multiplication, so the work per rank is (N/world) * (log2(N)/2 + 1)
+    of them; the all-to-all moves N * 128 B / world per rank once.
+    """
+
+    def __init__(self, log_n, rank, world, ops, group=None, log_n1=None):
+        self.log_n, self.rank, self.world, self.ops, self.group = log_n, rank, world, ops, group
+        self.log_n1 = log_n1 if log_n1 is not None else (log_n + 1) // 2
+        self.n1, self.n2 = 1 << self.log_n1, 1 << (log_n - self.log_n1)
+        if self.n1 % world or self.n2 % world:
+            raise _lib.SynthesisError(6, "both NTT factors must be divisible by the number of ranks")
+        self.c, self.k = self.n2 // world, self.n1 // world
+
+    def local_input(self, bases_full):
+        b = np.ascontiguousarray(bases_full, dtype=np.uint64).reshape(self.n1, self.n2, 8)
+        return np.ascontiguousarray(b[:, self.rank * self.c:(self.rank + 1) * self.c])
+
+    def inverse(self, local):
+        import torch
+        import torch.distributed as td
+        t = local if isinstance(local, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(local).view(np.int64))
+        n2, c, k, w = self.n2, self.c, self.k, self.world
+        pts = self.ops.enter(t.transpose(0, 1).contiguous())               # (C, N1, E): this rank's columns as rows
+        e = pts.shape[-1]
+        self.ops.ntt_rows(pts)                                             # over n1 -> k1 (inverse, unscaled)
+        self.ops.twiddle(pts, self.log_n, self.rank * c)                   # * w_N^-(n2 * k1)
+        send = pts.view(c, w, k, e).permute(1, 0, 2, 3).contiguous()       # (world, C, K): block q goes to rank q
+        recv = torch.empty_like(send)
+        if w == 1:
+            recv.copy_(send)
+        else:
+            td.all_to_all_single(recv, send, group=self.group)
+        rows = recv.view(n2, k, e).transpose(0, 1).contiguous()            # (K, N2): my k1 rows, all n2
+        self.ops.ntt_rows(rows)                                            # over n2 -> k2
+        return self.ops.leave(rows, self.log_n)                            # * 1/N, affine
+
+    def gather_natural(self, rows):
+        """All ranks' outputs reassembled into the natural-order Lagrange key (test helper; O(N) traffic)."""
+        import torch
+        import torch.distributed as td
+        rows = rows.contiguous()
+        parts = [torch.empty_like(rows) for _ in range(self.world)]
+        if self.world == 1:
+            parts[0].copy_(rows)
+        else:
+            td.all_gather(parts, rows, group=self.group)
+        full = torch.cat(parts, dim=0)                                     # (N1, N2): [k1][k2]
+        return full.transpose(0, 1).contiguous().cpu().numpy().view(np.uint64).reshape(-1, 8)  # index k1 + N1*k2

@@ -132,3 +132,60 @@ def test_four_step_single_rank_matches_plain_ntt(orc):
     assert (d.gather_natural(d.forward(d.local_input(x))) == orc.ntt(x)).all()
     with pytest.raises(_lib.SynthesisError):
         dist.DistributedNtt(3, 0, 4, _HostNttOps(orc))  # factors 4 x 2 are not both divisible by 4 ranks
+
+
+class _HostEcOps:
+    """Checker-backed stand-in for CudaEcNttOps: points stay affine, the row transforms are the oracle's (scaled) EC
+    inverse NTT, so `leave` has nothing left to scale."""
+
+    def __init__(self, orc):
+        self.orc = orc
+
+    def enter(self, t):
+        return t.clone()
+
+    def ntt_rows(self, t):
+        a = t.numpy().view(np.uint64)
+        for r in range(a.shape[0]):
+            a[r] = self.orc.ec_intt(a[r])
+
+    def twiddle(self, t, log_total, row0):
+        from plonkit_b200.bn254 import R_MOD, root_of_unity
+        a = t.numpy().view(np.uint64)
+        winv = pow(root_of_unity(log_total), -1, R_MOD)
+        for r in range(a.shape[0]):
+            for c in range(a.shape[1]):
+                a[r, c] = self.orc.g1_mul(a[r, c], pow(winv, (row0 + r) * c, R_MOD))
+
+    def leave(self, t, log_total):
+        return t
+
+
+def _ec_worker(rank, world, port, ret):
+    import torch.distributed as td
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    td.init_process_group(backend="gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, ROOT)
+        from oracle import oracle as orc
+        key = reader.load_key_monomial_form(os.path.join(SIMPLE, "setup_2^10.key"))
+        ok = True
+        for log_n, log_n1 in ((4, 2), (5, 2)):
+            bases = key.g1_bases[: 1 << log_n]
+            d = dist.DistributedEcIntt(log_n, rank, world, _HostEcOps(orc), log_n1=log_n1)
+            out = d.inverse(d.local_input(bases))
+            ok = ok and bool((d.gather_natural(out) == orc.ec_intt(bases)).all())
+        ret[rank] = ok
+    finally:
+        td.destroy_process_group()
+
+
+def test_four_step_distributed_ec_intt_over_gloo():
+    """Crs::from_powers split over 2 ranks: column transforms, inverse twiddles, one all-to-all, row transforms."""
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_ec_worker, args=(2, 29644, ret), nprocs=2, join=True)
+    assert [ret[r] for r in range(2)] == [True, True]

@@ -23,3 +23,17 @@ def test_sharded_committer_single_rank(ctx, orc, simple_key):
     c = dist.ShardedCommitter(simple_key.g1_bases[:1000], 0, 1, ctx=ctx)
     s = synth.random_field_elements(1000, seed=3)
     assert (c.commit(s) == orc.msm(s, simple_key.g1_bases[:1000], threads=4)).all()
+
+
+def test_four_step_ec_intt_with_device_primitives(ctx, orc, simple_key):
+    """Crs::from_powers through the device-pointer EC primitives (pk_dev_ec_*) == the oracle's EC inverse NTT and ==
+    the single-call pk_ec_intt_g1."""
+    import torch
+    for log_n, log_n1 in ((3, 1), (6, 3), (9, 5)):
+        bases = simple_key.g1_bases[: 1 << log_n]
+        d = dist.DistributedEcIntt(log_n, 0, 1, dist.CudaEcNttOps(ctx, 0), log_n1=log_n1)
+        local = torch.from_numpy(d.local_input(bases).view(np.int64)).cuda()
+        got = d.gather_natural(d.inverse(local))
+        assert (got == orc.ec_intt(bases, threads=8)).all(), log_n
+    ctx.srs_load_g1(simple_key.g1_bases[:512])
+    assert (got == ctx.ec_intt_g1(9)).all()

@@ -50,6 +50,28 @@ def main():
         ref = ctx.ntt(x)
         print("four-step NTT 2^%d over %d GPUs: %.2f ms (device-resident, one all-to-all), == single GPU: %s"
               % (log_n, world, dt * 1e3, bool((full == ref).all())), flush=True)
+    td.barrier(device_ids=[local])
+    # ---- four-step distributed EC inverse NTT (dump-lagrange / Crs::from_powers)
+    log_e = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+    key = srs[: 1 << log_e]
+    de = dist.DistributedEcIntt(log_e, rank, world, dist.CudaEcNttOps(ctx, local))
+    loc = torch.from_numpy(de.local_input(key).view(np.int64)).cuda()
+    out = de.inverse(loc)
+    td.barrier(device_ids=[local])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = de.inverse(loc)
+    torch.cuda.synchronize()
+    td.barrier(device_ids=[local])
+    dt = time.perf_counter() - t0
+    full = de.gather_natural(out)
+    if rank == 0:
+        ctx.srs_load_g1(key)
+        t0 = time.perf_counter()
+        ref = ctx.ec_intt_g1(log_e)
+        dt1 = time.perf_counter() - t0
+        print("four-step EC-iNTT (dump-lagrange) 2^%d over %d GPUs: %.1f ms (device-resident, one all-to-all); one GPU: %.1f ms; "
+              "== single GPU: %s" % (log_e, world, dt * 1e3, dt1 * 1e3, bool((full == ref).all())), flush=True)
     td.destroy_process_group()
 
 
