@@ -344,6 +344,14 @@ def bench_ours(args):
         "clocks": clocks,
         "prep_s": prep_s,
     }
+    # BASELINE.json's secondary metrics on the same GPU: single-set MSM (uniform scalars) and NTT at the bench size
+    try:
+        ms_msm, ms_ntt = ctx.bench_msm(n, 3), ctx.bench_ntt(args.log_n, 5)
+        out["micro"] = {"msm_mscalar_per_s": n / ms_msm / 1e3, "msm_ms": ms_msm, "ntt_gelem_per_s": n / ms_ntt / 1e6, "ntt_ms": ms_ntt,
+                        "msm_hbm_frac_at_96B_per_pair": 96.0 * n / (ms_msm * 1e-3) / 1e9 / peak,
+                        "ntt_hbm_frac_at_64B_per_elem": 64.0 * n / (ms_ntt * 1e-3) / 1e9 / peak, "log_n": args.log_n}
+    except Exception as ex:  # secondary figures must never cost the headline line
+        out["micro"] = {"error": str(ex)}
     if world == 1 and not args.no_cpu:
         cores = effective_cores()
         ls = cpu_sample_log_n(cores, args.log_n, 1, 40.0, srs_extra=0)  # bounded sample: ~10-30 s of CPU work
