@@ -4,27 +4,14 @@
 //                src/bin/main.rs:360-381): an inverse FFT over G1 POINTS turning [tau^j] G into [L_i(tau)] G.
 //                Every butterfly is a 254-bit scalar multiplication plus a point add/sub.
 // Both are setup-time tools, not part of the per-proof path.  First version: one kernel per radix-2 stage over an
-// XYZZ array in global memory, plain double-and-add for the twiddle multiplication.
+// XYZZ array in global memory; the twiddle multiplication is the GLV double-and-add of ecmul.cuh.
+#include "ecmul.cuh"
 #include "msm.cuh"
 #include "ntt.cuh"
 
 namespace pk {
 
 static inline dim3 grid1d(size_t n, int block) { return dim3((unsigned)((n + block - 1) / block)); }
-
-// k * P for a canonical 254-bit scalar, left-to-right double-and-add
-__device__ __forceinline__ g1_xyzz_t scalar_mul(const g1_xyzz_t& P, const fr_t& k_canonical) {
-    g1_xyzz_t r = g1_xyzz_t::infinity();
-    bool started = false;
-    for (int i = 253; i >= 0; --i) {
-        if (started) r = r.dbl();
-        if ((k_canonical.v[i >> 5] >> (i & 31)) & 1) {
-            r = started ? r.add(P) : P;
-            started = true;
-        }
-    }
-    return r;
-}
 
 __global__ void __launch_bounds__(128) srs_gen_kernel(g1_affine_t* out, fr_t tau, size_t n) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;

@@ -1,6 +1,7 @@
 // Host build (g++) of the product's field / curve / transcript headers, for CPU-side checks of the exact
 // instruction sequences the device code runs (the carry-flag primitives are emulated on the host, see fp.cuh).
 #include "../plonkit_b200/csrc/ec.cuh"
+#include "../plonkit_b200/csrc/ecmul.cuh"
 #include "../tools/micro/fp_f64.cuh"
 #include "../tools/micro/fp_wide.cuh"
 #include <cfenv>
@@ -68,6 +69,18 @@ void hc_lazy_field(const uint32_t* a, const uint32_t* b, uint32_t* o, int n) {
         fq_t r = x.lmul(y).lmul(x.ladd(y)).lsub(y.lmul(y)).lsub(x.ladd(x).ladd(y)).lnormalize();
         memcpy(o + 8 * i, r.v, 32);
     }
+}
+// GLV: out_k = (|k1| (5 limbs), sign1, |k2| (5 limbs), sign2); out_pt[0] = k * p (GLV), out_pt[1] = k * p (plain 254-bit walk)
+void hc_glv(const uint64_t* p, const uint32_t* k_canonical, uint32_t* out_k, uint64_t* out_pt) {
+    bool n1, n2;
+    glv::decompose(k_canonical, out_k, n1, out_k + 6, n2);
+    out_k[5] = n1; out_k[11] = n2;
+    fr_t k; memcpy(k.v, k_canonical, 32);
+    g1_xyzz_t P = g1_xyzz_t::from_affine(load_pt(p));
+    g1_xyzz_t P3 = P.dbl().add(P);                       // non-trivial ZZ
+    g1_xyzz_t Q = P3.add(P.dbl().neg());                 // == P with ZZ != 1
+    store_pt(scalar_mul(Q, k).to_affine(), out_pt);
+    store_pt(scalar_mul_plain(Q, k).to_affine(), out_pt + 8);
 }
 void hc_keccak(const uint8_t* d, uint64_t n, uint8_t* out) { Keccak256 h; h.update(d, n); h.finish(out); }
 // transcript: commit `n` 32-byte big-endian values, then draw `m` challenges (canonical LE limbs out)

@@ -278,6 +278,28 @@ def test_lazy_form_field_chain(hc):
     assert limbs_to_ints(out.view(np.uint64)) == want
 
 
+def test_glv_decomposition_and_scalar_multiplication(hc, orc, simple_key):
+    """ecmul.cuh: k = k1 + k2 * LAMBDA with short halves, and k * P through the endomorphism == the plain 254-bit walk ==
+    the oracle's scalar multiplication (which the EC inverse NTT of Crs::from_powers is made of)."""
+    lam = 0xb3c4d79d41a917585bfc41088d8daaa78b17ea66b99c90dd
+    assert (lam * lam + lam + 1) % R_MOD == 0
+    rng = np.random.default_rng(13)
+    ks = [0, 1, 2, R_MOD - 1, R_MOD - 2, lam, lam + 1, (1 << 253), (1 << 127), (1 << 128) - 1] + \
+         [int.from_bytes(rng.bytes(32), "little") % R_MOD for _ in range(60)]
+    inf = np.zeros(8, dtype=np.uint64)
+    for n, k in enumerate(ks):
+        p = simple_key.g1_bases[3 + n % 50] if n != 5 else inf
+        kk = ints_to_limbs([k]).view(np.uint32)
+        out_k = np.zeros(12, dtype=np.uint32)
+        out_pt = np.zeros((2, 8), dtype=np.uint64)
+        hc.hc_glv(_p(np.ascontiguousarray(p)), _p(kk), _p(out_k), _p(out_pt))
+        k1 = sum(int(out_k[i]) << (32 * i) for i in range(5)) * (-1 if out_k[5] else 1)
+        k2 = sum(int(out_k[6 + i]) << (32 * i) for i in range(5)) * (-1 if out_k[11] else 1)
+        assert (k1 + k2 * lam - k) % R_MOD == 0 and abs(k1) < (1 << 129) and abs(k2) < (1 << 129)
+        want = orc.g1_mul(p, k)
+        assert (out_pt[0] == want).all() and (out_pt[1] == want).all(), hex(k)
+
+
 def test_host_keccak_and_transcript_match_oracle(hc, orc):
     for msg in (b"", b"abc", b"a" * 135, b"a" * 136, b"a" * 137, bytes(range(200)) * 3):
         out = ctypes.create_string_buffer(32)

@@ -33,6 +33,7 @@ def main():
             print("MSM 2^20 witness-like (40%% zero, 10%% one), through host buffers: %.2f ms" % (dt * 1e3), flush=True)
     for lg in (10, 12, 14, 16, 18, 20):
         ctx.srs_load_g1(srs[: 1 << lg])
+        ctx.ec_intt_g1(lg)  # first call at a size builds its twiddle table
         t = time.perf_counter(); ctx.ec_intt_g1(lg); dt = time.perf_counter() - t
         print("EC-iNTT (dump-lagrange) 2^%d: %.1f ms  (HBM-roofline frac %.6f at 128 B/point)" % (lg, dt * 1e3, 128.0 * (1 << lg) / dt / 6571.6e9), flush=True)
     # restated CPU baseline (oracle port, all usable host cores) for the same primitives, bounded sizes
