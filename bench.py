@@ -338,7 +338,7 @@ def bench_ours(args):
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes, "ms_per_launch": accum_ms,
                      "share_of_step": prof["msm_accum_ms"] / ms_prof, "ms_per_step_profiled": ms_prof / args.steps,
-                     "note": "integer-multiply-pipe bound (10 x 254-bit Montgomery products per pair and window; 85-87 % of the measured IMAD.WIDE peak, DESIGN.md 4.5); timed by CUDA events on the library stream in a separate single-prover pass; share_of_step is relative to that pass"},
+                     "note": "integer-multiply-pipe bound (10 x 254-bit Montgomery products per pair and window; 89 % of the measured IMAD.WIDE issue ceiling, DESIGN.md 4.5); timed by CUDA events on the library stream in a separate single-prover pass; share_of_step is relative to that pass"},
         "ntt": {"ms_per_step": prof["ntt_ms"] / args.steps, "launches_per_step": prof["ntt_launches"] / args.steps},
         "phase_ms": prof["phase_ms"],
         "clocks": clocks,
