@@ -162,15 +162,7 @@ void srs_load(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits
     uint32_t chunk = 64;
     while (M / chunk > (size_t(1) << 19)) chunk *= 2;
     s->chunk1 = chunk;
-    // scratch 0 serves a full batch, scratch 1 the second half of a split batch (see msm_run_batch)
-    alloc_scratch(s, s->scratch[0], nb);
-    if (nb >= 2) alloc_scratch(s, s->scratch[1], nb / 2);
-    if (!s->stream2) {
-        PK_CUDA(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
-        PK_CUDA(cudaEventCreateWithFlags(&s->ev_ready, cudaEventDisableTiming));
-        PK_CUDA(cudaEventCreateWithFlags(&s->ev_sorted, cudaEventDisableTiming));
-        PK_CUDA(cudaEventCreateWithFlags(&s->ev_done2, cudaEventDisableTiming));
-    }
+    alloc_scratch(s, s->scratch, nb);
     PK_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
@@ -510,7 +502,7 @@ void affine_to_abi(const g1_affine_t& p, uint64_t out[8]) {
 
 // enqueues one group of <= sc.max_sets scalar sets on stream st; the nb XYZZ results land in host_pt (pinned) once st drains
 static void msm_enqueue_group(pk_ctx* ctx, MsmScratch& sc, cudaStream_t st, const fr_t* const* scalars, int nb, uint64_t n,
-                              uint64_t base_offset, g1_xyzz_t* host_pt, cudaEvent_t sorted_event) {
+                              uint64_t base_offset, g1_xyzz_t* host_pt) {
     SrsTables* s = ctx->srs;
     const uint32_t B = s->B;
     const uint32_t NB = (uint32_t)nb * B;
@@ -533,7 +525,6 @@ static void msm_enqueue_group(pk_ctx* ctx, MsmScratch& sc, cudaStream_t st, cons
     msm_fine_sort_kernel<<<NC, FS_THREADS, FS_CAP * sizeof(uint2) + ((size_t(1) << fine_bits) + FS_THREADS) * sizeof(uint32_t), st>>>(
         sc.tmp_entries.p, sc.entries.p, sc.coarse_offset.p, fine_bits);
     ctx->prof.kernel_launches += 6;
-    if (sorted_event) PK_CUDA(cudaEventRecord(sorted_event, st));
     // accumulation levels (worst-case grids; the device-side counts bound the real work)
     size_t max_entries = (size_t)nb * n * s->W;
     AccumParams p;
@@ -590,29 +581,14 @@ void msm_run_batch(pk_ctx* ctx, const fr_t* const* scalars, int nb, uint64_t n, 
         for (int k = 0; k < nb; ++k) out[k] = g1_affine_t::infinity();
         return;
     }
-    const int group = s->scratch[0].max_sets;
+    const int group = s->scratch.max_sets;
     g1_xyzz_t* host_pt = reinterpret_cast<g1_xyzz_t*>(ctx->pinned);
-    // Optional (PK_MSM_OVERLAP=1): split a group of >= 2 sets in two halves on two streams, staggered by the first
-    // half's sort, so that the memory/latency-bound kernels of one half overlap the integer-bound accumulation of the
-    // other.  Measured on B200 at N = 2^20 this LOSES 4 % (52.8 vs 50.9 ms per proof): the halves pay the latency-bound
-    // tail kernels twice and the accumulation kernels already fill the machine.  Off by default; never used while
-    // per-kernel event timing is on.
-    static const bool want_overlap = [] { const char* e = getenv("PK_MSM_OVERLAP"); return e && e[0] == '1'; }();
-    const bool overlap = want_overlap && !ctx->prof.enabled && s->scratch[1].max_sets > 0 && n >= 4096;
+    // (Splitting a group over two streams so that one half's sort overlaps the other half's accumulation was measured
+    // at N = 2^20: 4 % slower, the halves pay the latency-bound tail kernels twice.  The overlap that pays is between
+    // independent proofs, each on its own context: plonk.ProverPool.)
     for (int k = 0; k < nb; k += group) {
         const int g = nb - k < group ? nb - k : group;
-        const int ga = overlap && g >= 2 ? (g + 1) / 2 : g, gb = g - ga;
-        if (gb > 0) {
-            PK_CUDA(cudaEventRecord(s->ev_ready, ctx->stream));  // the scalars are produced on the main stream
-            PK_CUDA(cudaStreamWaitEvent(s->stream2, s->ev_ready, 0));
-        }
-        msm_enqueue_group(ctx, s->scratch[0], ctx->stream, scalars + k, ga, n, base_offset, host_pt, gb > 0 ? s->ev_sorted : nullptr);
-        if (gb > 0) {
-            PK_CUDA(cudaStreamWaitEvent(s->stream2, s->ev_sorted, 0));
-            msm_enqueue_group(ctx, s->scratch[1], s->stream2, scalars + k + ga, gb, n, base_offset, host_pt + ga, nullptr);
-            PK_CUDA(cudaEventRecord(s->ev_done2, s->stream2));
-            PK_CUDA(cudaStreamWaitEvent(ctx->stream, s->ev_done2, 0));
-        }
+        msm_enqueue_group(ctx, s->scratch, ctx->stream, scalars + k, g, n, base_offset, host_pt);
         PK_CUDA(cudaStreamSynchronize(ctx->stream));
         for (int j = 0; j < g; ++j) out[k + j] = host_pt[j].to_affine();
     }

@@ -13,7 +13,7 @@ struct WindowPlan {
     uint8_t width[64];
 };
 
-// per-stream working set of one MSM group
+// working set of one MSM group
 struct MsmScratch {
     int max_sets = 0;
     DevBuf<uint32_t> coarse_count, coarse_offset, coarse_cursor;  // [NC + 1] coarse-bin histogram / offsets / cursors
@@ -36,16 +36,8 @@ struct SrsTables {
     int lo_bits = 0, hi_bits = 0;  // bucket id = hi * 2^lo_bits + lo (two-level bucket reduction)
     DevBuf<g1_affine_t> table;   // [W][n]: table[w][i] = 2^(c*w) * base_i, affine, Montgomery form
 
-    MsmScratch scratch[2];               // [0]: a full batch; [1]: the second half of a split batch
-    cudaStream_t stream2 = nullptr;      // second stream + events for the split
-    cudaEvent_t ev_ready = nullptr, ev_sorted = nullptr, ev_done2 = nullptr;
+    MsmScratch scratch;
     uint32_t chunk1 = 64;                // entries per thread at level 1 (for a single scalar set)
-    ~SrsTables() {
-        if (stream2) cudaStreamDestroy(stream2);
-        if (ev_ready) cudaEventDestroy(ev_ready);
-        if (ev_sorted) cudaEventDestroy(ev_sorted);
-        if (ev_done2) cudaEventDestroy(ev_done2);
-    }
 };
 
 // loads n affine bases (canonical limbs, host) and builds the window tables
