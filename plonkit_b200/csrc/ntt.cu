@@ -4,7 +4,7 @@
 // bitreversed_lde_using_bitreversed_ntt} (call sites src/plonk.rs:104,140,152-159), which on
 // the CPU are an in-place Cooley-Tukey radix-2 transform split over host threads.
 //
-// Device design: a size-2^L transform is cut into passes of up to 10 stages.  Each pass stages a tile of 2^k
+// Device design: a size-2^L transform is cut into passes of up to 9 stages (see ntt_tile_log).  Each pass stages a tile of 2^k
 // (strided) x C (contiguous) elements in shared memory — C >= 4 keeps every global access a >=128 B run of
 // 128-bit loads/stores — runs its k butterfly stages there with one Montgomery multiplication per butterfly
 // held in registers, and writes the tile back.  Forward transforms are decimation-in-frequency (natural ->
@@ -211,12 +211,21 @@ template <bool DIT> __global__ void __launch_bounds__(512) ntt_pass_kernel(NttPa
     }
 }
 
-// pass plan: one contiguous pass of up to 10 stages + strided passes of up to 8 stages
+// log2 of the shared-memory tile (elements); 2^(tile - 1) threads per block.  Measured on B200 (2^20 / 2^24 transform):
+// tile 2^10 (512 threads, 2 blocks per SM) 0.237 / 4.20 ms, 2^9 0.206 / 3.54 ms, 2^8 0.198 / 3.50 ms — smaller blocks let the
+// load, butterfly and store phases of different blocks overlap on an SM.  2^9 keeps >= 64-byte runs in the strided passes.
+// PK_NTT_TILE_LOG overrides (8..10).
+static int ntt_tile_log() {
+    static const int v = [] { const char* e = getenv("PK_NTT_TILE_LOG"); int t = e ? atoi(e) : 9; return t < 8 ? 8 : (t > 10 ? 10 : t); }();
+    return v;
+}
+#define NTT_TILE_LOG ntt_tile_log()
+// pass plan: one contiguous pass of up to NTT_TILE_LOG stages + strided passes of up to 8 stages
 struct PassPlan { int n; int k[8]; int bl[8]; int c_log[8]; };
 static PassPlan plan_passes(int L, bool dit) {
     PassPlan pl;
     pl.n = 0;
-    int kc = L < 10 ? L : 10;
+    int kc = L < NTT_TILE_LOG ? L : NTT_TILE_LOG;
     int rem = L - kc;
     int ns = (rem + 7) / 8;
     int ks[8];
@@ -227,7 +236,7 @@ static PassPlan plan_passes(int L, bool dit) {
         int s0 = kc;
         for (int i = 0; i < ns; ++i) {
             pl.k[pl.n] = ks[i]; pl.bl[pl.n] = s0;
-            int cl = 10 - ks[i]; if (cl > s0) cl = s0;
+            int cl = NTT_TILE_LOG - ks[i]; if (cl > s0) cl = s0;
             pl.c_log[pl.n] = cl;
             s0 += ks[i]; pl.n++;
         }
@@ -237,7 +246,7 @@ static PassPlan plan_passes(int L, bool dit) {
         for (int i = 0; i < ns; ++i) {
             int bl = L - s0 - ks[i];
             pl.k[pl.n] = ks[i]; pl.bl[pl.n] = bl;
-            int cl = 10 - ks[i]; if (cl > bl) cl = bl;
+            int cl = NTT_TILE_LOG - ks[i]; if (cl > bl) cl = bl;
             pl.c_log[pl.n] = cl;
             s0 += ks[i]; pl.n++;
         }
