@@ -4,6 +4,7 @@ subcommand names, flags, defaults and overwrite guards:
     analyse                  -c/--circuit  -o/--output analyse.json                         (main.rs:313-331)
     setup                    -p/--power  -m/--srs_monomial_form  --overwrite                (main.rs:334-343)
     dump-lagrange            -m  -l/--srs_lagrange_form  -c  --overwrite                    (main.rs:360-381)
+                             (under torchrun with N processes: the EC inverse NTT is split over N GPUs)
     prove                    -m  [-l]  -c  -w witness.wtns  -p proof.bin  -j proof.json  -i public.json
                              -t keccak  --overwrite                                          (main.rs:384-424)
     export-verification-key  -m  -c  -v vk.bin  --overwrite                                 (main.rs:484-504)
@@ -75,8 +76,26 @@ def cmd_setup(o):
 
 def cmd_dump_lagrange(o):
     c = CircomCircuit(reader.load_r1cs(resolve_circuit_file(o.circuit)), None, None, AUX_OFFSET)
-    setup = plonk.SetupForProver.prepare_setup_for_prover(c, reader.load_key_monomial_form(o.srs_monomial_form), None)
-    key = setup.get_srs_lagrange_form_from_monomial_form()
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    if world > 1:
+        # one process per GPU (torchrun): the EC inverse NTT is split four-step across the ranks, rank 0 writes the file
+        import torch
+        import torch.distributed as td
+        from . import _lib, dist
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+        mono = reader.load_key_monomial_form(o.srs_monomial_form)
+        n = 1 << max(plonk.domain_log2(c), 0)
+        pts = dist.lagrange_key_distributed(mono.g1_bases[:n], _lib.Context(local), rank, world, local)
+        td.barrier(device_ids=[local])
+        td.destroy_process_group()
+        if rank != 0:
+            return
+        key = reader.Crs(pts, mono.g2_raw, "lagrange")
+    else:
+        setup = plonk.SetupForProver.prepare_setup_for_prover(c, reader.load_key_monomial_form(o.srs_monomial_form), None)
+        key = setup.get_srs_lagrange_form_from_monomial_form()
     _guard(o.srs_lagrange_form, "srs_lagrange_form", o.overwrite)
     with open(o.srs_lagrange_form, "wb") as f:
         key.write(f)

@@ -233,3 +233,17 @@ class DistributedEcIntt:
             td.all_gather(parts, rows, group=self.group)
         full = torch.cat(parts, dim=0)                                     # (N1, N2): [k1][k2]
         return full.transpose(0, 1).contiguous().cpu().numpy().view(np.uint64).reshape(-1, 8)  # index k1 + N1*k2
+
+
+def lagrange_key_distributed(bases, ctx, rank, world, device, group=None):
+    """`Crs::from_powers` (src/plonk.rs:179-185) of the first 2^k monomial bases across the ranks of `group`: every rank
+    runs its share of the four-step EC inverse NTT on its GPU and all ranks end up with the full Lagrange key (natural
+    order, (N, 8) canonical limbs) — what `plonkit dump-lagrange` writes.  One process per GPU under torchrun."""
+    import torch
+    b = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
+    log_n = b.shape[0].bit_length() - 1
+    if 1 << log_n != b.shape[0]:
+        raise _lib.SynthesisError(6, "the Lagrange key needs a power-of-two number of bases")
+    d = DistributedEcIntt(log_n, rank, world, CudaEcNttOps(ctx, device), group=group)
+    local = torch.from_numpy(d.local_input(b).view(np.int64)).cuda(device)
+    return d.gather_natural(d.inverse(local))

@@ -52,6 +52,11 @@ def _as_assembly(circuit) -> Assembly:
     raise TypeError("circuit must be a CircomCircuit or an Assembly")
 
 
+def domain_log2(circuit) -> int:
+    """log2 of the evaluation domain of a circuit (setup_polynomials.n.next_power_of_two(), src/plonk.rs:180)."""
+    return _as_assembly(circuit).n.bit_length() - 1
+
+
 class SetupForProver:
     """src/plonk.rs:50-55: setup polynomials + SRS, resident on the device."""
 
