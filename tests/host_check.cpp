@@ -45,7 +45,7 @@ void hc_fr_ops(const uint64_t* a, const uint64_t* b, uint64_t* add, uint64_t* su
     }
 }
 // out[0] = p + q (mixed), out[1] = p + q (full), out[2] = 2p, out[3] = k * p (mul_small),
-// out[4] = (((3p - 2p) + q) + q') + q'' through add_mixed_lazy chained WITHOUT normalising in between (q' = -2q.., see below)
+// out[4] = ((p + q) + q) + p through add_mixed_lazy chained WITHOUT normalising in between
 void hc_g1_ops(const uint64_t* p, const uint64_t* q, uint32_t k, uint64_t* out) {
     g1_affine_t P = load_pt(p), Q = load_pt(q);
     g1_xyzz_t X = g1_xyzz_t::from_affine(P), Y = g1_xyzz_t::from_affine(Q);
@@ -60,7 +60,6 @@ void hc_g1_ops(const uint64_t* p, const uint64_t* q, uint32_t k, uint64_t* out) 
     // in [0, 2p) across the three additions and are normalised once)
     g1_xyzz_t L = Xn.add_mixed_lazy(Q).add_mixed_lazy(Q).add_mixed_lazy(P).lnorm();
     store_pt(L.to_affine(), out + 32);
-    // field level: lazy product chain vs canonical
 }
 void hc_lazy_field(const uint32_t* a, const uint32_t* b, uint32_t* o, int n) {
     // o = normalise( lsub( lmul(lmul(a,b), ladd(a,b)), lmul(b,b) ) )  vs the same with canonical ops computed by the caller
