@@ -33,18 +33,82 @@
 using namespace orc;
 
 // ---------------------------------------------------------------- threading (stands in for bellman's Worker)
+// A persistent pool (bellman's Worker keeps a futures thread-pool + crossbeam scopes alive; spawning fresh threads per
+// call made 32 threads slower than 16).  run(n, f) executes f(0..n-1) on the pool, the caller takes part.
+#include <condition_variable>
+#include <functional>
+class Pool {
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv, cv_done;
+    std::function<void(int)> job;
+    int njobs = 0, pending = 0;
+    std::atomic<int> next{0};
+    uint64_t gen = 0;
+    bool stop = false;
+    static thread_local bool in_worker;
+    void loop() {
+        in_worker = true;
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || gen != seen; });
+                if (stop) return;
+                seen = gen;
+            }
+            drain();
+        }
+    }
+    void drain() {
+        int done = 0;
+        for (;;) {
+            int i = next.fetch_add(1);
+            if (i >= njobs) break;
+            job(i);
+            ++done;
+        }
+        if (done) {
+            std::lock_guard<std::mutex> lk(mu);
+            pending -= done;
+            if (pending == 0) cv_done.notify_all();
+        }
+    }
+public:
+    ~Pool() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        for (auto& t : workers) t.join();
+    }
+    void run(int n, const std::function<void(int)>& f) {
+        if (n <= 0) return;
+        if (n == 1 || in_worker) { for (int i = 0; i < n; ++i) f(i); return; }
+        static std::mutex run_mu;  // one parallel region at a time (callers are single-threaded per prove anyway)
+        std::lock_guard<std::mutex> rl(run_mu);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            while ((int)workers.size() < n - 1) workers.emplace_back([this] { loop(); });
+            job = f; njobs = n; pending = n; next = 0; ++gen;
+        }
+        cv.notify_all();
+        drain();
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+};
+thread_local bool Pool::in_worker = false;
+static Pool& pool() { static Pool* p = new Pool(); return *p; }  // leaked on purpose: no teardown order issues at exit
+
 template <class F> static void parallel_chunks(size_t n, int threads, F f) {
     if (threads < 1) threads = 1;
     if (n == 0) return;
     size_t chunk = (n + threads - 1) / threads;  // Worker::get_chunk_size [ext]
     if (threads == 1 || n < 64) { f(0, n, 0); return; }
-    std::vector<std::thread> th;
-    int tid = 0;
-    for (size_t b = 0; b < n; b += chunk, ++tid) {
-        size_t e = std::min(n, b + chunk);
-        th.emplace_back([=] { f(b, e, tid); });
-    }
-    for (auto& t : th) t.join();
+    int nchunks = (int)((n + chunk - 1) / chunk);
+    pool().run(nchunks, [&](int tid) {
+        size_t b = (size_t)tid * chunk, e = std::min(n, b + chunk);
+        f(b, e, tid);
+    });
 }
 
 static int log2_floor(size_t x) { int l = 0; while ((size_t(1) << (l + 1)) <= x) ++l; return l; }
@@ -98,25 +162,22 @@ static void parallel_fft(Fr* a, size_t n, const Fr& omega, int log_n, int log_cp
     size_t new_n = size_t(1) << log_new_n;
     std::vector<hvec<Fr>> tmp(num_cpus, hvec<Fr>(new_n, Fr::zero()));
     Fr new_omega = omega.pow_u64(num_cpus);
-    std::vector<std::thread> th;
-    for (size_t j = 0; j < num_cpus; ++j) {
-        th.emplace_back([&, j] {
-            Fr omega_j = omega.pow_u64(j);
-            Fr omega_step = omega.pow_u64((u64)j << log_new_n);
-            Fr elt = Fr::one();
-            hvec<Fr>& t = tmp[j];
-            for (size_t i = 0; i < new_n; ++i) {
-                for (size_t s = 0; s < num_cpus; ++s) {
-                    size_t idx = (i + (s << log_new_n)) % n;
-                    t[i] += a[idx] * elt;
-                    elt *= omega_step;
-                }
-                elt *= omega_j;
+    pool().run((int)num_cpus, [&](int jj) {
+        const size_t j = (size_t)jj;
+        Fr omega_j = omega.pow_u64(j);
+        Fr omega_step = omega.pow_u64((u64)j << log_new_n);
+        Fr elt = Fr::one();
+        hvec<Fr>& t = tmp[j];
+        for (size_t i = 0; i < new_n; ++i) {
+            for (size_t s = 0; s < num_cpus; ++s) {
+                size_t idx = (i + (s << log_new_n)) % n;
+                t[i] += a[idx] * elt;
+                elt *= omega_step;
             }
-            serial_fft(t.data(), new_n, new_omega, log_new_n);
-        });
-    }
-    for (auto& t : th) t.join();
+            elt *= omega_j;
+        }
+        serial_fft(t.data(), new_n, new_omega, log_new_n);
+    });
     size_t mask = num_cpus - 1;
     parallel_chunks(n, (int)num_cpus, [&](size_t b, size_t e, int) {
         for (size_t idx = b; idx < e; ++idx) a[idx] = tmp[idx & mask][idx >> log_cpus];
@@ -335,12 +396,47 @@ static hvec<Fr> divide_by_linear(const hvec<Fr>& p, const Fr& z) {
     return q;
 }
 
-// LDE of a coefficient vector (len N) onto the coset 7*H_{4N}, natural order
+// LDE of a coefficient vector (len N) onto the coset 7*H_{4N}, natural order.  As bellman's
+// bitreversed_lde_using_bitreversed_ntt(factor = 4) does, this is 4 coset NTTs of size N (shift 7*w_4N^s fills the
+// positions 4j + s), not one zero-padded size-4N transform.
 static hvec<Fr> lde4(const hvec<Fr>& coeffs, int threads) {
-    hvec<Fr> v(coeffs.size() * 4, Fr::zero());
-    std::copy(coeffs.begin(), coeffs.end(), v.begin());
-    coset_fft(v, threads);
+    const size_t N = coeffs.size();
+    const int log_n = log2_floor(N);
+    hvec<Fr> v(N * 4);
+    const Fr w4 = omega_for(log_n + 2), g7 = Fr::from_u64(COSET_GEN), wn = omega_for(log_n);
+    hvec<Fr> t(N);
+    for (int s = 0; s < 4; ++s) {
+        std::copy(coeffs.begin(), coeffs.end(), t.begin());
+        distribute_powers(t.data(), N, g7 * w4.pow_u64(s), threads);
+        best_fft(t.data(), N, wn, log_n, threads);
+        parallel_chunks(N, threads, [&](size_t b, size_t e, int) { for (size_t j = b; j < e; ++j) v[4 * j + s] = t[j]; });
+    }
     return v;
+}
+
+// Polynomial<Values>::batch_inversion: every Worker chunk runs Montgomery's trick on its own range
+static void batch_inverse_par(Fr* a, size_t n, int threads) {
+    parallel_chunks(n, threads, [&](size_t b, size_t e, int) { batch_inverse(a + b, e - b); });
+}
+// calculate_shifted_grand_product: z[0] = 1, z[j+1] = z[j] * f[j]; per-chunk products, serial spine, per-chunk fill
+static void shifted_grand_product_par(const Fr* f, Fr* z, size_t n, int threads) {
+    if (n == 0) return;
+    if (threads < 1) threads = 1;
+    const size_t m = n - 1;  // factors used
+    const size_t chunk = (m + threads - 1) / threads;
+    const size_t nchunks = chunk ? (m + chunk - 1) / chunk : 0;
+    hvec<Fr> part(nchunks + 1, Fr::one());
+    parallel_chunks(m, threads, [&](size_t b, size_t e, int tid) {
+        Fr acc = Fr::one();
+        for (size_t j = b; j < e; ++j) acc *= f[j];
+        part[tid + 1] = acc;
+    });
+    for (size_t c = 1; c <= nchunks; ++c) part[c] = part[c - 1] * part[c];
+    z[0] = Fr::one();
+    parallel_chunks(m, threads, [&](size_t b, size_t e, int tid) {
+        Fr acc = part[tid];
+        for (size_t j = b; j < e; ++j) { acc *= f[j]; z[j + 1] = acc; }
+    });
 }
 
 struct SetupPolys {
@@ -472,6 +568,15 @@ void orc_g1_mul(const uint64_t* xy, const uint64_t* k, uint64_t* out) {
     hvec<G1Affine> b = load_points(xy, 1, 1);
     store_point(G1::from_affine(b[0]).mul(k).to_affine(), out);
 }
+// out[i] = k[i] * P for n canonical scalars (plain double-and-add per scalar; the closed-form check of the EC inverse FFT)
+void orc_g1_mul_fixed(const uint64_t* xy, const uint64_t* k, uint64_t n, uint64_t* out, int threads) {
+    init_fields();
+    hvec<G1Affine> b = load_points(xy, 1, 1);
+    const G1 P = G1::from_affine(b[0]);
+    parallel_chunks(n, threads, [&](size_t lo, size_t hi, int) {
+        for (size_t i = lo; i < hi; ++i) store_point(P.mul(k + 4 * i).to_affine(), out + 8 * i);
+    });
+}
 void orc_g1_add(const uint64_t* p, const uint64_t* q, uint64_t* out) {
     init_fields();
     hvec<G1Affine> a = load_points(p, 1, 1), b = load_points(q, 1, 1);
@@ -560,7 +665,7 @@ void orc_setup_commitments(const orc_assembly* as, const uint64_t* srs, uint64_t
 // Writes proof.bin bytes to proof_out (capacity >= 16 + 32*num_inputs + 1096) and returns the
 // length, or a negative error code (-1: gate identity unsatisfied, -2: quotient not a polynomial).
 // challenges_out (optional): beta,gamma,alpha,zeta,v canonical LE [5][4].
-static double g_last_setup_s = 0, g_last_prove_s = 0;
+static double g_last_setup_s = 0, g_last_prove_s = 0, g_last_setup_lde_s = 0;
 // seconds spent by the last orc_prove in (a) rebuilding the setup polynomials, which the reference does once in
 // prepare_setup_for_prover (src/plonk.rs:104), and (b) everything SetupForProver::prove does per call
 // Polynomial primitives of bellman restated one by one (checkers for pk_poly_*): op 0 evaluate_at (Horner), 1 divide_single
@@ -584,7 +689,9 @@ void orc_poly_op(int op, const uint64_t* in, uint64_t n, const uint64_t* z, uint
     }
 }
 
-void orc_last_timings(double* out) { out[0] = g_last_setup_s; out[1] = g_last_prove_s; }
+// [0] setup polynomials, [1] SetupForProver::prove as the reference runs it, [2] the part of [1] spent on the 11 LDEs of
+// the setup polynomials (recomputed per call by the reference: precomputations = None, src/plonk.rs:156)
+void orc_last_timings(double* out) { out[0] = g_last_setup_s; out[1] = g_last_prove_s; out[2] = g_last_setup_lde_s; }
 
 int64_t orc_prove(const orc_assembly* as, const uint64_t* srs, uint8_t* proof_out, uint64_t* challenges_out, int threads) {
     init_fields();
@@ -606,18 +713,24 @@ int64_t orc_prove(const orc_assembly* as, const uint64_t* srs, uint8_t* proof_ou
     hvec<Fr> wv[4];
     for (int c = 0; c < 4; ++c) {
         wv[c].resize(N);
-        for (size_t r = 0; r < N; ++r) wv[c][r] = vars[as->wire_idx[(size_t)c * N + r]];
+        parallel_chunks(N, threads, [&](size_t b, size_t e, int) {
+            for (size_t r = b; r < e; ++r) wv[c][r] = vars[as->wire_idx[(size_t)c * N + r]];
+        });
     }
     hvec<Fr> selv[7];
     for (int s = 0; s < 7; ++s) selv[s] = load_frs(as->selectors + (size_t)s * N * 4, N, threads);
     hvec<Fr> pi_vals(N, Fr::zero());
     for (size_t i = 0; i < NI; ++i) pi_vals[i] = wv[0][i];
     // is_satisfied_using_one_shot_check (src/plonk.rs:137)
-    for (size_t r = 0; r + 1 < N; ++r) {
-        Fr g = selv[0][r] * wv[0][r] + selv[1][r] * wv[1][r] + selv[2][r] * wv[2][r] + selv[3][r] * wv[3][r] +
-               selv[4][r] * wv[0][r] * wv[1][r] + selv[5][r] + selv[6][r] * wv[3][r + 1] + pi_vals[r];
-        if (!g.is_zero()) return -1;
-    }
+    std::atomic<int> unsat{0};
+    parallel_chunks(N - 1, threads, [&](size_t b, size_t e, int) {
+        for (size_t r = b; r < e; ++r) {
+            Fr g = selv[0][r] * wv[0][r] + selv[1][r] * wv[1][r] + selv[2][r] * wv[2][r] + selv[3][r] * wv[3][r] +
+                   selv[4][r] * wv[0][r] * wv[1][r] + selv[5][r] + selv[6][r] * wv[3][r + 1] + pi_vals[r];
+            if (!g.is_zero()) unsat = 1;
+        }
+    });
+    if (unsat) return -1;
 
     Transcript tr;
     for (size_t i = 0; i < NI; ++i) tr.update_fr(pi_vals[i]);
@@ -647,10 +760,10 @@ int64_t orc_prove(const orc_assembly* as, const uint64_t* srs, uint8_t* proof_ou
             num[j] = nn; den[j] = dd;
         }
     });
-    batch_inverse(den.data(), N);
+    batch_inverse_par(den.data(), N, threads);
+    parallel_chunks(N, threads, [&](size_t b, size_t e, int) { for (size_t j = b; j < e; ++j) num[j] *= den[j]; });
     hvec<Fr> zv(N);
-    zv[0] = Fr::one();
-    for (size_t j = 0; j + 1 < N; ++j) zv[j + 1] = zv[j] * num[j] * den[j];
+    shifted_grand_product_par(num.data(), zv.data(), N, threads);
     hvec<Fr> zp = zv;
     ifft(zp, threads);
     G1Affine Cz = commit(zp, bases.data(), threads);
@@ -661,8 +774,10 @@ int64_t orc_prove(const orc_assembly* as, const uint64_t* srs, uint8_t* proof_ou
     const size_t M = 4 * N;
     hvec<Fr> lw[4], lsel[7], lsig[4];
     for (int c = 0; c < 4; ++c) lw[c] = lde4(w[c], threads);
+    auto t_lde0 = std::chrono::steady_clock::now();
     for (int s = 0; s < 7; ++s) lsel[s] = lde4(sp.sel[s], threads);
     for (int c = 0; c < 4; ++c) lsig[c] = lde4(sp.sigma[c], threads);
+    g_last_setup_lde_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_lde0).count();
     hvec<Fr> lz = lde4(zp, threads);
     hvec<Fr> pi_poly = pi_vals;
     ifft(pi_poly, threads);

@@ -153,6 +153,15 @@ def g1_mul(point, k):
     return out
 
 
+def g1_mul_fixed(point, scalars, threads=1):
+    """[k * P for k in scalars] -> (n, 8)"""
+    p = np.ascontiguousarray(point, dtype=np.uint64).reshape(8)
+    kk = ints_to_limbs([int(k) % R_MOD for k in scalars])
+    out = np.zeros((kk.shape[0], 8), dtype=np.uint64)
+    lib().orc_g1_mul_fixed(_p(p), _p(kk), ctypes.c_uint64(kk.shape[0]), _p(out), threads)
+    return out
+
+
 def g1_add(p, q):
     a = np.ascontiguousarray(p, dtype=np.uint64).reshape(8)
     b = np.ascontiguousarray(q, dtype=np.uint64).reshape(8)
@@ -247,8 +256,9 @@ def verify_trapdoor(proof_bytes: bytes, vk_commitments, tau=42) -> bool:
 
 
 def last_timings():
-    """(setup_s, prove_s) of the last prove() call: setup polynomials (reference: once, in prepare_setup_for_prover)
-    vs. the per-call work of SetupForProver::prove"""
-    out = (ctypes.c_double * 2)()
+    """(setup_s, prove_s, setup_lde_s) of the last prove() call: setup polynomials (reference: once, in
+    prepare_setup_for_prover), the per-call work of SetupForProver::prove, and the share of the latter spent on the 11
+    setup-polynomial LDEs that the reference recomputes on every call (precomputations = None, src/plonk.rs:156)"""
+    out = (ctypes.c_double * 3)()
     lib().orc_last_timings(out)
-    return out[0], out[1]
+    return out[0], out[1], out[2]

@@ -152,6 +152,7 @@ class Context:
         self._h = h
         self.device = device
         self.srs_size = 0
+        self.srs_tag = None  # which key is resident (plonk.SetupForProver._ensure_srs); None after a direct load
         self._children = weakref.WeakSet()  # device-side objects that must be released before the context
 
     def close(self):
@@ -172,10 +173,12 @@ class Context:
             raise SynthesisError(rc, self._lib.pk_last_error(self._h).decode())
 
     # ---- SRS
-    def srs_load_g1(self, bases, window_bits=0):
+    def srs_load_g1(self, bases, window_bits=0, tag=None):
         b = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
+        self.srs_tag = None
         self._check(self._lib.pk_srs_load_g1(self._h, _ptr(b), b.shape[0], window_bits))
         self.srs_size = b.shape[0]
+        self.srs_tag = tag
 
     def srs_gen(self, n, tau=42):
         out = np.zeros((n, 8), dtype=np.uint64)

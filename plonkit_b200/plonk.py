@@ -22,7 +22,7 @@ from . import _lib
 from ._lib import Context, SynthesisError
 from .bn254 import limbs_to_ints
 from .circuit import AUX_OFFSET, Assembly, CircomCircuit, analyse, is_satisfied, synthesize  # noqa: F401  (re-exported)
-from .reader import Crs, Proof, VerificationKey
+from .reader import CRS_42_G2, Crs, Proof, VerificationKey
 
 SETUP_MIN_POW2 = 10  # src/plonk.rs:26
 SETUP_MAX_POW2 = 26  # src/plonk.rs:27
@@ -37,11 +37,11 @@ def default_context(device=0) -> Context:
 
 
 def gen_key_monomial_form(power: int, ctx: Context = None) -> Crs:
-    """Crs::crs_42(1 << power): [42^i] G (src/plonk.rs:30-48).  The G2 part (verify-side only) is left empty."""
+    """Crs::crs_42(1 << power): [42^i] G plus the two G2 elements [1]G2, [42]G2 (src/plonk.rs:30-48)."""
     if not (SETUP_MIN_POW2 <= power <= SETUP_MAX_POW2):
         raise ValueError("setup power of two is not in the correct range")
     ctx = ctx or default_context()
-    return Crs(ctx.srs_gen(1 << power, 42), b"", "monomial")
+    return Crs(ctx.srs_gen(1 << power, 42), CRS_42_G2, "monomial")
 
 
 def _as_assembly(circuit) -> Assembly:
@@ -91,11 +91,11 @@ class SetupForProver:
         return self
 
     def _ensure_srs(self):
-        # the context keeps one SRS resident; reload only if another key was loaded in between
-        tag = (id(self.key_monomial_form), self.n)
-        if getattr(self.ctx, "_srs_tag", None) != tag:
-            self.ctx.srs_load_g1(self.key_monomial_form.g1_bases[:self.n])
-            self.ctx._srs_tag = tag
+        # the context keeps one SRS resident; reload only if another key was loaded in between.  The tag is a token
+        # owned by the Crs object (never reused, unlike id()) and Context.srs_load_g1 clears it on every direct load.
+        tag = (self.key_monomial_form.token, self.n)
+        if self.ctx.srs_tag != tag:
+            self.ctx.srs_load_g1(self.key_monomial_form.g1_bases[:self.n], tag=tag)
 
     def close(self):
         if getattr(self, "_h", None):

@@ -5,6 +5,7 @@ Mirrors src/reader.rs (loaders) and the bellman `Crs::{read,write}`, `Proof::{re
 G1 uncompressed = x || y with infinity = 0x40 followed by 63 zero bytes.  In memory everything is
 little-endian u64 limbs (see bn254.py).
 """
+import itertools
 import json
 import struct
 from dataclasses import dataclass, field
@@ -42,12 +43,37 @@ def g1_to_bytes(pts) -> bytes:
 
 
 # ---------------------------------------------------------------- SRS (.key): Crs::read / Crs::write  (App. B.1)
+# The two G2 elements of Crs::crs_42 (src/plonk.rs:41,47): [1]G2 and [42]G2, 128 B each (x.c1 | x.c0 | y.c1 | y.c0, big
+# endian), exactly as keys/setup/setup_2^10.key carries them.  G2 arithmetic (verify side) is outside this repository,
+# and the trapdoor of crs_42 is the constant 42, so the encodings are constants.
+CRS_42_G2 = bytes.fromhex(
+    "198e9393920d483a7260bfb731fb5d25f1aa493335a9e71297e485b7aef312c2"
+    "1800deef121f1e76426a00665e5c4479674322d4f75edadd46debd5cd992f6ed"
+    "090689d0585ff075ec9e99ad690c3395bc4b313370b38ef355acdadcd122975b"
+    "12c85ea5db8c6deb4aab71808dcb408fe3d1e7690c43d37b4ce6cc0166fa7daa"
+    "12740934ba9615b77b6a49b06fcce83ce90d67b1d0e2a530069e3a7306569a91"
+    "116da8c89a0d090f3d8644ada33a5f1c8013ba7204aeca62d66d931b99afe6e7"
+    "25222d9816e5f86b4a7dedd00d04acc5c979c18bd22b834ea8c6d07c0ba441db"
+    "076441042e77b6309644b56251f059cf14befc72ac8a6157d30924e58dc4c172")
+
+
+_crs_tokens = itertools.count(1)
+
+
+def _read_exact(f, n: int, what: str) -> bytes:
+    b = f.read(n)
+    if len(b) != n:
+        raise ValueError("truncated file: %s needs %d bytes, got %d" % (what, n, len(b)))
+    return b
+
+
 @dataclass
 class Crs:
     """bellman `Crs<Bn256, CrsForMonomialForm | CrsForLagrangeForm>`: g1 bases + the two G2 elements (kept raw)."""
     g1_bases: np.ndarray            # (n, 8) uint64 canonical LE affine
     g2_raw: bytes = b""             # n_g2 * 128 bytes exactly as in the file (verify-side only)
     form: str = "monomial"
+    token: int = field(default_factory=lambda: next(_crs_tokens), compare=False, repr=False)  # identity of this key
 
     @property
     def size(self):
@@ -55,10 +81,12 @@ class Crs:
 
     @staticmethod
     def read(f) -> "Crs":
-        n = struct.unpack(">Q", f.read(8))[0]
-        g1 = g1_from_bytes(f.read(64 * n), n)
-        n2 = struct.unpack(">Q", f.read(8))[0]
-        g2 = f.read(128 * n2)
+        n = struct.unpack(">Q", _read_exact(f, 8, "G1 count"))[0]
+        g1 = g1_from_bytes(_read_exact(f, 64 * n, "G1 bases"), n)
+        n2 = struct.unpack(">Q", _read_exact(f, 8, "G2 count"))[0]
+        if n2 != 2:
+            raise ValueError("a Crs file carries exactly two G2 elements, this one declares %d" % n2)
+        g2 = _read_exact(f, 128 * n2, "G2 bases")
         return Crs(g1, g2)
 
     def write(self, f):
@@ -193,7 +221,7 @@ class VerificationKey:
         perm = g1_from_bytes(f.read(64 * 4), 4)
         assert u64() == 3
         nr = limbs_to_ints(be_bytes_to_limbs(f.read(96), 3))
-        g2 = f.read(256)
+        g2 = _read_exact(f, 256, "G2 elements of the verification key")
         return VerificationKey(n, ni, sel, nxt, perm, nr, g2)
 
 

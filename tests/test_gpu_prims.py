@@ -49,23 +49,23 @@ def test_ntt_golden_vector_and_edge_inputs(ctx, orc):
         ctx.ntt(np.zeros((3, 4), dtype=np.uint64))                      # not a power of two
 
 
-def test_ntt_large_round_trip_and_linearity(ctx):
+def test_ntt_and_lde4_at_bench_size_2pow20_match_oracle(ctx, orc):
+    """BASELINE configs[1] size: forward / inverse / coset NTT and the x4 LDE of 2^20 elements == oracle, element for
+    element; plus the round trip."""
     log_n = 20
     x = synth.random_field_elements(1 << log_n, seed=1)
     y = ctx.ntt(x)
+    assert (y == orc.ntt(x, threads=16)).all()
     assert (ctx.ntt(y, inverse=True) == x).all()
-    # linearity at full size: NTT(x + x2) == NTT(x) + NTT(x2), checked on a sample of positions
-    x2 = synth.random_field_elements(1 << log_n, seed=2)
-    idx = np.arange(0, 1 << log_n, 4099)
-    xs = limbs_to_ints(x[idx])
-    s = ints_to_limbs([(a + b) % R_MOD for a, b in zip(limbs_to_ints(x), limbs_to_ints(x2))]) if False else None
-    y2 = ctx.ntt(x2)
-    xi, x2i = limbs_to_ints(x[:4096]), limbs_to_ints(x2[:4096])
-    small_sum = ints_to_limbs([(a + b) % R_MOD for a, b in zip(xi, x2i)])
-    ys = ctx.ntt(small_sum)
-    ya, yb = limbs_to_ints(ctx.ntt(x[:4096])), limbs_to_ints(ctx.ntt(x2[:4096]))
-    assert limbs_to_ints(ys) == [(a + b) % R_MOD for a, b in zip(ya, yb)]
-    assert len(xs) == len(idx) and y2.shape == y.shape
+    assert (ctx.ntt(x, inverse=True, coset=True) == orc.ntt(x, inverse=True, coset=True, threads=16)).all()
+    ref = orc.lde4(x, threads=16)
+    assert (ctx.lde4(x) == ref).all()
+    br = ctx.lde4(x, bitreversed=True)          # the order the prover keeps (bellman's bitreversed LDE)
+    idx = np.arange(4 << log_n, dtype=np.uint32)
+    rev = np.zeros_like(idx)
+    for b in range(log_n + 2):
+        rev |= ((idx >> np.uint32(b)) & np.uint32(1)) << np.uint32(log_n + 1 - b)
+    assert (br[rev] == ref).all()
 
 
 @pytest.mark.parametrize("log_n", [1, 3, 8, 12])
@@ -156,6 +156,50 @@ def test_msm_2pow16_uniform_and_skewed(ctx, orc):
     assert (ctx.msm_g1(s2) == orc.msm(s2, b2, threads=8)).all()
 
 
+@pytest.fixture(scope="module")
+def srs20(ctx, orc):
+    """[42^i]G, i < 2^20, made on the device and spot-checked against the oracle: the first 2^10 points against the
+    oracle's generator, 64 random ones against a fixed-base multiplication G * (42^i mod r)."""
+    n = 1 << 20
+    srs = ctx.srs_gen(n, 42)
+    assert (srs[:1024] == orc.srs_gen(1024, 42, threads=8)).all()
+    g = ints_to_limbs([1, 2]).reshape(8)
+    rng = np.random.default_rng(7)
+    for i in rng.integers(1024, n, size=64):
+        assert (srs[i] == orc.g1_mul(g, pow(42, int(i), R_MOD))).all(), i
+    return srs
+
+
+@pytest.mark.parametrize("log_n", [18, 20])
+def test_msm_at_bench_size_default_window_matches_oracle(ctx, orc, srs20, log_n):
+    """The MSM configuration bench.py times: N = 2^20 bases, default window plan (c = 20, 13 windows), and 2^18
+    (c = 18); uniform scalars and the witness-like mix of SURVEY 8(d) (40 % zero, 10 % one, 50 % uniform)."""
+    n = 1 << log_n
+    _load(ctx, srs20[:n])
+    s = synth.random_field_elements(n, seed=50 + log_n)
+    assert (ctx.msm_g1(s) == orc.msm(s, srs20[:n], threads=16)).all()
+    w = s.copy()
+    sel = np.random.default_rng(log_n).random(n)
+    w[sel < 0.4] = 0
+    w[(sel >= 0.4) & (sel < 0.5)] = ints_to_limbs([1])[0]
+    assert (ctx.msm_g1(w) == orc.msm(w, srs20[:n], threads=16)).all()
+
+
+@pytest.mark.parametrize("window_bits", [21, 22])
+def test_msm_wide_windows_with_a_three_set_tail(ctx, orc, simple_key, window_bits):
+    """Explicit window_bits >= 21 with an 11-commitment batch (4 + 4 + 3 sets, what make_verification_key issues): the
+    3-set tail has 3 * 2^(c-1) buckets, which is not a power of two."""
+    from plonkit_b200 import plonk, reader
+    asm = synth.poseidon_chain_assembly(10)
+    key = reader.Crs(simple_key.g1_bases)
+    ctx.srs_load_g1(key.g1_bases, window_bits, tag=(key.token, asm.n))
+    setup = plonk.SetupForProver.prepare_setup_for_prover(asm, key, None, ctx=ctx)
+    com = orc.setup_commitments(asm.n, asm.num_inputs, asm.wire_idx, asm.selectors, key.g1_bases, nvars=asm.nvars, threads=8)
+    from conftest import vk_commitments
+    assert (vk_commitments(setup.make_verification_key()) == com).all()
+    setup.close()
+
+
 def test_srs_generator_matches_reference_key(ctx, simple_key):
     """Crs::crs_42 (src/plonk.rs:41,47) == keys/setup/setup_2^10.key"""
     assert (ctx.srs_gen(1024, 42) == simple_key.g1_bases).all()
@@ -167,6 +211,48 @@ def test_ec_intt_matches_oracle(ctx, orc, simple_key):
     for log_n in (0, 1, 4, 7):
         got = ctx.ec_intt_g1(log_n)
         assert (got == orc.ec_intt(simple_key.g1_bases[: 1 << log_n], threads=8)).all(), log_n
+
+
+def test_ec_intt_2pow12_full_compare(ctx, orc, srs20):
+    """Crs::from_powers at 2^12: every output point == the oracle's EC inverse FFT (the oracle needs ~2 s here)."""
+    _load(ctx, srs20[: 1 << 12])
+    assert (ctx.ec_intt_g1(12) == orc.ec_intt(srs20[: 1 << 12], threads=16)).all()
+
+
+@pytest.mark.parametrize("log_n,samples", [(16, 1 << 16), (20, 1 << 10)])
+def test_ec_intt_outputs_are_the_lagrange_basis_in_the_exponent(ctx, orc, srs20, log_n, samples):
+    """BASELINE configs[3] check (SURVEY 8d cfg 4): out[i] == L_i(42) * G with L_i(tau) = w^i (tau^N - 1) / (N (tau - w^i))
+    computed in Fr with Python integers and one fixed-base multiplication by the oracle.  2^16: EVERY index (full
+    compare; the oracle's own EC inverse FFT would need a minute here, the closed form is exact and independent of it);
+    2^20: 2^10 random indices of the full-size run."""
+    n = 1 << log_n
+    _load(ctx, srs20[:n])
+    out = ctx.ec_intt_g1(log_n)
+    g = ints_to_limbs([1, 2]).reshape(8)
+    tau = 42
+    w = orc.omega(log_n)
+    zh = (pow(tau, n, R_MOD) - 1) % R_MOD
+    ninv = pow(n, R_MOD - 2, R_MOD)
+    idx = np.arange(n) if samples >= n else np.unique(np.random.default_rng(log_n).integers(0, n, size=samples))
+    # batch-invert (tau - w^i) with Montgomery's trick in Python integers
+    wi = [pow(w, int(i), R_MOD) for i in idx] if samples < n else None
+    if wi is None:
+        wi, x = [], 1
+        for _ in range(n):
+            wi.append(x)
+            x = x * w % R_MOD
+    den = [(tau - v) % R_MOD for v in wi]
+    pre, acc = [], 1
+    for d in den:
+        pre.append(acc)
+        acc = acc * d % R_MOD
+    inv = pow(acc, R_MOD - 2, R_MOD)
+    scal = [0] * len(den)
+    for k in range(len(den) - 1, -1, -1):
+        scal[k] = wi[k] * zh % R_MOD * ninv % R_MOD * (inv * pre[k] % R_MOD) % R_MOD
+        inv = inv * den[k] % R_MOD
+    exp = orc.g1_mul_fixed(g, scal, threads=16)
+    assert (out[idx] == exp).all()
 
 
 @pytest.mark.parametrize("n", [1, 2, 255, 4096, 100003, 1 << 20])

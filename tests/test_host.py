@@ -66,6 +66,17 @@ def test_key_proof_vk_round_trip_reference_files(simple_key):
     vraw = open(os.path.join(SIMPLE, "vk.bin"), "rb").read()
     vk = reader.load_verification_key(os.path.join(SIMPLE, "vk.bin"))
     assert vk.to_bytes() == vraw and vk.non_residues == [5, 7, 10]
+    # Crs::crs_42's G2 part is a constant ([1]G2, [42]G2): the embedded copy is the reference key's, and so is the vk's
+    assert reader.CRS_42_G2 == raw[-256:] == vraw[-256:]
+    # truncated files and foreign G2 counts are rejected, not silently accepted
+    with pytest.raises(ValueError, match="truncated"):
+        reader.Crs.read(io.BytesIO(raw[:-1]))
+    with pytest.raises(ValueError, match="truncated"):
+        reader.VerificationKey.read(io.BytesIO(vraw[:-256]))
+    with pytest.raises(ValueError, match="two G2"):
+        reader.Crs.read(io.BytesIO(raw[:-264] + struct.pack(">Q", 0)))
+    # every Crs object has its own never-reused token (what SetupForProver uses to decide whether the resident SRS is current)
+    assert reader.Crs(simple_key.g1_bases).token != reader.Crs(simple_key.g1_bases).token
 
 
 def _wtns(vals, version=2, prime=None):
