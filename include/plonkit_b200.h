@@ -23,6 +23,8 @@ extern "C" {
 
 typedef struct pk_ctx pk_ctx;
 typedef struct pk_setup pk_setup;
+typedef struct pk_dist_setup pk_dist_setup;
+typedef struct pk_comm_group pk_comm_group;
 
 /* status codes; the shim maps them onto bellman's SynthesisError variants */
 enum {
@@ -142,6 +144,30 @@ int pk_witness_upload(pk_ctx* ctx, pk_setup* setup, const uint64_t* var_values, 
 /* SetupForProver::prove(circuit, "keccak") with the monomial-form SRS (src/plonk.rs:132-176): input values of the
  * public inputs are written to inputs_out[num_inputs][4].  var_values may be NULL to reuse the uploaded witness. */
 int pk_prove(pk_ctx* ctx, pk_setup* setup, const uint64_t* var_values, uint64_t nvars, pk_proof* proof, uint64_t* inputs_out);
+
+/* ---- one proof sharded over the GPUs of a node (BASELINE.json configs[2]) ---------------- */
+/* The reference runs one Worker (host threads) per call; here ONE SetupForProver::prove is cut across 1, 2, 4 or 8
+ * ranks, one context per GPU: commitments by base chunk (every rank loads ITS chunk of the key with pk_srs_load_g1:
+ * bases [rank n/world, (rank+1) n/world)), the quotient by coset, one all-to-all inside the size-4n inverse NTT.  The
+ * calls below are COLLECTIVE: every rank of the communicator makes the same call with the same circuit / witness and
+ * every rank receives the same proof (bytes identical to pk_prove's).
+ *
+ * Transports: pk_comm_attach_nccl — one process per GPU (torchrun); rank 0 makes the id with pk_comm_nccl_unique_id and
+ * the launcher broadcasts it.  pk_comm_attach_group — the ranks are threads of one process (contexts on one or several
+ * devices; direct peer copies).  A rank that fails aborts the communicator: its peers return an error from their next
+ * collective instead of hanging. */
+int pk_comm_group_create(int world, pk_comm_group** out);
+void pk_comm_group_destroy(pk_comm_group* group);
+int pk_comm_attach_group(pk_ctx* ctx, pk_comm_group* group, int rank);
+int pk_comm_nccl_unique_id(uint8_t out[128]);
+int pk_comm_attach_nccl(pk_ctx* ctx, const uint8_t unique_id[128], int rank, int world);
+/* prepare_setup_for_prover / make_verification_key / prove, sharded (same arguments as the pk_setup_* / pk_prove calls) */
+int pk_dist_setup_create(pk_ctx* ctx, const pk_assembly* assembly, pk_dist_setup** out);
+void pk_dist_setup_destroy(pk_dist_setup* setup);
+int pk_dist_setup_commitments(pk_ctx* ctx, pk_dist_setup* setup, uint64_t out_xy[11][8]);
+int pk_dist_witness_upload(pk_ctx* ctx, pk_dist_setup* setup, const uint64_t* var_values, uint64_t nvars);
+int pk_dist_prove(pk_ctx* ctx, pk_dist_setup* setup, const uint64_t* var_values, uint64_t nvars, pk_proof* proof,
+                  uint64_t* inputs_out);
 
 /* ---- measurement hooks --------------------------------------------------------------------------------- */
 typedef struct pk_profile {

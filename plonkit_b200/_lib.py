@@ -30,6 +30,8 @@ EXPORTS = [
     "pk_bench_fieldmul", "pk_timer_begin", "pk_timer_end", "pk_g1_sum", "pk_dev_fr_convert", "pk_dev_ntt_rows",
     "pk_dev_twiddle", "pk_poly_evaluate_at", "pk_poly_divide_by_linear", "pk_poly_shifted_grand_product",
     "pk_poly_batch_inversion", "pk_dev_ec_from_affine", "pk_dev_ec_ntt_rows", "pk_dev_ec_twiddle", "pk_dev_ec_to_affine",
+    "pk_comm_group_create", "pk_comm_group_destroy", "pk_comm_attach_group", "pk_comm_nccl_unique_id", "pk_comm_attach_nccl",
+    "pk_dist_setup_create", "pk_dist_setup_destroy", "pk_dist_setup_commitments", "pk_dist_witness_upload", "pk_dist_prove",
 ]
 
 
@@ -130,6 +132,18 @@ def load():
     lib.pk_poly_divide_by_linear.argtypes = [vp, vp, u64, vp, vp]
     lib.pk_poly_shifted_grand_product.argtypes = [vp, vp, u64, vp]
     lib.pk_poly_batch_inversion.argtypes = [vp, vp, u64]
+    lib.pk_comm_group_create.argtypes = [i32, ctypes.POINTER(vp)]
+    lib.pk_comm_group_destroy.argtypes = [vp]
+    lib.pk_comm_group_destroy.restype = None
+    lib.pk_comm_attach_group.argtypes = [vp, vp, i32]
+    lib.pk_comm_nccl_unique_id.argtypes = [vp]
+    lib.pk_comm_attach_nccl.argtypes = [vp, vp, i32, i32]
+    lib.pk_dist_setup_create.argtypes = [vp, ctypes.POINTER(PkAssembly), ctypes.POINTER(vp)]
+    lib.pk_dist_setup_destroy.argtypes = [vp]
+    lib.pk_dist_setup_destroy.restype = None
+    lib.pk_dist_setup_commitments.argtypes = [vp, vp, vp]
+    lib.pk_dist_witness_upload.argtypes = [vp, vp, vp, u64]
+    lib.pk_dist_prove.argtypes = [vp, vp, vp, u64, ctypes.POINTER(PkProof), vp]
     lib.pk_timer_begin.argtypes = [vp]
     lib.pk_timer_end.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     _lib = lib
@@ -184,6 +198,16 @@ class Context:
         out = np.zeros((n, 8), dtype=np.uint64)
         self._check(self._lib.pk_srs_gen(self._h, n, tau, _ptr(out)))
         return out
+
+    # ---- communicator of the sharded prover (this context = one rank)
+    def attach_group(self, group, rank):
+        self._check(self._lib.pk_comm_attach_group(self._h, group._h, rank))
+        self.rank, self.world = rank, group.world
+
+    def attach_nccl(self, unique_id: bytes, rank, world):
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        self._check(self._lib.pk_comm_attach_nccl(self._h, buf, rank, world))
+        self.rank, self.world = rank, world
 
     # ---- primitives
     def ntt(self, data, inverse=False, coset=False, fmt=FMT_CANONICAL):
@@ -302,6 +326,31 @@ class Context:
         g = ctypes.c_double()
         self._check(self._lib.pk_bench_fieldmul(self._h, which, ctypes.byref(g)))
         return g.value
+
+
+class CommGroup:
+    """In-process communicator (pk_comm_group): the ranks of a sharded prover as threads of this process."""
+
+    def __init__(self, world):
+        self._lib = load()
+        h = ctypes.c_void_p()
+        rc = self._lib.pk_comm_group_create(world, ctypes.byref(h))
+        if rc != PK_OK:
+            raise SynthesisError(rc, "pk_comm_group_create(%d)" % world)
+        self._h, self.world = h, world
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pk_comm_group_destroy(self._h)
+            self._h = None
+
+
+def nccl_unique_id() -> bytes:
+    buf = ctypes.create_string_buffer(128)
+    rc = load().pk_comm_nccl_unique_id(buf)
+    if rc != PK_OK:
+        raise SynthesisError(rc, "pk_comm_nccl_unique_id (is libnccl.so.2 loadable?)")
+    return buf.raw
 
 
 def g1_sum(points) -> np.ndarray:

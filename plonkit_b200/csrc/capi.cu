@@ -2,11 +2,14 @@
 // and device memory, error translation.  No exception crosses the boundary.
 #include <mutex>
 
+#include "comm.cuh"
 #include "msm.cuh"
 #include "ntt.cuh"
 #include "poly.cuh"
 
 using namespace pk;
+
+struct pk_comm_group { pk::LocalGroup g; explicit pk_comm_group(int w) : g(w) {} };
 
 namespace pk {
 void setup_create(pk_ctx* ctx, const pk_assembly* as, pk_setup** out);
@@ -20,6 +23,11 @@ void ec_dev_ntt_rows(pk_ctx* ctx, g1_xyzz_t* data, int log_len, size_t rows, boo
 void ec_dev_twiddle_rows(pk_ctx* ctx, g1_xyzz_t* a, size_t rows, size_t cols, int log_total, size_t row0, bool inverse);
 void ec_dev_to_affine(pk_ctx* ctx, const g1_xyzz_t* in, g1_affine_t* out_canonical, size_t n, int log_scale);
 void srs_gen(pk_ctx* ctx, uint64_t n, uint64_t tau, uint64_t* out_xy);
+void dist_setup_create(pk_ctx* ctx, const pk_assembly* as, pk_dist_setup** out);
+void dist_setup_commitments(pk_ctx* ctx, pk_dist_setup* s, uint64_t out_xy[11][8]);
+void dist_witness_upload(pk_ctx* ctx, pk_dist_setup* s, const uint64_t* var_values, uint64_t nvars);
+void dist_prove(pk_ctx* ctx, pk_dist_setup* s, const uint64_t* var_values, uint64_t nvars, pk_proof* proof, uint64_t* inputs_out);
+void dist_setup_free(pk_dist_setup* s);
 
 struct CtxExtras { PolyScratch poly; };
 static std::map<pk_ctx*, CtxExtras*> g_extras;
@@ -96,6 +104,7 @@ void pk_destroy(pk_ctx* ctx) {
     profile_resolve(ctx);
     delete ctx->srs;
     delete ctx->domains;
+    delete ctx->comm;
     {
         std::lock_guard<std::mutex> lk(g_mu);
         auto it = g_extras.find(ctx);
@@ -377,6 +386,83 @@ int pk_prove(pk_ctx* ctx, pk_setup* setup, const uint64_t* var_values, uint64_t 
     PK_REQUIRE(setup != nullptr, PK_ERR_INVALID, "null setup");
     prove(ctx, setup, var_values, nvars, proof, inputs_out);
     PK_API_END(ctx)
+}
+
+// ---------------------------------------------------------------- sharded prover (one proof over several GPUs)
+// A rank that fails tells its peers, so that they fail in their next collective instead of waiting for it forever.
+#define PK_DIST_API_END(ctx)                                              \
+        return PK_OK;                                                     \
+    } catch (const PkError& e) {                                          \
+        (ctx)->last_error = e.what();                                     \
+        cudaGetLastError();                                               \
+        if ((ctx)->comm) (ctx)->comm->abort();                            \
+        return e.code;                                                    \
+    } catch (const std::exception& e) {                                   \
+        (ctx)->last_error = e.what();                                     \
+        if ((ctx)->comm) (ctx)->comm->abort();                            \
+        return PK_ERR_INVALID;                                            \
+    } catch (...) {                                                       \
+        (ctx)->last_error = "unknown error";                              \
+        if ((ctx)->comm) (ctx)->comm->abort();                            \
+        return PK_ERR_INVALID;                                            \
+    }
+
+int pk_comm_group_create(int world, pk_comm_group** out) {
+    if (!out || world < 1 || world > 8) return PK_ERR_INVALID;
+    *out = new pk_comm_group(world);
+    return PK_OK;
+}
+void pk_comm_group_destroy(pk_comm_group* g) { delete g; }
+int pk_comm_attach_group(pk_ctx* ctx, pk_comm_group* group, int rank) {
+    PK_API_BEGIN(ctx)
+    PK_REQUIRE(group != nullptr, PK_ERR_INVALID, "null group");
+    PK_REQUIRE(ctx->comm == nullptr, PK_ERR_INVALID, "context already belongs to a communicator");
+    ctx->comm = make_local_comm(&group->g, rank, ctx->device);
+    PK_API_END(ctx)
+}
+int pk_comm_nccl_unique_id(uint8_t out[128]) {
+    if (!out) return PK_ERR_INVALID;
+    try {
+        nccl_unique_id(out);
+    } catch (...) {
+        return PK_ERR_CUDA;
+    }
+    return PK_OK;
+}
+int pk_comm_attach_nccl(pk_ctx* ctx, const uint8_t unique_id[128], int rank, int world) {
+    PK_API_BEGIN(ctx)
+    PK_REQUIRE(unique_id != nullptr, PK_ERR_INVALID, "null id");
+    PK_REQUIRE(ctx->comm == nullptr, PK_ERR_INVALID, "context already belongs to a communicator");
+    ctx->comm = make_nccl_comm(unique_id, rank, world);
+    PK_API_END(ctx)
+}
+int pk_dist_setup_create(pk_ctx* ctx, const pk_assembly* assembly, pk_dist_setup** out) {
+    PK_API_BEGIN(ctx)
+    if (ctx->comm) ctx->comm->begin();
+    dist_setup_create(ctx, assembly, out);
+    PK_DIST_API_END(ctx)
+}
+void pk_dist_setup_destroy(pk_dist_setup* setup) { dist_setup_free(setup); }
+int pk_dist_setup_commitments(pk_ctx* ctx, pk_dist_setup* setup, uint64_t out_xy[11][8]) {
+    PK_API_BEGIN(ctx)
+    PK_REQUIRE(setup != nullptr && out_xy != nullptr, PK_ERR_INVALID, "null argument");
+    if (ctx->comm) ctx->comm->begin();
+    dist_setup_commitments(ctx, setup, out_xy);
+    PK_DIST_API_END(ctx)
+}
+int pk_dist_witness_upload(pk_ctx* ctx, pk_dist_setup* setup, const uint64_t* var_values, uint64_t nvars) {
+    PK_API_BEGIN(ctx)
+    PK_REQUIRE(setup != nullptr, PK_ERR_INVALID, "null setup");
+    dist_witness_upload(ctx, setup, var_values, nvars);
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    PK_API_END(ctx)
+}
+int pk_dist_prove(pk_ctx* ctx, pk_dist_setup* setup, const uint64_t* var_values, uint64_t nvars, pk_proof* proof, uint64_t* inputs_out) {
+    PK_API_BEGIN(ctx)
+    PK_REQUIRE(setup != nullptr, PK_ERR_INVALID, "null setup");
+    if (ctx->comm) ctx->comm->begin();
+    dist_prove(ctx, setup, var_values, nvars, proof, inputs_out);
+    PK_DIST_API_END(ctx)
 }
 
 void pk_profile_enable(pk_ctx* ctx, int on) { if (ctx) ctx->prof.enabled = on != 0; }

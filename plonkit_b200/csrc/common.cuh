@@ -77,6 +77,7 @@ struct Profile {
 
 struct SrsTables;   // msm.cu
 struct DomainCache; // ntt.cu
+struct Comm;        // comm.cuh
 
 }  // namespace pk
 
@@ -88,6 +89,7 @@ struct pk_ctx {
     pk::Profile prof;
     pk::SrsTables* srs = nullptr;
     pk::DomainCache* domains = nullptr;
+    pk::Comm* comm = nullptr;          // set by pk_comm_attach_*: this context is one rank of a sharded prover
     // small pinned staging area for results (commitments, scalars)
     uint8_t* pinned = nullptr;
     size_t pinned_bytes = 0;

@@ -29,6 +29,8 @@
 //
 // Algorithmic HBM bytes: 96 B per (scalar, base) pair.  The kernels are bound by 32-bit integer
 // multiply throughput, not HBM: one mixed addition is 10 Montgomery products of ~130 IMAD.WIDE each.
+#include <memory>
+
 #include "msm.cuh"
 
 namespace pk {
@@ -79,9 +81,10 @@ static int pick_window_bits(uint64_t n) {
 
 // coarse bins hold 2^fine_bits buckets: small enough that one bin's entries (~6.6 K at N = 2^20) fit the fine sort's
 // shared-memory staging area, and at most 2^14 bins so the per-block bin counters of the coarse kernels fit too (128 KB)
-static int msm_fine_bits(int lg_total_buckets) {
-    int fb = lg_total_buckets < 8 ? lg_total_buckets : 8;
-    if (lg_total_buckets - fb > 14) fb = lg_total_buckets - 14;
+static int msm_fine_bits(size_t total_buckets) {
+    const int lg = ilog2(total_buckets);
+    int fb = lg < 8 ? lg : 8;
+    while (((total_buckets + (size_t(1) << fb) - 1) >> fb) > (size_t(1) << 14)) ++fb;  // a 3-set group is not a power of two
     return fb;
 }
 
@@ -95,8 +98,12 @@ static int max_batch_for(const SrsTables* s) {
 static void alloc_scratch(const SrsTables* s, MsmScratch& sc, int nb) {
     const size_t M = (size_t)s->n * s->W;
     const size_t NB = (size_t)nb * s->B;
-    const int fb = msm_fine_bits(ilog2(NB));
-    const size_t ncmax = 2 * (NB >> fb) + 2;  // a 3-set group has a coarser floor(log2) than the 4-set one it shares with
+    size_t ncmax = 2;
+    for (int k = 1; k <= nb; ++k) {  // every group size that may run on this scratch
+        const size_t nbk = (size_t)k * s->B;
+        const size_t nc = ((nbk + (size_t(1) << msm_fine_bits(nbk)) - 1) >> msm_fine_bits(nbk)) + 2;
+        if (nc > ncmax) ncmax = nc;
+    }
     sc.max_sets = nb;
     sc.coarse_count.alloc(ncmax);
     sc.coarse_offset.alloc(ncmax);
@@ -123,10 +130,12 @@ void srs_load(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits
     int W = (255 + c - 1) / c;
     PK_REQUIRE((uint64_t)W * n < (uint64_t(1) << 31), PK_ERR_DEGREE_TOO_LARGE, "window table index does not fit 31 bits");
     PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    // the old tables go first (two resident copies may not fit); the new ones are published only once every
+    // allocation and kernel has succeeded, so a failed load leaves "no SRS", never a half-built one
     delete ctx->srs;
     ctx->srs = nullptr;
-    SrsTables* s = new SrsTables();
-    ctx->srs = s;
+    std::unique_ptr<SrsTables> holder(new SrsTables());
+    SrsTables* s = holder.get();
     // Window widths: the 255 scalar bits (254 + one spare for the signed-digit carry) are split as evenly as possible
     // over W windows (e.g. c = 20: eight 20-bit and five 19-bit windows).  A plain "12 x 20 bits + 14 bits" split
     // would pile the short top window's 2^20 entries onto 2^14 buckets and unbalance the per-bin sort 4:1.
@@ -164,6 +173,8 @@ void srs_load(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits
     s->chunk1 = chunk;
     alloc_scratch(s, s->scratch, nb);
     PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    PK_CUDA(cudaGetLastError());
+    ctx->srs = holder.release();
 }
 
 // ---------------------------------------------------------------- window scan + sort by bucket (two-level radix partition)
@@ -500,16 +511,16 @@ void affine_to_abi(const g1_affine_t& p, uint64_t out[8]) {
     memcpy(out + 4, y.v, 32);
 }
 
-// enqueues one group of <= sc.max_sets scalar sets on stream st; the nb XYZZ results land in host_pt (pinned) once st drains
+// enqueues one group of <= sc.max_sets scalar sets on stream st; the nb XYZZ results are copied to `dst` (pinned host
+// memory or device memory) in stream order
 static void msm_enqueue_group(pk_ctx* ctx, MsmScratch& sc, cudaStream_t st, const fr_t* const* scalars, int nb, uint64_t n,
-                              uint64_t base_offset, g1_xyzz_t* host_pt) {
+                              uint64_t base_offset, g1_xyzz_t* dst) {
     SrsTables* s = ctx->srs;
     const uint32_t B = s->B;
     const uint32_t NB = (uint32_t)nb * B;
     ScalarSets sets;
     for (int k = 0; k < MSM_MAX_BATCH; ++k) sets.s[k] = scalars[k < nb ? k : 0];
-    const int lg = ilog2(NB);
-    const int fine_bits = msm_fine_bits(lg);
+    const int fine_bits = msm_fine_bits(NB);
     const uint32_t NC = (NB + (1u << fine_bits) - 1) >> fine_bits;
     PK_CUDA(cudaMemsetAsync(sc.coarse_count.p, 0, (size_t)(NC + 1) * sizeof(uint32_t), st));
     PK_CUDA(cudaMemsetAsync(sc.buckets.p, 0, (size_t)NB * sizeof(g1_xyzz_t), st));
@@ -570,7 +581,7 @@ static void msm_enqueue_group(pk_ctx* ctx, MsmScratch& sc, cudaStream_t st, cons
     msm_fold_kernel<<<nb, 128, 0, st>>>(sc.red.p, wblocks, 1024, result);
     ctx->prof.kernel_launches += 4;
     PK_CUDA(cudaGetLastError());
-    PK_CUDA(cudaMemcpyAsync(host_pt, result, nb * sizeof(g1_xyzz_t), cudaMemcpyDeviceToHost, st));
+    PK_CUDA(cudaMemcpyAsync(dst, result, nb * sizeof(g1_xyzz_t), cudaMemcpyDefault, st));
 }
 
 void msm_run_batch(pk_ctx* ctx, const fr_t* const* scalars, int nb, uint64_t n, uint64_t base_offset, g1_affine_t* out) {
@@ -591,6 +602,21 @@ void msm_run_batch(pk_ctx* ctx, const fr_t* const* scalars, int nb, uint64_t n, 
         msm_enqueue_group(ctx, s->scratch, ctx->stream, scalars + k, g, n, base_offset, host_pt);
         PK_CUDA(cudaStreamSynchronize(ctx->stream));
         for (int j = 0; j < g; ++j) out[k + j] = host_pt[j].to_affine();
+    }
+}
+
+void msm_run_batch_dev(pk_ctx* ctx, const fr_t* const* scalars, int nb, uint64_t n, uint64_t base_offset, g1_xyzz_t* out_dev) {
+    SrsTables* s = ctx->srs;
+    PK_REQUIRE(s != nullptr, PK_ERR_DEGREE_TOO_LARGE, "no SRS loaded (pk_srs_load_g1)");
+    PK_REQUIRE(base_offset + n <= s->n, PK_ERR_DEGREE_TOO_LARGE, "MSM longer than the resident SRS");
+    if (n == 0) {
+        PK_CUDA(cudaMemsetAsync(out_dev, 0, nb * sizeof(g1_xyzz_t), ctx->stream));  // ZZ = 0: infinity
+        return;
+    }
+    const int group = s->scratch.max_sets;
+    for (int k = 0; k < nb; k += group) {
+        const int g = nb - k < group ? nb - k : group;
+        msm_enqueue_group(ctx, s->scratch, ctx->stream, scalars + k, g, n, base_offset, out_dev + k);
     }
 }
 

@@ -45,6 +45,9 @@ void srs_load(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits
 // out[k] = sum_i scalars[k][i] * base[base_offset + i] for k < nb <= MSM_MAX_BATCH; scalars on the device in
 // Montgomery form; results affine (Montgomery) on the host.  One pass over the shared kernels for the whole batch.
 void msm_run_batch(pk_ctx* ctx, const fr_t* const* scalars, int nb, uint64_t n, uint64_t base_offset, g1_affine_t* out);
+// same, but the nb XYZZ sums stay on the device (out_dev[k]) and nothing is synchronised: the partial sums of a sharded
+// commitment, which are all-gathered and folded before they are normalised
+void msm_run_batch_dev(pk_ctx* ctx, const fr_t* const* scalars, int nb, uint64_t n, uint64_t base_offset, g1_xyzz_t* out_dev);
 g1_affine_t msm_run(pk_ctx* ctx, const fr_t* scalars, uint64_t n, uint64_t base_offset);
 // host helper: affine Montgomery point -> canonical u64[8] ((0,0) for infinity)
 void affine_to_abi(const g1_affine_t& p, uint64_t out[8]);

@@ -255,9 +255,12 @@ static PassPlan plan_passes(int L, bool dit) {
     return pl;
 }
 
+// L_tw > L (inverse only): the 2^L elements are one aligned block of a size-2^L_tw transform in bit-reversed order and
+// only the block-local stages (bits 0 .. L-1, twiddles of the big domain) are run — the first part of a transform
+// whose upper stages cross GPUs (sharded prover).
 template <bool DIT>
 static void run_passes(pk_ctx* ctx, const fr_t* src, fr_t* dst, int L, const fr_t* pre, const fr_t* post, const fr_t* post_const,
-                       int batch, size_t src_stride, size_t dst_stride, size_t pre_stride) {
+                       int batch, size_t src_stride, size_t dst_stride, size_t pre_stride, int L_tw = 0) {
     PK_REQUIRE(L >= 0 && L <= 28, PK_ERR_DEGREE_TOO_LARGE, "domain larger than 2^28");
     size_t n = size_t(1) << L;
     if (L == 0) {  // size-1 transform is the identity (all scale factors are 1)
@@ -265,7 +268,9 @@ static void run_passes(pk_ctx* ctx, const fr_t* src, fr_t* dst, int L, const fr_
             PK_CUDA(cudaMemcpyAsync(dst + b * dst_stride, src + b * src_stride, sizeof(fr_t), cudaMemcpyDeviceToDevice, ctx->stream));
         return;
     }
-    ensure_twiddles(ctx, L);
+    if (L_tw < L) L_tw = L;
+    PK_REQUIRE(L_tw == L || DIT, PK_ERR_INVALID, "block-local stages exist for the inverse transform only");
+    ensure_twiddles(ctx, L_tw);
     DomainCache* dc = ctx->domains;
     PassPlan pl = plan_passes(L, DIT);
     ScopedKernelTimer timer(ctx, 1, (uint64_t)n * batch * pl.n);
@@ -278,12 +283,12 @@ static void run_passes(pk_ctx* ctx, const fr_t* src, fr_t* dst, int L, const fr_
         p.src_stride = first ? src_stride : dst_stride;
         p.dst_stride = dst_stride;
         p.tw = dc->tw.p;
-        p.tw_shift = dc->tw_log - L;
+        p.tw_shift = dc->tw_log - L_tw;
         p.pre = first ? pre : nullptr;
         p.pre_stride = pre_stride;
         p.post = last ? post : nullptr;
         if (last && !post && post_const) { p.use_post_const = 1; p.post_const = *post_const; }
-        p.L = L; p.bl = pl.bl[i]; p.k = pl.k[i]; p.c_log = pl.c_log[i];
+        p.L = L_tw; p.bl = pl.bl[i]; p.k = pl.k[i]; p.c_log = pl.c_log[i];
         unsigned E = 1u << (p.k + p.c_log);
         unsigned threads = E >> 1; if (threads < 1) threads = 1;
         dim3 grid((unsigned)(n / E), batch);
@@ -345,6 +350,98 @@ void lde4_slots(pk_ctx* ctx, const fr_t* coeffs, fr_t* out4n, int log_n) {
 void icoset4n_from_slots(pk_ctx* ctx, const fr_t* vals4n, fr_t* coeffs4n, int log_n) {
     CosetTables* ct = get_coset_tables(ctx, log_n);
     ntt_inverse_from_bitrev(ctx, vals4n, coeffs4n, log_n + 2, ct->iscale4n.p);
+}
+
+void ntt_inverse_local_stages(pk_ctx* ctx, const fr_t* src, fr_t* dst, int log_block, int log_total) {
+    if (log_block == 0) {
+        if (src != dst) PK_CUDA(cudaMemcpyAsync(dst, src, sizeof(fr_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        return;
+    }
+    run_passes<true>(ctx, src, dst, log_block, nullptr, nullptr, nullptr, 1, 0, 0, 0, log_total);
+}
+
+// ---------------------------------------------------------------- pieces of the coset-sharded quotient (sharded prover)
+// b[i] = c^i * sum_{u < F} a[i + u * n/F] * kappa^u  (i < n/F): the polynomial a (n coefficients) restricted to the coset
+// c * H_{n/F}, on which X^(n/F) is the constant kappa = c^(n/F); cpow[i] = c^i.  A forward NTT of size n/F finishes the
+// evaluation.  F = 1 is a plain pre-scale.
+__global__ void coset_fold_kernel(const fr_t* a, const fr_t* cpow, fr_t kappa, int F, size_t nf, fr_t* b) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= nf) return;
+    fr_t acc = ld_fp(a + (size_t)(F - 1) * nf + i);
+    for (int u = F - 2; u >= 0; --u) acc = acc * kappa + ld_fp(a + (size_t)u * nf + i);
+    st_fp(b + i, acc * ldg_fp(cpow + i));
+}
+void coset_fold(pk_ctx* ctx, const fr_t* a, const fr_t* cpow, const fr_t& kappa, int F, size_t nf, fr_t* b) {
+    coset_fold_kernel<<<grid1d(nf, 256), 256, 0, ctx->stream>>>(a, cpow, kappa, F, nf, b);
+    ctx->prof.kernel_launches++;
+}
+// out[i] = a[i] * w^i with w the primitive 2^log_n-th root: the coefficients of a(w X)
+__global__ void omega_scale_kernel(const fr_t* a, fr_t* out, const fr_t* tw, int tw_shift, int log_n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >> log_n) return;
+    const size_t half = size_t(1) << (log_n - 1);
+    fr_t w = ldg_fp(tw + ((i & (half - 1)) << tw_shift));
+    if (i & half) w = w.neg();
+    st_fp(out + i, ld_fp(a + i) * w);
+}
+void omega_scale(pk_ctx* ctx, const fr_t* a, fr_t* out, int log_n) {
+    PK_REQUIRE(log_n >= 1, PK_ERR_INVALID, "omega_scale needs a domain of at least 2");
+    ensure_twiddles(ctx, log_n);
+    DomainCache* dc = ctx->domains;
+    omega_scale_kernel<<<grid1d(size_t(1) << log_n, 256), 256, 0, ctx->stream>>>(a, out, dc->tw.p, dc->tw_log - log_n, log_n);
+    ctx->prof.kernel_launches++;
+}
+// The upper log2(G) stages of a size-2^L inverse transform (decimation in time) whose lower stages ran block-locally on
+// G ranks: in[c][k'] = element k0 + k' of rank c's block after its local stages (what the all-to-all delivers), block
+// length m = 2^L / G.  One thread owns the G values of one k, runs the stages in registers and writes
+// out[c][k'] = coefficient (c * m + k0 + k') times g7inv^index / 2^L  (kscale[k'] = g7inv^(k0 + k') / 2^L, cscale[c] = g7inv^(c m)).
+struct CrossArgs { fr_t cscale[8]; };
+template <int G> __global__ void __launch_bounds__(128) ntt_cross_kernel(const fr_t* in, fr_t* out, const fr_t* kscale, CrossArgs ca,
+                                                                         const fr_t* tw, int tw_shift, int L, size_t m, size_t k0,
+                                                                         size_t per) {
+    size_t kk = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (kk >= per) return;
+    fr_t v[G];
+#pragma unroll
+    for (int c = 0; c < G; ++c) v[c] = ld_fp(in + (size_t)c * per + kk);
+    const size_t k = k0 + kk;
+    const size_t half_n = size_t(1) << (L - 1);
+    int log_m = 0;
+    while ((size_t(1) << log_m) < m) ++log_m;
+#pragma unroll
+    for (int u = 0; (1 << u) < G; ++u) {
+        const int s = log_m + u;
+#pragma unroll
+        for (int c = 0; c < G; ++c) {
+            if (c & (1 << u)) continue;
+            const size_t low = k + (size_t)(c & ((1 << u) - 1)) * m;
+            const size_t e = low << (L - 1 - s);
+            const fr_t a = v[c], b = v[c | (1 << u)];
+            const fr_t t = (e == 0) ? b.neg() : b * ldg_fp(tw + ((half_n - e) << tw_shift));
+            v[c] = a - t;
+            v[c | (1 << u)] = a + t;
+        }
+    }
+    const fr_t ks = ldg_fp(kscale + kk);
+#pragma unroll
+    for (int c = 0; c < G; ++c) st_fp(out + (size_t)c * per + kk, v[c] * ks * ca.cscale[c]);
+}
+void ntt_inverse_cross_stages(pk_ctx* ctx, const fr_t* in, fr_t* out, const fr_t* kscale, const fr_t* cscale, int G, int log_total,
+                              size_t k0) {
+    PK_REQUIRE(G == 1 || G == 2 || G == 4 || G == 8, PK_ERR_INVALID, "the sharded prover runs on 1, 2, 4 or 8 ranks");
+    ensure_twiddles(ctx, log_total);
+    DomainCache* dc = ctx->domains;
+    const size_t m = (size_t(1) << log_total) / G, per = m / G;
+    CrossArgs ca;
+    for (int c = 0; c < 8; ++c) ca.cscale[c] = c < G ? cscale[c] : fr_t::one();
+    const int ts = dc->tw_log - log_total;
+    dim3 grid = grid1d(per, 128);
+    if (G == 1) ntt_cross_kernel<1><<<grid, 128, 0, ctx->stream>>>(in, out, kscale, ca, dc->tw.p, ts, log_total, m, k0, per);
+    else if (G == 2) ntt_cross_kernel<2><<<grid, 128, 0, ctx->stream>>>(in, out, kscale, ca, dc->tw.p, ts, log_total, m, k0, per);
+    else if (G == 4) ntt_cross_kernel<4><<<grid, 128, 0, ctx->stream>>>(in, out, kscale, ca, dc->tw.p, ts, log_total, m, k0, per);
+    else ntt_cross_kernel<8><<<grid, 128, 0, ctx->stream>>>(in, out, kscale, ca, dc->tw.p, ts, log_total, m, k0, per);
+    ctx->prof.kernel_launches++;
+    PK_CUDA(cudaGetLastError());
 }
 
 void ntt_rows_natural(pk_ctx* ctx, fr_t* data, fr_t* tmp, int log_len, size_t rows, bool inverse) {

@@ -41,6 +41,17 @@ void twiddle_rows(pk_ctx* ctx, fr_t* a, size_t rows, size_t cols, int log_total,
 void lde4_slots(pk_ctx* ctx, const fr_t* coeffs, fr_t* out4n, int log_n);
 // evaluations on 7*H_4N in slot layout -> 4N coefficients (natural), in place allowed
 void icoset4n_from_slots(pk_ctx* ctx, const fr_t* vals4n, fr_t* coeffs4n, int log_n);
+// ---- pieces of the sharded prover (one proof over several GPUs; dist_prover.cu)
+// block-local stages (bits 0 .. log_block-1) of a size-2^log_total inverse transform on one aligned block of the
+// bit-reversed input; no scaling
+void ntt_inverse_local_stages(pk_ctx* ctx, const fr_t* src, fr_t* dst, int log_block, int log_total);
+// the upper log2(G) stages after the all-to-all, with the coset / size scaling fused (see ntt.cu)
+void ntt_inverse_cross_stages(pk_ctx* ctx, const fr_t* in, fr_t* out, const fr_t* kscale, const fr_t* cscale, int G, int log_total,
+                              size_t k0);
+// b[i] = cpow[i] * sum_u a[i + u nf] kappa^u, i < nf: restriction of a to the coset c H_nf (cpow[i] = c^i, kappa = c^nf)
+void coset_fold(pk_ctx* ctx, const fr_t* a, const fr_t* cpow, const fr_t& kappa, int F, size_t nf, fr_t* b);
+// out[i] = a[i] w_n^i: coefficients of a(w X)
+void omega_scale(pk_ctx* ctx, const fr_t* a, fr_t* out, int log_n);
 // canonical <-> Montgomery on device arrays
 void fr_to_mont(pk_ctx* ctx, fr_t* data, size_t n);
 void fr_from_mont(pk_ctx* ctx, const fr_t* src, fr_t* dst, size_t n);

@@ -386,26 +386,28 @@ struct QuotKernelArgs {
 __global__ void __launch_bounds__(256) quotient_kernel(QuotKernelArgs q) {
     const int log_n = q.a.log_n;
     const size_t n = size_t(1) << log_n;
-    size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (idx >= 4 * n) return;
-    const int s = (int)(idx >> log_n);
-    const uint32_t p = (uint32_t)(idx & (n - 1));
+    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;  // position inside the arrays
+    if (idx >= q.a.range_len) return;
+    const size_t gidx = q.a.range_lo + idx;                            // position in the 4n slot layout
+    const int s = (int)(gidx >> log_n);
+    const uint32_t p = (uint32_t)(gidx & (n - 1));
     const uint32_t j = brev_n(p, log_n);
-    const uint32_t pn = brev_n((j + 1) & (uint32_t)(n - 1), log_n);
-    const size_t idn = ((size_t)s << log_n) + pn;
+    // neighbour w*X: same slot, natural index j + 1 (gathered when the whole slot is resident)
+    const size_t idn = q.a.z_next ? idx : ((size_t)s << log_n) + brev_n((j + 1) & (uint32_t)(n - 1), log_n) - q.a.range_lo;
 
     fr_t a = ld_fp(q.a.w[0] + idx), b = ld_fp(q.a.w[1] + idx), c = ld_fp(q.a.w[2] + idx), d = ld_fp(q.a.w[3] + idx);
+    const fr_t dn = q.a.w3_next ? ld_fp(q.a.w3_next + idx) : ld_fp(q.a.w[3] + idn);
     fr_t gate = ld_fp(q.a.sel[0] + idx) * a + ld_fp(q.a.sel[1] + idx) * b + ld_fp(q.a.sel[2] + idx) * c + ld_fp(q.a.sel[3] + idx) * d +
-                ld_fp(q.a.sel[4] + idx) * (a * b) + ld_fp(q.a.sel[5] + idx) + ld_fp(q.a.sel[6] + idx) * ld_fp(q.a.w[3] + idn);
+                ld_fp(q.a.sel[4] + idx) * (a * b) + ld_fp(q.a.sel[5] + idx) + ld_fp(q.a.sel[6] + idx) * dn;
     if (q.a.num_direct_inputs < 0) {
         gate = gate + ld_fp(q.a.pi + idx);
     } else {
         for (int i = 0; i < q.a.num_direct_inputs; ++i) {
             const uint32_t pj = brev_n((j - (uint32_t)i) & (uint32_t)(n - 1), log_n);
-            gate = gate + q.a.inputs[i] * ld_fp(q.a.l0 + ((size_t)s << log_n) + pj);
+            gate = gate + q.a.inputs[i] * ld_fp(q.a.l0 + ((size_t)s << log_n) + pj - q.a.range_lo);
         }
     }
-    fr_t zv = ld_fp(q.a.z + idx), zn = ld_fp(q.a.z + idn);
+    fr_t zv = ld_fp(q.a.z + idx), zn = q.a.z_next ? ld_fp(q.a.z_next + idx) : ld_fp(q.a.z + idn);
     fr_t bx = q.bg[s] * omega_pow(q.tw, q.tw_shift, log_n, j);
     fr_t ag = a + q.a.gamma, bgm = b + q.a.gamma, cg = c + q.a.gamma, dg = d + q.a.gamma;
     fr_t num = zv * (ag + bx) * (bgm + times_k(bx, 1)) * (cg + times_k(bx, 2)) * (dg + times_k(bx, 3));
@@ -420,6 +422,13 @@ void quotient_slots(pk_ctx* ctx, const QuotientArgs& a) {
     DomainCache* dc = ctx->domains;
     QuotKernelArgs q;
     q.a = a;
+    if (q.a.range_len == 0) {
+        q.a.range_lo = 0;
+        q.a.range_len = size_t(4) << log_n;
+    } else {
+        PK_REQUIRE(a.w3_next && a.z_next && a.num_direct_inputs < 0, PK_ERR_INVALID,
+                   "a partial quotient range needs the shifted LDEs and the public-input LDE");
+    }
     q.alpha2 = a.alpha.sqr();
     fr_t g7;
     for (int i = 0; i < 8; ++i) g7.v[i] = FrRoots::gen7(i);
@@ -435,7 +444,7 @@ void quotient_slots(pk_ctx* ctx, const QuotientArgs& a) {
     }
     q.tw = dc->tw.p;
     q.tw_shift = dc->tw_log - log_n;
-    quotient_kernel<<<grid1d(4 * n, 256), 256, 0, ctx->stream>>>(q);
+    quotient_kernel<<<grid1d(q.a.range_len, 256), 256, 0, ctx->stream>>>(q);
     ctx->prof.kernel_launches++;
     PK_CUDA(cudaGetLastError());
 }

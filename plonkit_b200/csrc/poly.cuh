@@ -57,6 +57,13 @@ struct QuotientArgs {
     fr_t* out;
     fr_t beta, gamma, alpha;
     int log_n;
+    // Sharded prover: the arrays above hold only the contiguous range [range_lo, range_lo + range_len) of the 4n slot
+    // layout (element 0 of every array = position range_lo), and the values at w*X come from their own arrays (the LDEs
+    // of d(wX), Z(wX)) because the neighbour position may live on another GPU.  range_len = 0 means the whole domain
+    // with the in-slot neighbour gather (single-GPU prover).
+    size_t range_lo = 0, range_len = 0;
+    const fr_t* w3_next = nullptr;
+    const fr_t* z_next = nullptr;
 };
 void quotient_slots(pk_ctx* ctx, const QuotientArgs& a);
 

@@ -77,7 +77,7 @@ static void fr_to_abi(const fr_t& x, uint64_t out[4]) {
 
 // sigma as target positions: cycles over the positions of each variable, rows scanned in order,
 // columns a..d inside a row; dummy variable 0 stays the identity.
-static std::vector<uint32_t> build_sigma_targets(const uint32_t* wire_idx, uint64_t n, uint64_t nvars) {
+std::vector<uint32_t> build_sigma_targets(const uint32_t* wire_idx, uint64_t n, uint64_t nvars) {
     const uint32_t NONE = 0xffffffffu;
     std::vector<uint32_t> target(4 * n), first(nvars, NONE), prev(nvars, NONE);
     for (uint64_t i = 0; i < 4 * n; ++i) target[i] = (uint32_t)i;

@@ -158,6 +158,135 @@ class SetupForProver:
         return Crs(pts, self.key_monomial_form.g2_raw, "lagrange")
 
 
+class ShardedSetupForProver:
+    """ONE rank of a `SetupForProver` whose proof is computed by `world` GPUs together (BASELINE.json
+    configs[2]): same methods, same proof bytes; every call is collective (all ranks call it with the same arguments,
+    all ranks get the same result).  `ctx` must already be attached to a communicator (Context.attach_nccl under
+    torchrun, Context.attach_group for the ranks-as-threads form `ShardedProver` drives)."""
+
+    def __init__(self):
+        raise TypeError("use ShardedSetupForProver.prepare_setup_for_prover")
+
+    @classmethod
+    def prepare_setup_for_prover(cls, circuit, key_monomial_form: Crs, ctx: Context):
+        self = object.__new__(cls)
+        asm = _as_assembly(circuit)
+        if key_monomial_form.size < asm.n:
+            raise SynthesisError(2, "monomial SRS holds %d bases, the circuit needs %d" % (key_monomial_form.size, asm.n))
+        self.ctx, self.key_monomial_form = ctx, key_monomial_form
+        self.n, self.num_inputs, self.nvars = asm.n, asm.num_inputs, asm.nvars
+        world, rank = ctx.world, ctx.rank
+        if asm.n % world:
+            raise SynthesisError(6, "domain size is not divisible by the number of ranks")
+        cn = asm.n // world
+        ctx.srs_load_g1(key_monomial_form.g1_bases[rank * cn:(rank + 1) * cn])  # this rank's chunk of the key only
+        wire_idx = np.ascontiguousarray(asm.wire_idx, dtype=np.uint32)
+        selectors = np.ascontiguousarray(asm.selectors, dtype=np.uint64)
+        a = _lib.PkAssembly(asm.n, asm.num_inputs, asm.nvars, wire_idx.ctypes.data, selectors.ctypes.data)
+        h = ctypes.c_void_p()
+        ctx._check(ctx._lib.pk_dist_setup_create(ctx._h, ctypes.byref(a), ctypes.byref(h)))
+        self._h = h
+        ctx._children.add(self)
+        return self
+
+    def close(self):
+        if getattr(self, "_h", None):
+            if getattr(self.ctx, "_h", None):
+                self.ctx._lib.pk_dist_setup_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def make_verification_key(self) -> VerificationKey:
+        out = np.zeros((11, 8), dtype=np.uint64)
+        self.ctx._check(self.ctx._lib.pk_dist_setup_commitments(self.ctx._h, self._h, out.ctypes.data))
+        return VerificationKey(self.n - 1, self.num_inputs, out[:6].copy(), out[6:7].copy(), out[7:11].copy(), [5, 7, 10],
+                               self.key_monomial_form.g2_raw)
+
+    def upload_witness(self, values):
+        vals = np.ascontiguousarray(values, dtype=np.uint64).reshape(-1, 4)
+        self.ctx._check(self.ctx._lib.pk_dist_witness_upload(self.ctx._h, self._h, vals.ctypes.data, vals.shape[0]))
+
+    def prove(self, circuit=None, transcript: str = "keccak") -> Proof:
+        if transcript != "keccak":
+            raise NotImplementedError("the sharded prover implements the 'keccak' transcript")
+        vals, nvars = None, 0
+        if circuit is not None:
+            arr = circuit if isinstance(circuit, np.ndarray) else _as_assembly(circuit).var_values
+            if arr is None:
+                raise SynthesisError(1, "circuit has no witness")
+            vals = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 4)
+            nvars = vals.shape[0]
+        pr = _lib.PkProof()
+        inputs = np.zeros((max(self.num_inputs, 1), 4), dtype=np.uint64)
+        self.ctx._check(self.ctx._lib.pk_dist_prove(self.ctx._h, self._h, vals.ctypes.data if vals is not None else None, nvars,
+                                                    ctypes.byref(pr), inputs.ctypes.data))
+        return _proof_from_struct(pr, inputs[:self.num_inputs])
+
+
+class ShardedProver:
+    """`world` ranks of a sharded prover as threads of THIS process, one context each, on `devices` (default: every rank
+    on device 0 — how the single-GPU parity tests exercise world sizes 2, 4 and 8; pass distinct devices to spread one
+    proof over the GPUs of a node from a single process, peer copies over NVLink).  `prove` returns rank 0's proof after
+    checking that every rank produced the same bytes."""
+
+    def __init__(self, circuit, key_monomial_form: Crs, world: int, devices=None):
+        self.world = world
+        devices = list(devices) if devices is not None else [0] * world
+        self.group = _lib.CommGroup(world)
+        self.ctxs = [Context(devices[r]) for r in range(world)]
+        for r, c in enumerate(self.ctxs):
+            c.attach_group(self.group, r)
+        self.setups = self._collective(lambda r: ShardedSetupForProver.prepare_setup_for_prover(circuit, key_monomial_form, self.ctxs[r]))
+
+    def _collective(self, fn):
+        import threading
+        out, errs = [None] * self.world, [None] * self.world
+
+        def run(r):
+            try:
+                out[r] = fn(r)
+            except Exception as ex:
+                errs[r] = ex
+        th = [threading.Thread(target=run, args=(r,)) for r in range(self.world)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        for e in errs:  # the first genuine failure, not the "a peer rank failed" echoes
+            if e is not None and "peer rank" not in str(e):
+                raise e
+        for e in errs:
+            if e is not None:
+                raise e
+        return out
+
+    def make_verification_key(self) -> VerificationKey:
+        return self._collective(lambda r: self.setups[r].make_verification_key())[0]
+
+    def upload_witness(self, values):
+        self._collective(lambda r: self.setups[r].upload_witness(values))
+
+    def prove(self, circuit=None, transcript: str = "keccak") -> Proof:
+        proofs = self._collective(lambda r: self.setups[r].prove(circuit, transcript))
+        ref = proofs[0].to_bytes()
+        if any(p.to_bytes() != ref for p in proofs[1:]):
+            raise SynthesisError(6, "ranks of the sharded prover disagree on the proof")
+        return proofs[0]
+
+    def close(self):
+        for s_ in getattr(self, "setups", []) or []:
+            s_.close()
+        for c in self.ctxs:
+            c.close()
+        self.group.close()
+        self.setups, self.ctxs = [], []
+
+
 class ProverPool:
     """Several `SetupForProver` instances of the SAME circuit on one GPU, each with its own library context (stream, SRS
     window tables, scratch) and its own host thread: proofs are independent objects, and while one sits in its
