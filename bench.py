@@ -212,6 +212,32 @@ def workload_config(args, world):
     }
 
 
+def sharded_single_proof(args, td, rank, world, local, srs, asm, steps):
+    """ONE proof of the same 2^log_n circuit computed by all `world` GPUs together (plonk.ShardedSetupForProver over NCCL:
+    commitments by base chunk, quotient by coset, one all-to-all in the size-4n inverse NTT) — the strong-scaling latency
+    line next to the replica throughput.  Returns (ms per proof as max over ranks, proof bytes, phase ms of this rank)."""
+    import torch
+    from plonkit_b200 import _lib, plonk, reader
+    ids = [_lib.nccl_unique_id() if rank == 0 else None]
+    td.broadcast_object_list(ids, src=0)
+    c = _lib.Context(local)
+    c.attach_nccl(ids[0], rank, world)
+    sp = plonk.ShardedSetupForProver.prepare_setup_for_prover(asm, reader.Crs(srs), c)
+    sp.upload_witness(asm.var_values)
+    got = None
+    for _ in range(3):
+        got = sp.prove(None).to_bytes()
+    barrier(td, local)
+    c.timer_begin()
+    for _ in range(steps):
+        sp.prove(None)
+    ms = max_over_ranks(td, local, c.timer_end() / steps)
+    phases = c.profile()["phase_ms"]
+    sp.close()
+    c.close()
+    return ms, got, phases
+
+
 def bench_ours(args):
     world, rank, local, td = dist_setup(args.gpus)
     from plonkit_b200 import _lib, plonk, reader, synth
@@ -314,6 +340,19 @@ def bench_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     if ref_bytes is not None:
         assert all(b == ref_bytes for b in pb), "proof bytes changed between runs / provers"
+    shard = None
+    if world > 1 and not args.no_shard:
+        # same circuit and witness on every rank (the replica legs above use a different public input per rank)
+        asm0 = asm if rank == 0 else synth.poseidon_chain_assembly(args.log_n, inputs=(3, 4, 5))
+        for s_ in setups[1:]:   # the extra replica provers are done: free their share of HBM
+            s_.close()
+        ms_shard, shard_bytes, shard_phases = sharded_single_proof(args, td, rank, world, local, srs, asm0, args.steps)
+        shard = {"ms_per_proof": ms_shard, "proofs_per_s": 1e3 / ms_shard, "n_gpus": world, "transport": "nccl",
+                 "bytes_equal_single_gpu_proof": bool(shard_bytes == ref_bytes) if rank == 0 else None,
+                 "phase_ms_rank0": shard_phases[:6],
+                 "what": "ONE proof of the same circuit computed by all %d GPUs together (strong scaling, latency): commitments "
+                         "sharded by base chunk (all-gather of 128-byte partial sums + device fold), quotient sharded by coset, one "
+                         "all-to-all inside the size-4n inverse NTT; not part of `value`" % world}
 
     if rank != 0:
         return 0
@@ -356,6 +395,9 @@ def bench_ours(args):
         "clocks": clocks,
         "prep_s": prep_s,
     }
+    if shard is not None:
+        shard["speedup_vs_one_gpu"] = (ms_single / args.steps) / shard["ms_per_proof"]
+        out["sharded_single_proof"] = shard
     # BASELINE.json's secondary metrics on the same GPU: single-set MSM (uniform scalars) and NTT at the bench size
     try:
         ms_msm, ms_ntt = ctx.bench_msm(n, 3), ctx.bench_ntt(args.log_n, 5)
@@ -391,6 +433,7 @@ def main():
     ap.add_argument("--log-n", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--inflight", type=int, default=3, help="independent provers (proofs in flight) per GPU")
+    ap.add_argument("--no-shard", action="store_true", help="N > 1: skip the sharded single-proof (latency) leg")
     ap.add_argument("--ref-budget-s", type=float, default=300.0, help="--impl reference: wall-clock budget for the CPU proofs")
     args = ap.parse_args()
     if args.warmup < 1:

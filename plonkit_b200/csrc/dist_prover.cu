@@ -15,9 +15,11 @@
 //   * the size-4n inverse NTT of the quotient: block-local stages on each rank's range, ONE all-to-all (each rank sends
 //     1/G of its range to every peer: 4n 32 B / G in total per rank), the last log2 G stages in registers with the
 //     coset / size scaling fused, and an all-gather of the coefficients into natural order.
-//   * wire / grand-product inverse NTTs, scans, evaluations and the opening polynomials are replicated: every rank holds
-//     the witness, they cost a few percent of a proof, and replicating them keeps every rank's transcript identical
-//     without a broadcast.
+//   * grand product, evaluations, linearisation and opening polynomials: sharded by rows / coefficient chunk; what a
+//     scan or a sum needs from the other chunks (prefix products, partial sums, division carries) travels as a few
+//     32-byte scalars per rank, and the finished chunk of Z is all-gathered (n 32 B) for its inverse NTT.
+//   * the five size-n inverse NTTs (wires, Z) and the witness gather are replicated: every rank holds the witness and
+//     needs all coefficients for its LDEs anyway; every rank derives the same transcript, no broadcast.
 //
 // Every rank returns the same proof.  The collectives come from comm.cuh (NCCL between processes, peer copies
 // between the threads of one process).
@@ -56,6 +58,8 @@ struct pk_dist_setup {
     DevBuf<fr_t> tmp_a, tmp_b, tmp_c, fold;
     DevBuf<fr_t> zpow, zinvpow, zwpow, zwinvpow, r_coef;
     DevBuf<g1_xyzz_t> part_pts, all_pts;       // [16], [G][16]
+    DevBuf<fr_t> xs, xr;                       // [16], [G][16]: partial scalars of a sharded scan / evaluation and their all-gather
+    DevBuf<fr_t> zchunk;                       // [cn]
 };
 
 namespace pk {
@@ -118,6 +122,29 @@ static void dist_commit(pk_dist_setup* s, const fr_t* const* polys, int nb, g1_a
     for (int k = 0; k < nb; ++k) out[k] = host[k].to_affine();
 }
 
+// all-gather of the (<= 16) field elements in s->xs; host copy [G][16] returned (synchronises)
+static std::vector<fr_t> gather_scalars(pk_dist_setup* s) {
+    pk_ctx* ctx = s->ctx;
+    ctx->comm->all_gather(s->xs.p, s->xr.p, 16 * sizeof(fr_t), ctx->stream);
+    std::vector<fr_t> h((size_t)s->G * 16);
+    PK_CUDA(cudaMemcpyAsync(h.data(), s->xr.p, h.size() * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return h;
+}
+// results[k] = sum_i polys[k][i] pows[k][i] over the whole vectors: every rank sums its chunk, the partial sums are all-gathered
+static void dist_dot_batch(pk_dist_setup* s, int npoly, const fr_t* const* polys, const fr_t* const* pows, fr_t* results) {
+    const fr_t* pp[16];
+    const fr_t* ww[16];
+    for (int k = 0; k < npoly; ++k) { pp[k] = polys[k] + s->clo; ww[k] = pows[k] + s->clo; }
+    poly_dot_batch_dev(s->ctx, npoly, pp, ww, s->cn, s->xs.p);
+    std::vector<fr_t> h = gather_scalars(s);
+    for (int k = 0; k < npoly; ++k) {
+        fr_t acc = h[k];
+        for (int q = 1; q < s->G; ++q) acc = acc + h[(size_t)q * 16 + k];
+        results[k] = acc;
+    }
+}
+
 // evaluations of the coefficient vector `coef` (n) on this rank's range of the quotient domain -> out (m)
 static void range_lde(pk_dist_setup* s, const fr_t* coef, fr_t* out) {
     pk_ctx* ctx = s->ctx;
@@ -178,6 +205,7 @@ void dist_setup_create(pk_ctx* ctx, const pk_assembly* as, pk_dist_setup** out) 
         s->tmp_a.alloc(n); s->tmp_b.alloc(n); s->tmp_c.alloc(n); s->fold.alloc(s->nf);
         s->zpow.alloc(n); s->zinvpow.alloc(n); s->zwpow.alloc(n); s->zwinvpow.alloc(n); s->r_coef.alloc(n);
         s->part_pts.alloc(16); s->all_pts.alloc((size_t)G * 16);
+        s->xs.alloc(16); s->xr.alloc((size_t)G * 16); s->zchunk.alloc(s->cn);
 
         // coset shifts of this rank's parts.  Slot sl of the layout is the coset g_sl H_n with g_sl = 7 w_4n^brev2(sl);
         // part q of a slot split 2^sub ways holds the natural indices j = brev_sub(q) mod 2^sub, i.e. the coset
@@ -290,16 +318,29 @@ void dist_prove(pk_ctx* ctx, pk_dist_setup* s, const uint64_t* var_values, uint6
     const fr_t beta = d_challenge(tr), gamma = d_challenge(tr);
     mark();
 
-    // ---- round 2
-    perm_num_den(ctx, s->w_nat.p, s->sigma_vals.p, beta, gamma, s->tmp_a.p, s->tmp_b.p, log_n);
-    poly_scan(ctx, true, false, s->tmp_a.p, s->tmp_a.p, n);
-    poly_scan(ctx, true, true, s->tmp_b.p, s->tmp_b.p, n);
-    fr_t total_den;
-    PK_CUDA(cudaMemcpyAsync(&total_den, s->tmp_b.p, sizeof(fr_t), cudaMemcpyDeviceToHost, st));
-    PK_CUDA(cudaStreamSynchronize(st));
-    PK_REQUIRE(!total_den.is_zero(), PK_ERR_DIVISION_BY_ZERO, "zero denominator in the permutation grand product");
-    z_finish(ctx, s->tmp_a.p, s->tmp_b.p, total_den.inverse(), s->tmp_c.p, log_n);
-    ntt_inverse_from_bitrev(ctx, s->tmp_c.p, s->z_coef.p, log_n);
+    // ---- round 2: the grand product, sharded by rows.  Every rank scans ITS chunk of the numerators / denominators; the
+    // chunk totals are all-gathered, the prefix (suffix) products of the chunks below (above) and the one field inversion
+    // happen on the host, and the finished chunk of Z is all-gathered (n 32 B in total) for the replicated inverse NTT.
+    {
+        const uint64_t cn = s->cn, clo = s->clo;
+        perm_num_den_range(ctx, s->w_nat.p, s->sigma_vals.p, beta, gamma, s->tmp_a.p, s->tmp_b.p, log_n, clo, cn);
+        poly_scan(ctx, true, false, s->tmp_a.p, s->tmp_a.p, cn);  // pn[i] = prod_{lo <= j <= lo + i} num_j
+        poly_scan(ctx, true, true, s->tmp_b.p, s->tmp_b.p, cn);   // sd[i] = prod_{lo + i <= j < hi} den_j
+        PK_CUDA(cudaMemcpyAsync(s->xs.p, s->tmp_a.p + cn - 1, sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
+        PK_CUDA(cudaMemcpyAsync(s->xs.p + 1, s->tmp_b.p, sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
+        std::vector<fr_t> h = gather_scalars(s);
+        fr_t below = fr_t::one(), above = fr_t::one(), total_den = fr_t::one();
+        for (int q = 0; q < G; ++q) {
+            if (q < s->rank) below = below * h[(size_t)q * 16];
+            if (q > s->rank) above = above * h[(size_t)q * 16 + 1];
+            total_den = total_den * h[(size_t)q * 16 + 1];
+        }
+        PK_REQUIRE(!total_den.is_zero(), PK_ERR_DIVISION_BY_ZERO, "zero denominator in the permutation grand product");
+        z_finish_chunk(ctx, s->tmp_a.p, s->tmp_b.p, below * above * total_den.inverse(), s->zchunk.p, clo, cn);
+        ctx->comm->all_gather(s->zchunk.p, s->tmp_c.p, cn * sizeof(fr_t), st);
+        bitrev_permute(ctx, s->tmp_c.p, s->tmp_a.p, log_n);
+        ntt_inverse_from_bitrev(ctx, s->tmp_a.p, s->z_coef.p, log_n);
+    }
     g1_affine_t Cz;
     {
         const fr_t* polys[1] = {s->z_coef.p};
@@ -355,11 +396,12 @@ void dist_prove(pk_ctx* ctx, pk_dist_setup* s, const uint64_t* var_values, uint6
     const fr_t zeta = d_challenge(tr);
     mark();
 
-    // ---- round 4 (replicated)
+    // ---- round 4: evaluations, sharded by coefficient chunk (partial sums all-gathered: 13 x 32 B per rank)
+    const uint64_t cn = s->cn, clo = s->clo;
     const fr_t omega = host_root_of_unity(log_n);
     const fr_t zeta_omega = zeta * omega;
-    poly_powers(ctx, s->zpow.p, zeta, n);
-    poly_powers(ctx, s->zwpow.p, zeta_omega, n);
+    poly_powers_from(ctx, s->zpow.p + clo, zeta, clo, cn);
+    poly_powers_from(ctx, s->zwpow.p + clo, zeta_omega, clo, cn);
     fr_t evv[13];
     {
         const fr_t* polys[13];
@@ -370,7 +412,7 @@ void dist_prove(pk_ctx* ctx, pk_dist_setup* s, const uint64_t* var_values, uint6
         for (int k = 0; k < 11; ++k) pows[k] = s->zpow.p;
         polys[11] = s->w_coef.p + 3 * n; pows[11] = s->zwpow.p;
         polys[12] = s->z_coef.p; pows[12] = s->zwpow.p;
-        poly_dot_batch(ctx, 13, polys, pows, n, evv);
+        dist_dot_batch(s, 13, polys, pows, evv);
     }
     const fr_t* wz = evv;
     const fr_t* sz = evv + 4;
@@ -388,16 +430,17 @@ void dist_prove(pk_ctx* ctx, pk_dist_setup* s, const uint64_t* var_values, uint6
     fr_t sfac = alpha * beta * zzw;
     for (int i = 0; i < 3; ++i) sfac = sfac * (wz[i] + beta * sz[i] + gamma);
     {
-        const fr_t* in[9] = {s->sel_coef.p + 5 * n, s->sel_coef.p, s->sel_coef.p + n, s->sel_coef.p + 2 * n, s->sel_coef.p + 3 * n,
-                             s->sel_coef.p + 4 * n, s->sel_coef.p + 6 * n, s->z_coef.p, s->sigma_coef.p + 3 * n};
+        const fr_t* in[9] = {s->sel_coef.p + 5 * n + clo, s->sel_coef.p + clo, s->sel_coef.p + n + clo, s->sel_coef.p + 2 * n + clo,
+                             s->sel_coef.p + 3 * n + clo, s->sel_coef.p + 4 * n + clo, s->sel_coef.p + 6 * n + clo, s->z_coef.p + clo,
+                             s->sigma_coef.p + 3 * n + clo};
         fr_t coef[9] = {fr_t::one(), wz[0], wz[1], wz[2], wz[3], wz[0] * wz[1], dzw, zfac, sfac.neg()};
-        poly_lincomb(ctx, s->r_coef.p, 9, in, coef, n);
+        poly_lincomb(ctx, s->r_coef.p + clo, 9, in, coef, cn);
     }
     fr_t rz;
     {
         const fr_t* polys[1] = {s->r_coef.p};
         const fr_t* pows[1] = {s->zpow.p};
-        poly_dot_batch(ctx, 1, polys, pows, n, &rz);
+        dist_dot_batch(s, 1, polys, pows, &rz);
     }
     for (int c = 0; c < 4; ++c) d_commit_fr(tr, wz[c]);
     d_commit_fr(tr, dzw);
@@ -408,26 +451,38 @@ void dist_prove(pk_ctx* ctx, pk_dist_setup* s, const uint64_t* var_values, uint6
     const fr_t v = d_challenge(tr);
     mark();
 
-    // ---- round 5
+    // ---- round 5: opening polynomials, every rank its own chunk of the coefficients.  The synthetic division is a suffix
+    // sum: the chunk's local sums plus a carry from the chunks above (their totals are all-gathered: 2 x 32 B per rank).
     fr_t vp[11];
     vp[0] = fr_t::one();
     for (int i = 1; i <= 10; ++i) vp[i] = vp[i - 1] * v;
     {
-        const fr_t* in[12] = {s->t4.p, s->t4.p + n, s->t4.p + 2 * n, s->t4.p + 3 * n, s->r_coef.p, s->w_coef.p, s->w_coef.p + n,
-                              s->w_coef.p + 2 * n, s->w_coef.p + 3 * n, s->sigma_coef.p, s->sigma_coef.p + n, s->sigma_coef.p + 2 * n};
+        const fr_t* in[12] = {s->t4.p + clo, s->t4.p + n + clo, s->t4.p + 2 * n + clo, s->t4.p + 3 * n + clo, s->r_coef.p + clo,
+                              s->w_coef.p + clo, s->w_coef.p + n + clo, s->w_coef.p + 2 * n + clo, s->w_coef.p + 3 * n + clo,
+                              s->sigma_coef.p + clo, s->sigma_coef.p + n + clo, s->sigma_coef.p + 2 * n + clo};
         fr_t coef[12] = {fr_t::one(), zeta_n, zn2, zn3, vp[1], vp[2], vp[3], vp[4], vp[5], vp[6], vp[7], vp[8]};
-        poly_lincomb(ctx, s->tmp_a.p, 12, in, coef, n);
+        poly_lincomb(ctx, s->tmp_a.p + clo, 12, in, coef, cn);
     }
     {
-        const fr_t* in[2] = {s->z_coef.p, s->w_coef.p + 3 * n};
+        const fr_t* in[2] = {s->z_coef.p + clo, s->w_coef.p + 3 * n + clo};
         fr_t coef[2] = {vp[9], vp[10]};
-        poly_lincomb(ctx, s->tmp_b.p, 2, in, coef, n);
+        poly_lincomb(ctx, s->tmp_b.p + clo, 2, in, coef, cn);
     }
     PK_REQUIRE(!zeta.is_zero(), PK_ERR_DIVISION_BY_ZERO, "challenge z is zero");
-    poly_powers(ctx, s->zinvpow.p, zeta.inverse(), n);
-    poly_powers(ctx, s->zwinvpow.p, zeta_omega.inverse(), n);
-    poly_divide_linear(ctx, s->tmp_a.p, s->zpow.p, s->zinvpow.p, s->r_coef.p, s->tmp_c.p, n);
-    poly_divide_linear(ctx, s->tmp_b.p, s->zwpow.p, s->zwinvpow.p, s->tmp_a.p, s->tmp_c.p, n);
+    poly_powers_from(ctx, s->zinvpow.p + clo, zeta.inverse(), clo + 1, cn);        // z^-(k + 1), k in the chunk
+    poly_powers_from(ctx, s->zwinvpow.p + clo, zeta_omega.inverse(), clo + 1, cn);
+    // suffix sums of agg(X) z^j (into r_coef's chunk... r is folded into agg already) and of agg2(X) (z w)^j
+    poly_divide_linear_chunk_scan(ctx, s->tmp_a.p + clo, s->zpow.p + clo, s->tmp_c.p + clo, cn);
+    poly_divide_linear_chunk_scan(ctx, s->tmp_b.p + clo, s->zwpow.p + clo, s->zchunk.p, cn);
+    PK_CUDA(cudaMemcpyAsync(s->xs.p, s->tmp_c.p + clo, sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
+    PK_CUDA(cudaMemcpyAsync(s->xs.p + 1, s->zchunk.p, sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
+    {
+        std::vector<fr_t> h = gather_scalars(s);
+        fr_t carry1 = fr_t::zero(), carry2 = fr_t::zero();
+        for (int q = s->rank + 1; q < G; ++q) { carry1 = carry1 + h[(size_t)q * 16]; carry2 = carry2 + h[(size_t)q * 16 + 1]; }
+        poly_divide_linear_chunk_finish(ctx, s->tmp_c.p + clo, s->zinvpow.p + clo, carry1, s->r_coef.p + clo, cn);
+        poly_divide_linear_chunk_finish(ctx, s->zchunk.p, s->zwinvpow.p + clo, carry2, s->tmp_a.p + clo, cn);
+    }
     g1_affine_t Wz[2];
     {
         const fr_t* polys[2] = {s->r_coef.p, s->tmp_a.p};

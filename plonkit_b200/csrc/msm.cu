@@ -17,11 +17,11 @@
 //       offsets          u32_scan_*               exclusive scan of the coarse histogram
 //       scatter          msm_coarse_kernel<true>  partition of (bucket, table index | sign) entries by coarse bin
 //                        msm_fine_sort_kernel     per-bin counting sort by bucket, histogram in shared memory
-//       bucket accum     msm_accum_kernel<true>   mixed XYZZ additions; load-balanced segmented reduction:
+//       bucket accum     msm_accum_kernel         mixed XYZZ additions; load-balanced segmented reduction:
 //                                                 every thread owns a fixed-length chunk of the sorted list,
 //                                                 whole runs go straight to their bucket, runs cut by a chunk
-//                                                 edge become partial entries for the next level
-//                        msm_accum_kernel<false>  same over partial entries (full XYZZ adds) until one chunk remains
+//                                                 edge become partial entries
+//                        msm_accum_level/finish   the partial entries (full XYZZ adds), two grid levels + one block
 //       bucket reduce    msm_super_hi/lo_kernel   bucket id = hi*L + lo: G1[hi] = sum_lo B, G0[lo] = sum_hi B (tree sums)
 //                        msm_weighted_kernel      sum_hi (L*hi + 1) G1[hi] + sum_lo lo G0[lo]  ==  sum_b (b + 1) B_b
 //                        msm_fold_kernel          -> one XYZZ point per scalar set; the host normalises it to affine
@@ -113,9 +113,9 @@ static void alloc_scratch(const SrsTables* s, MsmScratch& sc, int nb) {
     sc.tmp_entries.alloc(nb * M);
     sc.buckets.alloc(NB);
     const size_t nchunks = (nb * M + s->chunk1 - 1) / s->chunk1;
-    for (int k = 0; k < 2; ++k) {
-        sc.pkeys[k].alloc(2 * nchunks + 2);
-        sc.ppts[k].alloc(2 * nchunks + 2);
+    for (int k = 0; k < 2; ++k) {  // partial-run lists: 2 entries per level-1 chunk
+        sc.pkeys[k].alloc(2 * nchunks + 64);
+        sc.ppts[k].alloc(2 * nchunks + 64);
     }
     sc.counts.alloc(16);
     sc.super.alloc((size_t)nb * ((size_t(1) << s->hi_bits) + (size_t(1) << s->lo_bits)));
@@ -367,20 +367,31 @@ __global__ void __launch_bounds__(1024) u32_scan_apply_kernel(const uint32_t* in
 }
 
 // ---------------------------------------------------------------- bucket accumulation (segmented reduction over the sorted list)
+// Level 1 — msm_accum_kernel: every thread owns a fixed-length chunk of the sorted entry list (perfect balance for any
+// scalar distribution) and adds its entries with mixed additions, the window-table gather of entry i + 1 in flight during
+// the ten products of entry i.  Runs that lie inside a chunk go straight to their bucket; a run cut by a chunk edge
+// leaves a partial (key, XYZZ) entry: slot 2t for the run entering chunk t from the left, slot 2t + 1 for the one leaving
+// it on the right.  A slot without a partial sum is a key with bit 31 set and no point is stored or ever loaded.
+// (Stitching the cut runs inside the block / warp through shared memory was built and measured: bit-exact, but the extra
+// live state pushes the kernel over 128 registers and the hot loop slows by 6-10 %: 6.6 / 6.9 ms vs 6.2 ms per launch.)
+// Levels 2, 3 — msm_accum_level_kernel: the same segmented reduction over those entries with full additions, 16 per
+// thread; chunk edges are shifted by one entry so that the pair (tail of chunk t, head of chunk t + 1) — the common case,
+// a run cut once — is never cut again: after level 2 almost every slot is a "no partial" marker.
+// Rest — msm_accum_finish_kernel: ONE block loops over the remaining levels.
+#define ACC_THREADS 128
+#define KEY_INF 0x80000000u
 struct AccumParams {
-    const uint32_t* keys;       // level >= 2: sorted bucket ids of this level's entries
-    const uint2* ent;           // level 1: sorted (bucket id, table index | sign << 31)
-    const g1_xyzz_t* pts;       // level >= 2: partial sums
+    const uint2* ent;           // sorted (bucket id, table index | sign << 31)
     const g1_affine_t* table;
-    const uint32_t* count_in;   // number of entries of this level (device)
-    uint32_t* count_out;        // number of entries of the next level
+    const uint32_t* count_in;   // number of entries (device)
+    uint32_t* count_out;        // number of partial entries for level 2
     uint32_t chunk;             // entries per thread
     g1_xyzz_t* buckets;
-    uint32_t* out_keys;         // [2 * chunks]
+    uint32_t* out_keys;         // [2 * blocks]
     g1_xyzz_t* out_pts;
 };
 
-template <bool LEVEL1> __global__ void __launch_bounds__(128) msm_accum_kernel(AccumParams p) {
+__global__ void __launch_bounds__(ACC_THREADS) msm_accum_kernel(AccumParams p) {
     const uint32_t count = *p.count_in;
     const uint32_t nchunks = (count + p.chunk - 1) / p.chunk;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -388,64 +399,150 @@ template <bool LEVEL1> __global__ void __launch_bounds__(128) msm_accum_kernel(A
     if (t >= nchunks) return;
     const uint32_t s = t * p.chunk;
     const uint32_t e = (s + p.chunk < count) ? s + p.chunk : count;
-    auto key_at = [&](uint32_t i) -> uint32_t { return LEVEL1 ? p.ent[i].x : p.keys[i]; };
+    const bool head_partial = s > 0 && p.ent[s - 1].x == p.ent[s].x;
+    const bool tail_partial = e < count && p.ent[e].x == p.ent[e - 1].x;
+    // one entry ahead: the window-table gather of entry i + 1 (a random 64-byte read) is in flight while the ten
+    // products of entry i execute
+    uint2 en_next = p.ent[s];
+    g1_affine_t pt_next = ldg_affine(p.table + (en_next.y & 0x7fffffffu));
+    const uint32_t first_key = en_next.x;
+    uint32_t cur = first_key;
+    bool in_head = true, head_out = false;
+    g1_xyzz_t acc = g1_xyzz_t::infinity();
+    const g1_xyzz_t inf = g1_xyzz_t::infinity();
+    // a partial sum goes to its out slot; "no partial" is a key with KEY_INF set and no point store
+    auto emit = [&](uint32_t slot, uint32_t key, const g1_xyzz_t& v) {
+        if (v.is_inf()) p.out_keys[slot] = key | KEY_INF;
+        else { p.out_keys[slot] = key; st_xyzz(p.out_pts + slot, v); }
+    };
+    for (uint32_t i = s; i < e; ++i) {
+        const uint2 en = en_next;
+        g1_affine_t pt = pt_next;
+        if (i + 1 < e) {
+            en_next = p.ent[i + 1];
+            pt_next = ldg_affine(p.table + (en_next.y & 0x7fffffffu));
+        }
+        if (en.x != cur) {
+            acc = acc.lnorm();
+            if (in_head && head_partial) { emit(2 * t, first_key, acc); head_out = true; }
+            else if (!acc.is_inf()) st_xyzz(p.buckets + cur, acc);
+            in_head = false;
+            acc = inf;
+            cur = en.x;
+        }
+        if (en.y >> 31) pt.y = pt.y.neg();
+        acc = acc.add_mixed_lazy(pt);  // coordinates stay in [0, 2p) inside a run
+    }
+    acc = acc.lnorm();
+    if (in_head) {  // a single run
+        if (head_partial || tail_partial) emit(2 * t, cur, acc);
+        else {
+            if (!acc.is_inf()) st_xyzz(p.buckets + cur, acc);
+            p.out_keys[2 * t] = cur | KEY_INF;
+        }
+        p.out_keys[2 * t + 1] = cur | KEY_INF;
+    } else {
+        if (!head_out) p.out_keys[2 * t] = first_key | KEY_INF;
+        if (tail_partial) emit(2 * t + 1, cur, acc);
+        else {
+            if (!acc.is_inf()) st_xyzz(p.buckets + cur, acc);
+            p.out_keys[2 * t + 1] = cur | KEY_INF;
+        }
+    }
+}
+
+// one chunk [s, e) of a (key, point) level: complete runs -> buckets, the cut first / last run -> out entries 2t, 2t + 1
+__device__ __forceinline__ void accum_level_chunk(const uint32_t* keys, const g1_xyzz_t* pts, uint32_t count, uint32_t s, uint32_t e,
+                                                  uint32_t t, g1_xyzz_t* buckets, uint32_t* out_keys, g1_xyzz_t* out_pts) {
+    auto key_at = [&](uint32_t i) -> uint32_t { return keys[i] & ~KEY_INF; };
     const bool head_partial = s > 0 && key_at(s - 1) == key_at(s);
     const bool tail_partial = e < count && key_at(e) == key_at(e - 1);
     const uint32_t first_key = key_at(s);
     uint32_t cur = first_key;
     bool in_head = true;
     g1_xyzz_t acc = g1_xyzz_t::infinity();
-    const g1_xyzz_t inf = g1_xyzz_t::infinity();
-    // level 1 runs one entry ahead: the window-table gather of entry i + 1 (a random 64-byte read) is in flight while
-    // the ten products of entry i execute
-    uint2 en_next = make_uint2(0, 0);
-    g1_affine_t pt_next;
-    if (LEVEL1) {
-        en_next = p.ent[s];
-        pt_next = ldg_affine(p.table + (en_next.y & 0x7fffffffu));
-    }
+    auto emit = [&](uint32_t slot, uint32_t key, const g1_xyzz_t& v) {
+        if (v.is_inf()) out_keys[slot] = key | KEY_INF;
+        else { out_keys[slot] = key; st_xyzz(out_pts + slot, v); }
+    };
+    bool head_done = false;
     for (uint32_t i = s; i < e; ++i) {
-        const uint2 en = en_next;
-        g1_affine_t pt = pt_next;
-        if (LEVEL1 && i + 1 < e) {
-            en_next = p.ent[i + 1];
-            pt_next = ldg_affine(p.table + (en_next.y & 0x7fffffffu));
-        }
-        const uint32_t k = LEVEL1 ? en.x : p.keys[i];
+        const uint32_t kraw = keys[i];
+        const uint32_t k = kraw & ~KEY_INF;
         if (k != cur) {
-            if (in_head && head_partial) st_xyzz(p.out_pts + 2 * (size_t)t, LEVEL1 ? acc.lnorm() : acc);
-            else if (!acc.is_inf()) st_xyzz(p.buckets + cur, LEVEL1 ? acc.lnorm() : acc);
+            if (in_head && head_partial) { emit(2 * t, first_key, acc); head_done = true; }
+            else if (!acc.is_inf()) st_xyzz(buckets + cur, acc);
             in_head = false;
-            acc = inf;
+            acc = g1_xyzz_t::infinity();
             cur = k;
         }
-        if (LEVEL1) {
-            if (en.y >> 31) pt.y = pt.y.neg();
-            acc = acc.add_mixed_lazy(pt);  // coordinates stay in [0, 2p) inside a run
-        } else {
-            acc = acc.add(ld_xyzz(p.pts + i));
+        if (!(kraw & KEY_INF)) acc = acc.add(ld_xyzz(pts + i));
+    }
+    if (in_head) {  // a single run
+        if (head_partial || tail_partial) emit(2 * t, cur, acc);
+        else {
+            if (!acc.is_inf()) st_xyzz(buckets + cur, acc);
+            out_keys[2 * t] = cur | KEY_INF;
+        }
+        out_keys[2 * t + 1] = cur | KEY_INF;
+    } else {
+        if (!head_done) out_keys[2 * t] = first_key | KEY_INF;
+        if (tail_partial) emit(2 * t + 1, cur, acc);
+        else {
+            if (!acc.is_inf()) st_xyzz(buckets + cur, acc);
+            out_keys[2 * t + 1] = cur | KEY_INF;
         }
     }
-    // the last run: the tail run, or the only run of the chunk
-    if (in_head) {
-        const bool partial = head_partial || tail_partial;
-        if (partial) st_xyzz(p.out_pts + 2 * (size_t)t, LEVEL1 ? acc.lnorm() : acc);
-        else {
-            if (!acc.is_inf()) st_xyzz(p.buckets + cur, LEVEL1 ? acc.lnorm() : acc);
-            st_xyzz(p.out_pts + 2 * (size_t)t, inf);
+}
+#define LEVEL_CHUNK 16
+// chunk t covers entries [t * LEVEL_CHUNK + 1, (t + 1) * LEVEL_CHUNK + 1), chunk 0 also entry 0
+__device__ __forceinline__ uint32_t level_chunks(uint32_t count) { return count <= 1 ? (count ? 1u : 0u) : (count - 1 + LEVEL_CHUNK - 1) / LEVEL_CHUNK; }
+struct LevelParams {
+    const uint32_t* keys;
+    const g1_xyzz_t* pts;
+    const uint32_t* count_in;
+    uint32_t* count_out;
+    g1_xyzz_t* buckets;
+    uint32_t* out_keys;
+    g1_xyzz_t* out_pts;
+    // finish kernel: ping-pong buffers
+    uint32_t* keys2;
+    g1_xyzz_t* pts2;
+};
+__global__ void __launch_bounds__(128) msm_accum_level_kernel(LevelParams p) {
+    const uint32_t count = *p.count_in;
+    const uint32_t nchunks = level_chunks(count);
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) *p.count_out = nchunks > 1 ? 2 * nchunks : 0;
+    if (t >= nchunks) return;
+    const uint32_t s = t ? t * LEVEL_CHUNK + 1 : 0;
+    const uint32_t e = ((t + 1) * LEVEL_CHUNK + 1 < count) ? (t + 1) * LEVEL_CHUNK + 1 : count;
+    accum_level_chunk(p.keys, p.pts, count, s, e, t, p.buckets, p.out_keys, p.out_pts);
+}
+__global__ void __launch_bounds__(256) msm_accum_finish_kernel(LevelParams p) {
+    __shared__ uint32_t s_count;
+    if (threadIdx.x == 0) s_count = *p.count_in;
+    __syncthreads();
+    const uint32_t* keys = p.keys;
+    const g1_xyzz_t* pts = p.pts;
+    uint32_t* okeys = p.keys2;
+    g1_xyzz_t* opts = p.pts2;
+    for (int level = 0; level < 16; ++level) {
+        const uint32_t count = s_count;
+        if (count == 0) break;
+        const uint32_t nchunks = level_chunks(count);
+        for (uint32_t t = threadIdx.x; t < nchunks; t += blockDim.x) {
+            const uint32_t s = t ? t * LEVEL_CHUNK + 1 : 0;
+            const uint32_t e = ((t + 1) * LEVEL_CHUNK + 1 < count) ? (t + 1) * LEVEL_CHUNK + 1 : count;
+            accum_level_chunk(keys, pts, count, s, e, t, p.buckets, okeys, opts);
         }
-        st_xyzz(p.out_pts + 2 * (size_t)t + 1, inf);
-        p.out_keys[2 * (size_t)t] = cur;
-        p.out_keys[2 * (size_t)t + 1] = cur;
-    } else {
-        if (!head_partial) st_xyzz(p.out_pts + 2 * (size_t)t, inf);
-        if (tail_partial) st_xyzz(p.out_pts + 2 * (size_t)t + 1, LEVEL1 ? acc.lnorm() : acc);
-        else {
-            if (!acc.is_inf()) st_xyzz(p.buckets + cur, LEVEL1 ? acc.lnorm() : acc);
-            st_xyzz(p.out_pts + 2 * (size_t)t + 1, inf);
-        }
-        p.out_keys[2 * (size_t)t] = first_key;
-        p.out_keys[2 * (size_t)t + 1] = cur;
+        __syncthreads();
+        if (threadIdx.x == 0) s_count = nchunks > 1 ? 2 * nchunks : 0;
+        __syncthreads();
+        // next level reads what this one wrote
+        const uint32_t* tk = keys; const g1_xyzz_t* tp = pts;
+        keys = okeys; pts = opts;
+        okeys = const_cast<uint32_t*>(tk); opts = const_cast<g1_xyzz_t*>(tp);
     }
 }
 
@@ -536,39 +633,44 @@ static void msm_enqueue_group(pk_ctx* ctx, MsmScratch& sc, cudaStream_t st, cons
     msm_fine_sort_kernel<<<NC, FS_THREADS, FS_CAP * sizeof(uint2) + ((size_t(1) << fine_bits) + FS_THREADS) * sizeof(uint32_t), st>>>(
         sc.tmp_entries.p, sc.entries.p, sc.coarse_offset.p, fine_bits);
     ctx->prof.kernel_launches += 6;
-    // accumulation levels (worst-case grids; the device-side counts bound the real work)
-    size_t max_entries = (size_t)nb * n * s->W;
-    AccumParams p;
-    memset(&p, 0, sizeof(p));
-    p.table = s->table.p;
-    p.buckets = sc.buckets.p;
-    int level = 0;
-    uint32_t chunk = s->chunk1;
-    const uint32_t* keys = nullptr;
-    while (true) {
-        size_t nchunks = (max_entries + chunk - 1) / chunk;
-        p.keys = keys;
+    // accumulation: level 1, two grid levels over the partial entries, one finishing block
+    {
+        const size_t max_entries = (size_t)nb * n * s->W;
+        const size_t nchunks = (max_entries + s->chunk1 - 1) / s->chunk1;
+        AccumParams p;
+        memset(&p, 0, sizeof(p));
         p.ent = sc.entries.p;
-        p.pts = level == 0 ? nullptr : sc.ppts[(level - 1) & 1].p;
-        p.count_in = sc.counts.p + level;
-        p.count_out = sc.counts.p + level + 1;
-        p.chunk = chunk;
-        p.out_keys = sc.pkeys[level & 1].p;
-        p.out_pts = sc.ppts[level & 1].p;
-        if (level == 0) {
+        p.table = s->table.p;
+        p.count_in = sc.counts.p;
+        p.count_out = sc.counts.p + 1;
+        p.chunk = s->chunk1;
+        p.buckets = sc.buckets.p;
+        p.out_keys = sc.pkeys[0].p;
+        p.out_pts = sc.ppts[0].p;
+        {
             ScopedKernelTimer timer(ctx, 0, (uint64_t)nb * n, st);
-            msm_accum_kernel<true><<<grid1d(nchunks, 128), 128, 0, st>>>(p);
+            msm_accum_kernel<<<grid1d(nchunks, ACC_THREADS), ACC_THREADS, 0, st>>>(p);
             ctx->prof.msm_accum_launches++;
-        } else {
-            msm_accum_kernel<false><<<grid1d(nchunks, 128), 128, 0, st>>>(p);
         }
-        ctx->prof.kernel_launches++;
-        if (nchunks <= 1) break;
-        keys = sc.pkeys[level & 1].p;
-        max_entries = 2 * nchunks;
-        chunk = 16;
-        ++level;
-        PK_REQUIRE(level < 14, PK_ERR_INVALID, "MSM level overflow");
+        LevelParams lp;
+        memset(&lp, 0, sizeof(lp));
+        lp.buckets = sc.buckets.p;
+        size_t entries = 2 * nchunks;
+        int src = 0;
+        for (int level = 0; level < 2; ++level) {
+            const size_t chunks = (entries + LEVEL_CHUNK - 1) / LEVEL_CHUNK + 1;
+            lp.keys = sc.pkeys[src].p; lp.pts = sc.ppts[src].p;
+            lp.count_in = sc.counts.p + 1 + level; lp.count_out = sc.counts.p + 2 + level;
+            lp.out_keys = sc.pkeys[src ^ 1].p; lp.out_pts = sc.ppts[src ^ 1].p;
+            msm_accum_level_kernel<<<grid1d(chunks, 128), 128, 0, st>>>(lp);
+            entries = 2 * chunks;
+            src ^= 1;
+        }
+        lp.keys = sc.pkeys[src].p; lp.pts = sc.ppts[src].p;
+        lp.count_in = sc.counts.p + 3; lp.count_out = nullptr;
+        lp.keys2 = sc.pkeys[src ^ 1].p; lp.pts2 = sc.ppts[src ^ 1].p;
+        msm_accum_finish_kernel<<<1, 256, 0, st>>>(lp);
+        ctx->prof.kernel_launches += 4;
     }
     // bucket reduction
     const uint32_t H = 1u << s->hi_bits, L = 1u << s->lo_bits;

@@ -211,6 +211,147 @@ template <bool DIT> __global__ void __launch_bounds__(512) ntt_pass_kernel(NttPa
     }
 }
 
+// ---------------------------------------------------------------- the same pass with TMA staging of the tile
+// The coefficient tile comes in through the TMA unit: warp 0 arms an mbarrier with the tile's byte count and issues one
+// bulk copy (cp.async.bulk ... mbarrier::complete_tx::bytes) per contiguous row of the tile — a single 16 KB copy for
+// the contiguous pass, 2^k copies of C x 32 B for a strided pass — and the block waits on the barrier's phase instead of
+// pushing every element through registers.  Bulk copies land the tile in its natural layout (32-byte elements), so the
+// two 16-byte halves of element l are read in the order (l >> 2) & 1 selects: eight consecutive elements then cover all
+// eight 16-byte bank groups (the split lo/hi arrays of the non-TMA kernel get the same effect by construction).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ fr_t lds_fr_nat(const uint4* sm, unsigned l) {
+    const unsigned sw = (l >> 2) & 1;
+    const uint4 t0 = sm[2 * l + sw], t1 = sm[2 * l + (sw ^ 1)];
+    const uint4 a = sw ? t1 : t0, b = sw ? t0 : t1;
+    fr_t r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void sts_fr_nat(uint4* sm, unsigned l, const fr_t& x) {
+    const unsigned sw = (l >> 2) & 1;
+    const uint4 a = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]), b = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+    sm[2 * l + sw] = sw ? b : a;
+    sm[2 * l + (sw ^ 1)] = sw ? a : b;
+}
+
+template <bool DIT> __global__ void __launch_bounds__(512) ntt_pass_tma_kernel(NttPass p) {
+    extern __shared__ __align__(128) uint4 sm[];
+    const unsigned e_log = p.k + p.c_log;
+    const unsigned E = 1u << e_log, half = E >> 1;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 2 * E);
+    const unsigned tid = threadIdx.x;
+    const unsigned cmask = (1u << p.c_log) - 1;
+    const fr_t* src = p.src + blockIdx.y * p.src_stride;
+    fr_t* dst = p.dst + blockIdx.y * p.dst_stride;
+    const fr_t* pre = p.pre ? p.pre + blockIdx.y * p.pre_stride : nullptr;
+
+    const unsigned lo_groups_log = p.bl - p.c_log;
+    const size_t blk = blockIdx.x;
+    const size_t hi = blk >> lo_groups_log;
+    const size_t lo0 = (blk & ((size_t(1) << lo_groups_log) - 1)) << p.c_log;
+    const size_t base = (hi << (p.bl + p.k)) | lo0;
+
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid < 32) {
+        // rows of the tile that are contiguous in global memory: the whole tile when bl == c_log, else C elements
+        const bool whole = p.bl == p.c_log;
+        const unsigned nrows = whole ? 1u : (1u << p.k);
+        const unsigned row_bytes = whole ? E * 32u : (32u << p.c_log);
+        if (tid == 0) mbar_arrive_expect_tx(bar, E * 32u);
+        __syncwarp();
+        for (unsigned r = tid; r < nrows; r += 32)
+            tma_load_1d(reinterpret_cast<uint8_t*>(sm) + (size_t)r * row_bytes, src + (base | ((size_t)r << p.bl)), row_bytes, bar);
+    }
+    mbar_wait(bar, 0);
+    if (pre) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            unsigned l = tid + r * half;
+            if (l < E) {
+                size_t g = base | ((size_t)(l >> p.c_log) << p.bl) | (l & cmask);
+                sts_fr_nat(sm, l, lds_fr_nat(sm, l) * ldg_fp(pre + g));
+            }
+        }
+        __syncthreads();
+    }
+
+    const unsigned c = tid & cmask;
+    const unsigned q = tid >> p.c_log;
+    const size_t lo = lo0 | c;
+    const size_t half_n = size_t(1) << (p.L - 1);
+    for (int j = 0; j < p.k; ++j) {
+        const int bitpos = DIT ? j : p.k - 1 - j;
+        const unsigned lowmask = (1u << bitpos) - 1;
+        const unsigned t0 = ((q >> bitpos) << (bitpos + 1)) | (q & lowmask);
+        const unsigned l0 = (t0 << p.c_log) | c;
+        const unsigned l1 = l0 | (1u << (bitpos + p.c_log));
+        fr_t a = lds_fr_nat(sm, l0);
+        fr_t b = lds_fr_nat(sm, l1);
+        const size_t low = ((size_t)(t0 & lowmask) << p.bl) | lo;
+        if (!DIT) {
+            const int s = p.L - p.bl - p.k + j;
+            const size_t e = low << s;
+            fr_t u = a + b;
+            fr_t d = a - b;
+            if (e != 0) d = d * ldg_fp(p.tw + (e << p.tw_shift));
+            sts_fr_nat(sm, l0, u);
+            sts_fr_nat(sm, l1, d);
+        } else {
+            const int s = p.bl + j;
+            const size_t e = low << (p.L - 1 - s);
+            fr_t t = (e == 0) ? b.neg() : b * ldg_fp(p.tw + ((half_n - e) << p.tw_shift));
+            sts_fr_nat(sm, l0, a - t);
+            sts_fr_nat(sm, l1, a + t);
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        unsigned l = tid + r * half;
+        if (l < E) {
+            size_t g = base | ((size_t)(l >> p.c_log) << p.bl) | (l & cmask);
+            fr_t x = lds_fr_nat(sm, l);
+            if (p.post) x = x * ldg_fp(p.post + g);
+            else if (p.use_post_const) x = x * p.post_const;
+            st_fp(dst + g, x);
+        }
+    }
+}
+// PK_NTT_TMA = 1 / 0 selects the TMA-staged pass kernel (tiles of >= 16 elements only: bulk copies move >= 16 B rows and
+// the kernel needs a full warp to issue them)
+static int ntt_use_tma() {
+    static const int v = [] { const char* e = getenv("PK_NTT_TMA"); return e ? atoi(e) : 0; }();
+    return v;
+}
+
 // log2 of the shared-memory tile (elements); 2^(tile - 1) threads per block.  Measured on B200 (2^20 / 2^24 transform):
 // tile 2^10 (512 threads, 2 blocks per SM) 0.237 / 4.20 ms, 2^9 0.206 / 3.54 ms, 2^8 0.198 / 3.50 ms — smaller blocks let the
 // load, butterfly and store phases of different blocks overlap on an SM.  2^9 keeps >= 64-byte runs in the strided passes.
@@ -293,7 +434,10 @@ static void run_passes(pk_ctx* ctx, const fr_t* src, fr_t* dst, int L, const fr_
         unsigned threads = E >> 1; if (threads < 1) threads = 1;
         dim3 grid((unsigned)(n / E), batch);
         size_t smem = (size_t)E * 32;
-        ntt_pass_kernel<DIT><<<grid, threads, smem, ctx->stream>>>(p);
+        if (ntt_use_tma() && threads >= 32 && (p.src != p.dst || true))
+            ntt_pass_tma_kernel<DIT><<<grid, threads, smem + 16, ctx->stream>>>(p);
+        else
+            ntt_pass_kernel<DIT><<<grid, threads, smem, ctx->stream>>>(p);
         ctx->prof.kernel_launches++;
         ctx->prof.ntt_launches++;
     }

@@ -30,27 +30,31 @@ void fr_fill(pk_ctx* ctx, fr_t* out, const fr_t& c, size_t n) {
     ctx->prof.kernel_launches++;
 }
 
-struct PowTable { fr_t p[28]; };  // base^(2^k)
-__global__ void powers_kernel(fr_t* out, PowTable t, size_t n) {
+struct PowTable { fr_t p[29]; };  // base^(2^k)
+__global__ void powers_kernel(fr_t* out, PowTable t, size_t first, size_t n) {  // out[i] = base^(first + i)
     size_t start = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 16;
     if (start >= n) return;
     fr_t x = fr_t::one();
+    const size_t e = first + start;
 #pragma unroll 1
-    for (int k = 0; k < 28; ++k)
-        if ((start >> k) & 1) x = x * t.p[k];
+    for (int k = 0; k < 29; ++k)
+        if ((e >> k) & 1) x = x * t.p[k];
     const fr_t base = t.p[0];
     for (int r = 0; r < 16 && start + r < n; ++r) {
         st_fp(out + start + r, x);
         x = x * base;
     }
 }
-void poly_powers(pk_ctx* ctx, fr_t* out, const fr_t& base, size_t n) {
+void poly_powers_from(pk_ctx* ctx, fr_t* out, const fr_t& base, size_t first, size_t n) {
+    if (!n) return;
+    PK_REQUIRE(first + n <= (size_t(1) << 29), PK_ERR_INVALID, "power table too long");
     PowTable t;
     t.p[0] = base;
-    for (int k = 1; k < 28; ++k) t.p[k] = t.p[k - 1].sqr();
-    powers_kernel<<<grid1d((n + 15) / 16, 128), 128, 0, ctx->stream>>>(out, t, n);
+    for (int k = 1; k < 29; ++k) t.p[k] = t.p[k - 1].sqr();
+    powers_kernel<<<grid1d((n + 15) / 16, 128), 128, 0, ctx->stream>>>(out, t, first, n);
     ctx->prof.kernel_launches++;
 }
+void poly_powers(pk_ctx* ctx, fr_t* out, const fr_t& base, size_t n) { poly_powers_from(ctx, out, base, 0, n); }
 
 struct LinArgs { const fr_t* in[12]; fr_t coef[12]; int n_terms; };
 __global__ void lincomb_kernel(fr_t* out, LinArgs a, size_t n) {
@@ -96,18 +100,23 @@ __global__ void __launch_bounds__(256) dot_final_kernel(const fr_t* partial, int
     for (int i = threadIdx.x; i < nblk; i += blockDim.x) acc = acc + ld_fp(partial + blockIdx.x * nblk + i);
     block_reduce_add(acc, sh, out + blockIdx.x);
 }
-void poly_dot_batch(pk_ctx* ctx, int npoly, const fr_t* const* polys, const fr_t* const* pows, size_t n, fr_t* results_host) {
+void poly_dot_batch_dev(pk_ctx* ctx, int npoly, const fr_t* const* polys, const fr_t* const* pows, size_t n, fr_t* out_dev) {
     PK_REQUIRE(npoly >= 1 && npoly <= 16, PK_ERR_INVALID, "dot batch arity");
     PolyScratch* sc = poly_scratch(ctx);
     sc->dot_partial.ensure(16 * DOT_BLOCKS);
-    sc->dot_out.ensure(16);
     DotArgs a;
     for (int k = 0; k < npoly; ++k) { a.poly[k] = polys[k]; a.pow[k] = pows[k]; }
     int nblk = (int)((n + 255) / 256);
     if (nblk > DOT_BLOCKS) nblk = DOT_BLOCKS;
+    if (nblk < 1) nblk = 1;
     dot_kernel<<<dim3(nblk, npoly), 256, 0, ctx->stream>>>(a, n, sc->dot_partial.p);
-    dot_final_kernel<<<npoly, 256, 0, ctx->stream>>>(sc->dot_partial.p, nblk, sc->dot_out.p);
+    dot_final_kernel<<<npoly, 256, 0, ctx->stream>>>(sc->dot_partial.p, nblk, out_dev);
     ctx->prof.kernel_launches += 2;
+}
+void poly_dot_batch(pk_ctx* ctx, int npoly, const fr_t* const* polys, const fr_t* const* pows, size_t n, fr_t* results_host) {
+    PolyScratch* sc = poly_scratch(ctx);
+    sc->dot_out.ensure(16);
+    poly_dot_batch_dev(ctx, npoly, polys, pows, n, sc->dot_out.p);
     fr_t* host = reinterpret_cast<fr_t*>(ctx->pinned);
     PK_CUDA(cudaMemcpyAsync(host, sc->dot_out.p, npoly * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
     PK_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -220,6 +229,23 @@ __global__ void divide_finish_kernel(const fr_t* suffix, const fr_t* zinvpow, fr
 }
 void fr_mul_pointwise(pk_ctx* ctx, const fr_t* a, const fr_t* b, fr_t* out, size_t n) {
     mul_pointwise_kernel<<<grid1d(n, 256), 256, 0, ctx->stream>>>(a, b, out, n);
+    ctx->prof.kernel_launches++;
+}
+// chunk [lo, lo + len) of the same division on a rank of the sharded prover: suffix[i] = sum_{j >= i, j in chunk} p_j z^j,
+// then q[k] = (suffix[k + 1] + carry) * z^-(k + 1) with carry = the sum over the chunks above (zi[i] = z^-(lo + i + 1))
+void poly_divide_linear_chunk_scan(pk_ctx* ctx, const fr_t* p, const fr_t* zpow, fr_t* suffix, size_t len) {
+    mul_pointwise_kernel<<<grid1d(len, 256), 256, 0, ctx->stream>>>(p, zpow, suffix, len);
+    ctx->prof.kernel_launches++;
+    poly_scan(ctx, false, true, suffix, suffix, len);
+}
+__global__ void divide_finish_chunk_kernel(const fr_t* suffix, const fr_t* zi, fr_t carry, fr_t* q, size_t len) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    fr_t sfx = i + 1 < len ? ld_fp(suffix + i + 1) + carry : carry;
+    st_fp(q + i, sfx * ld_fp(zi + i));
+}
+void poly_divide_linear_chunk_finish(pk_ctx* ctx, const fr_t* suffix, const fr_t* zi, const fr_t& carry, fr_t* q, size_t len) {
+    divide_finish_chunk_kernel<<<grid1d(len, 256), 256, 0, ctx->stream>>>(suffix, zi, carry, q, len);
     ctx->prof.kernel_launches++;
 }
 void poly_divide_linear(pk_ctx* ctx, const fr_t* p, const fr_t* zpow, const fr_t* zinvpow, fr_t* q, fr_t* tmp, size_t n) {
@@ -335,10 +361,11 @@ void sigma_values(pk_ctx* ctx, const uint32_t* sigma_target, fr_t* sigma_vals, i
     ctx->prof.kernel_launches++;
 }
 __global__ void perm_num_den_kernel(const fr_t* w, const fr_t* sig, fr_t beta, fr_t gamma, fr_t* num, fr_t* den, const fr_t* tw,
-                                    int tw_shift, int log_n) {
-    size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+                                    int tw_shift, int log_n, size_t lo, size_t len) {  // rows [lo, lo + len) -> num/den[0..len)
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const size_t n = size_t(1) << log_n;
-    if (j >= n) return;
+    if (i >= len) return;
+    const size_t j = lo + i;
     fr_t bw = beta * omega_pow(tw, tw_shift, log_n, j);
     fr_t nn, dd;
 #pragma unroll
@@ -349,16 +376,32 @@ __global__ void perm_num_den_kernel(const fr_t* w, const fr_t* sig, fr_t beta, f
         nn = c ? nn * a : a;
         dd = c ? dd * b : b;
     }
-    st_fp(num + j, nn);
-    st_fp(den + j, dd);
+    st_fp(num + i, nn);
+    st_fp(den + i, dd);
+}
+void perm_num_den_range(pk_ctx* ctx, const fr_t* vals_nat, const fr_t* sigma_vals, const fr_t& beta, const fr_t& gamma, fr_t* num,
+                        fr_t* den, int log_n, size_t lo, size_t len) {
+    ensure_twiddles(ctx, log_n);
+    DomainCache* dc = ctx->domains;
+    perm_num_den_kernel<<<grid1d(len, 256), 256, 0, ctx->stream>>>(vals_nat, sigma_vals, beta, gamma, num, den, dc->tw.p,
+                                                                   dc->tw_log - log_n, log_n, lo, len);
+    ctx->prof.kernel_launches++;
 }
 void perm_num_den(pk_ctx* ctx, const fr_t* vals_nat, const fr_t* sigma_vals, const fr_t& beta, const fr_t& gamma, fr_t* num,
                   fr_t* den, int log_n) {
-    ensure_twiddles(ctx, log_n);
-    DomainCache* dc = ctx->domains;
-    size_t n = size_t(1) << log_n;
-    perm_num_den_kernel<<<grid1d(n, 256), 256, 0, ctx->stream>>>(vals_nat, sigma_vals, beta, gamma, num, den, dc->tw.p,
-                                                                 dc->tw_log - log_n, log_n);
+    perm_num_den_range(ctx, vals_nat, sigma_vals, beta, gamma, num, den, log_n, 0, size_t(1) << log_n);
+}
+// rows [lo, lo + len) of Z in natural order from the chunk-local scans: z[j] = pn[j - 1] * sd[j] * factor with pn[lo - 1] = 1
+// (the products of the chunks below / above and 1 / prod den are folded into `factor`); z[0] = 1
+__global__ void z_finish_chunk_kernel(const fr_t* pn, const fr_t* sd, fr_t factor, fr_t* z, size_t lo, size_t len) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    fr_t v = ld_fp(sd + i) * factor;
+    if (i) v = v * ld_fp(pn + i - 1);
+    st_fp(z + i, lo + i == 0 ? fr_t::one() : v);
+}
+void z_finish_chunk(pk_ctx* ctx, const fr_t* pn, const fr_t* sd, const fr_t& factor, fr_t* z, size_t lo, size_t len) {
+    z_finish_chunk_kernel<<<grid1d(len, 256), 256, 0, ctx->stream>>>(pn, sd, factor, z, lo, len);
     ctx->prof.kernel_launches++;
 }
 __global__ void z_finish_kernel(const fr_t* pn, const fr_t* sd, fr_t tinv, fr_t* z_br, int log_n) {

@@ -17,15 +17,21 @@ void fr_fill(pk_ctx* ctx, fr_t* out, const fr_t& c, size_t n);
 void fr_mul_pointwise(pk_ctx* ctx, const fr_t* a, const fr_t* b, fr_t* out, size_t n);
 // out[j] = base^j
 void poly_powers(pk_ctx* ctx, fr_t* out, const fr_t& base, size_t n);
+void poly_powers_from(pk_ctx* ctx, fr_t* out, const fr_t& base, size_t first, size_t n);  // out[i] = base^(first + i)
 // out[i] = sum_k coef[k] * in[k][i]  (nterms <= 12); out may alias an input
 void poly_lincomb(pk_ctx* ctx, fr_t* out, int nterms, const fr_t* const* in, const fr_t* coef, size_t n);
 // results[k] = sum_i polys[k][i] * pows[k][i]   (npoly <= 16), results on the host (synchronises the stream)
 void poly_dot_batch(pk_ctx* ctx, int npoly, const fr_t* const* polys, const fr_t* const* pows, size_t n, fr_t* results_host);
+// same sums, left on the device (out_dev[k]), nothing synchronised: partial sums of a sharded evaluation
+void poly_dot_batch_dev(pk_ctx* ctx, int npoly, const fr_t* const* polys, const fr_t* const* pows, size_t n, fr_t* out_dev);
 // inclusive scan under * (mul = true) or + ; reverse = suffix scan.  in/out may alias.
 void poly_scan(pk_ctx* ctx, bool mul, bool reverse, const fr_t* in, fr_t* out, size_t n);
 // q(X) = (p(X) - p(z)) / (X - z) given zpow[j] = z^j and zinvpow[j] = z^-j ; tmp is an n-element scratch; q != p
 void poly_divide_linear(pk_ctx* ctx, const fr_t* p, const fr_t* zpow, const fr_t* zinvpow, fr_t* q, fr_t* tmp, size_t n);
 
+// the same division on one chunk of the coefficients (sharded prover; see poly.cu)
+void poly_divide_linear_chunk_scan(pk_ctx* ctx, const fr_t* p, const fr_t* zpow, fr_t* suffix, size_t len);
+void poly_divide_linear_chunk_finish(pk_ctx* ctx, const fr_t* suffix, const fr_t* zi, const fr_t& carry, fr_t* q, size_t len);
 // out[i] = in[i]^-1, zeros stay zero (bellman batch_inversion); tmp_a, tmp_b: n-element scratch, out may alias in
 void poly_batch_inversion(pk_ctx* ctx, const fr_t* in, fr_t* out, fr_t* tmp_a, fr_t* tmp_b, size_t n);
 
@@ -40,6 +46,9 @@ bool gate_check(pk_ctx* ctx, const fr_t* vals_nat, const fr_t* sel_vals, uint32_
 void sigma_values(pk_ctx* ctx, const uint32_t* sigma_target, fr_t* sigma_vals, int log_n);
 void perm_num_den(pk_ctx* ctx, const fr_t* vals_nat, const fr_t* sigma_vals, const fr_t& beta, const fr_t& gamma, fr_t* num,
                   fr_t* den, int log_n);
+void perm_num_den_range(pk_ctx* ctx, const fr_t* vals_nat, const fr_t* sigma_vals, const fr_t& beta, const fr_t& gamma, fr_t* num,
+                        fr_t* den, int log_n, size_t lo, size_t len);
+void z_finish_chunk(pk_ctx* ctx, const fr_t* pn, const fr_t* sd, const fr_t& factor, fr_t* z, size_t lo, size_t len);
 // z_br[brev(0)] = 1 ; z_br[brev(j)] = pn[j-1] * sd[j] * tinv
 void z_finish(pk_ctx* ctx, const fr_t* pn, const fr_t* sd, const fr_t& tinv, fr_t* z_br, int log_n);
 

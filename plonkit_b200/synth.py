@@ -177,3 +177,54 @@ def random_gate_assembly(log_n: int, seed: int = SEED, reuse: float = 0.5, num_i
             rows.append((a, b, len(vals) - 1, 0, [1, 1, M1, 0, 0, k, 0]))
     from .circuit import assembly_from_rows
     return assembly_from_rows(rows, vals, num_inputs)
+
+
+def random_gate_assembly_layered(log_n: int, seed: int = SEED, layers: int = 16, reuse: float = 0.5) -> Assembly:
+    """The BASELINE config 3 shape (half multiplication gates c = a*b, half addition gates c = a + b + k, operands re-used
+    with probability `reuse`) at sizes where `random_gate_assembly`'s gate-by-gate Python loop is too slow (2^22 - 2^24):
+    gates are generated in `layers` layers with numpy; an operand of a gate in layer l either re-uses a variable created
+    in an earlier layer or is a fresh variable.  One public input."""
+    from .bn254 import limbs_to_ints
+    n = 1 << log_n
+    n_gates = n - 1
+    body = n_gates - 1
+    rng = np.random.default_rng(seed & 0xFFFFFFFF)
+    per = [body // layers + (1 if i < body % layers else 0) for i in range(layers)]
+    wire_idx = np.zeros((4, n), dtype=np.uint32)
+    selectors = np.zeros((7, n, 4), dtype=np.uint64)
+    m1 = ints_to_limbs([R_MOD - 1])[0]
+    one = ints_to_limbs([1])[0]
+    wire_idx[0, 0] = 1
+    selectors[0, 0] = m1
+    values = [0, rng.integers(1, 1 << 62).item()]  # variable 0 = dummy, variable 1 = the public input
+    row = 1
+    for g in per:
+        nv0 = len(values)                               # variables that exist before this layer
+        fresh_a = rng.random(g) >= reuse if nv0 > 2 else np.ones(g, dtype=bool)
+        fresh_b = rng.random(g) >= reuse if nv0 > 2 else np.ones(g, dtype=bool)
+        na, nb = int(fresh_a.sum()), int(fresh_b.sum())
+        new_vals = limbs_to_ints(random_field_elements(na + nb + g, seed=seed + row))  # fresh operands, then the constants k
+        a_idx = rng.integers(1, nv0, size=g, dtype=np.int64)
+        b_idx = rng.integers(1, nv0, size=g, dtype=np.int64)
+        a_idx[fresh_a] = nv0 + np.arange(na)
+        b_idx[fresh_b] = nv0 + na + np.arange(nb)
+        values.extend(new_vals[:na + nb])
+        ks = new_vals[na + nb:]
+        is_mul = rng.random(g) < 0.5
+        av = [values[i] for i in a_idx.tolist()]
+        bv = [values[i] for i in b_idx.tolist()]
+        cv = [(x * y % R_MOD) if mflag else ((x + y + k) % R_MOD) for x, y, k, mflag in zip(av, bv, ks, is_mul.tolist())]
+        c_idx = len(values) + np.arange(g)
+        values.extend(cv)
+        sl = slice(row, row + g)
+        wire_idx[0, sl], wire_idx[1, sl], wire_idx[2, sl] = a_idx, b_idx, c_idx
+        selectors[2, sl] = m1                            # q_c = -1
+        selectors[4, sl][is_mul] = one                   # q_m = 1
+        add = ~is_mul
+        selectors[0, sl][add] = one
+        selectors[1, sl][add] = one
+        kl = ints_to_limbs(ks)
+        selectors[5, sl][add] = kl[add]
+        row += g
+    return Assembly(n=n, num_inputs=1, wire_idx=wire_idx, selectors=selectors, var_values=ints_to_limbs(values), nvars=len(values),
+                    num_gates=n_gates)

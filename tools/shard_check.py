@@ -34,7 +34,10 @@ def main():
     ctx = _lib.Context(local)
     ctx.attach_nccl(ids[0], rank, world)
     t0 = time.time()
-    asm = synth.poseidon_chain_assembly(args.log_n) if args.kind == "poseidon" else synth.random_gate_assembly(args.log_n, seed=7)
+    if args.kind == "poseidon":
+        asm = synth.poseidon_chain_assembly(args.log_n)
+    else:  # BASELINE configs[2]: random wires
+        asm = synth.random_gate_assembly_layered(args.log_n, seed=7)
     gen = _lib.Context(local)
     srs = gen.srs_gen(asm.n, 42)
     key = reader.Crs(srs)
