@@ -39,6 +39,7 @@ class CircomCircuit:  # src/circom_circuit.rs:40-47
     witness: Optional[List[int]] = None
     wire_mapping: Optional[List[int]] = None
     aux_offset: int = AUX_OFFSET
+    strict: bool = True   # False: also transpile constraint shapes no reference fixture pins (see _transpile)
 
     def _w(self, i):
         if self.wire_mapping is None:
@@ -113,6 +114,15 @@ class _Gates:
 
 
 def _transpile(circuit: CircomCircuit, strict: bool = True) -> _Gates:
+    """R1CS constraints -> width-4 gates.
+
+    strict = True accepts only the constraint shapes whose gate layout the reference's golden vectors pin
+    (single-variable A and B, C = one variable or two variables + constant; src/tests.rs:14) and raises
+    `UnpinnedTranspilation` otherwise.  strict = False also transpiles arbitrary linear combinations — BYTE PARITY
+    UNPINNED: bellman's adaptor (src/transpile.rs:92-139 is only its wrapper) is not in the reference tree and no
+    fixture shows its layout for long combinations, so this is this repository's own sound layout: a combination of up
+    to three variables is collapsed into a fresh variable by one gate, a longer one by a running sum carried through the
+    d wire with q_dnext = -1; pinned shapes come out exactly as in strict mode."""
     r = circuit.r1cs
     have_w = circuit.witness is not None
     g = _Gates()
@@ -124,49 +134,103 @@ def _transpile(circuit: CircomCircuit, strict: bool = True) -> _Gates:
     # public-input gates first
     for i in range(1, r.num_inputs):
         g.rows.append((i, 0, 0, 0, [R_MOD - 1, 0, 0, 0, 0, 0, 0]))
+    M1 = R_MOD - 1
 
     def new_var(val):
         g.values.append(val)
         return len(g.values) - 1
+
+    def lc_value(terms, const):
+        if not have_w:
+            return None
+        return (sum(c * g.values[v] for v, c in terms) + const) % R_MOD
+
+    def chain(terms, const, out):
+        """Gates enforcing sum(terms) + const - out = 0 (out = None: the sum itself is zero).  More than four summands
+        run as a chain: every row adds up to three terms to the running sum in d and hands it to the next row's d."""
+        items = list(terms) + ([(out, M1)] if out is not None else [])
+        if len(items) <= 4:
+            wires = [v for v, _ in items] + [0] * (4 - len(items))
+            coefs = [c for _, c in items] + [0] * (4 - len(items))
+            g.rows.append((wires[0], wires[1], wires[2], wires[3], [coefs[0], coefs[1], coefs[2], coefs[3], 0, const, 0]))
+            return
+        first, rest = items[:4], items[4:]
+        acc_val = lc_value(first, const)
+        acc = new_var(acc_val)
+        g.rows.append((first[0][0], first[1][0], first[2][0], first[3][0],
+                       [first[0][1], first[1][1], first[2][1], first[3][1], 0, const, M1]))
+        while rest:
+            take, rest = rest[:3], rest[3:]
+            wires = [v for v, _ in take] + [0] * (3 - len(take))
+            coefs = [c for _, c in take] + [0] * (3 - len(take))
+            if rest:
+                nxt_val = None if not have_w else (acc_val + sum(c * g.values[v] for v, c in take)) % R_MOD
+                nxt = new_var(nxt_val)
+                g.rows.append((wires[0], wires[1], wires[2], acc, [coefs[0], coefs[1], coefs[2], 1, 0, 0, M1]))
+                acc, acc_val = nxt, nxt_val
+            else:
+                g.rows.append((wires[0], wires[1], wires[2], acc, [coefs[0], coefs[1], coefs[2], 1, 0, 0, 0]))
+
+    def collapse(terms, const):
+        """-> (variable, coefficient) with  LC == coefficient * variable; a fresh variable (and its gates) unless the
+        combination already is a single variable"""
+        if len(terms) == 1 and const == 0:
+            return terms[0]
+        t = new_var(lc_value(terms, const))
+        if len(terms) == 2:   # the pinned layout: (a = v1, b = v2, c = t), q_c = -1
+            (v1, c1), (v2, c2) = terms
+            g.rows.append((v1, v2, t, 0, [c1, c2, M1, 0, 0, const, 0]))
+        else:
+            chain(terms, const, t)
+        return t, 1
 
     for ci, (A, B, C) in enumerate(r.constraints):
         if (len(A) == 0 or len(B) == 0) and len(C) == 0:  # 0 * LC = 0 is ignored (circom_circuit.rs:122-123)
             continue
         before = len(g.rows)
         (ta, ka), (tb, kb), (tc, kc) = _norm_lc(A), _norm_lc(B), _norm_lc(C)
-        if not (len(ta) == 1 and ka == 0 and len(tb) == 1 and kb == 0):
-            raise UnpinnedTranspilation("constraint %d: A and B must be single-variable terms" % ci)
-        (x, alpha), (y, beta) = ta[0], tb[0]
-        qm = alpha * beta % R_MOD
-        if len(tc) == 1 and kc == 0:
-            z, gamma = tc[0]
-            g.rows.append((x, y, z, 0, [0, 0, (R_MOD - gamma) % R_MOD, 0, qm, 0, 0]))
-        elif len(tc) == 2:
-            (v1, c1), (v2, c2) = tc
-            tval = None
-            if have_w:
-                tval = (c1 * g.values[v1] + c2 * g.values[v2] + kc) % R_MOD
-            t = new_var(tval)
-            g.rows.append((v1, v2, t, 0, [c1, c2, R_MOD - 1, 0, 0, kc, 0]))
-            g.rows.append((x, y, t, 0, [0, 0, R_MOD - 1, 0, qm, 0, 0]))
+        pinned = len(ta) == 1 and ka == 0 and len(tb) == 1 and kb == 0 and ((len(tc) == 1 and kc == 0) or len(tc) == 2)
+        if not pinned and strict:
+            if not (len(ta) == 1 and ka == 0 and len(tb) == 1 and kb == 0):
+                raise UnpinnedTranspilation("constraint %d: A and B must be single-variable terms" % ci)
+            raise UnpinnedTranspilation("constraint %d: C side with %d variables is not pinned by any fixture" % (ci, len(tc)))
+        if not ta or not tb:
+            # a constant factor: k * LC_other - LC_C = 0 is linear
+            k, (to, ko) = (ka, (tb, kb)) if not ta else (kb, (ta, ka))
+            lin = {}
+            for v, c in to:
+                lin[v] = (lin.get(v, 0) + k * c) % R_MOD
+            for v, c in tc:
+                lin[v] = (lin.get(v, 0) - c) % R_MOD
+            terms = sorted((v, c) for v, c in lin.items() if c)
+            const = (k * ko - kc) % R_MOD
+            if not terms:
+                if const:
+                    raise ValueError("constraint %d is the contradiction %d = 0" % (ci, const))
+            else:
+                chain(terms, const, None)
         else:
-            if strict:
-                raise UnpinnedTranspilation("constraint %d: C side with %d variables is not pinned by any fixture" % (ci, len(tc)))
-            raise UnpinnedTranspilation("constraint %d" % ci)
+            (x, alpha), (y, beta) = collapse(ta, ka), collapse(tb, kb)
+            qm = alpha * beta % R_MOD
+            if not tc:
+                g.rows.append((x, y, 0, 0, [0, 0, 0, 0, qm, (R_MOD - kc) % R_MOD, 0]))
+            else:
+                z, gamma = collapse(tc, kc)
+                g.rows.append((x, y, z, 0, [0, 0, (R_MOD - gamma) % R_MOD, 0, qm, 0, 0]))
         g.hints += 1
         g.stats.append(ConstraintStat(str(ci), len(g.rows) - before))
     return g
 
 
-def transpile_with_gates_count(circuit: CircomCircuit):
+def transpile_with_gates_count(circuit: CircomCircuit, strict: Optional[bool] = None):
     """src/transpile.rs:127-139 -> (gates_count, hints_count).  Counts exclude the public-input gates."""
-    g = _transpile(circuit)
+    g = _transpile(circuit, circuit.strict if strict is None else strict)
     n_in = circuit.r1cs.num_inputs - 1
     return len(g.rows) - n_in, g.hints
 
 
-def synthesize(circuit: CircomCircuit, strict: bool = True) -> Assembly:
-    g = _transpile(circuit, strict)
+def synthesize(circuit: CircomCircuit, strict: Optional[bool] = None) -> Assembly:
+    g = _transpile(circuit, circuit.strict if strict is None else strict)
     return assembly_from_rows(g.rows, g.values, circuit.r1cs.num_inputs - 1)
 
 
@@ -189,9 +253,9 @@ def assembly_from_rows(rows, values, num_inputs) -> Assembly:
                     nvars=len(values), num_gates=n_gates)
 
 
-def analyse(circuit: CircomCircuit) -> dict:
+def analyse(circuit: CircomCircuit, strict: Optional[bool] = None) -> dict:
     """src/plonk.rs:72-95 (field order as serialised by the reference; src/tests.rs:14)"""
-    g = _transpile(circuit)
+    g = _transpile(circuit, circuit.strict if strict is None else strict)
     r = circuit.r1cs
     res = {
         "num_inputs": r.num_inputs,

@@ -228,3 +228,101 @@ def random_gate_assembly_layered(log_n: int, seed: int = SEED, layers: int = 16,
         row += g
     return Assembly(n=n, num_inputs=1, wire_idx=wire_idx, selectors=selectors, var_values=ints_to_limbs(values), nvars=len(values),
                     num_gates=n_gates)
+
+
+# ---------------------------------------------------------------- an R1CS of circomlib's Poseidon(2) shape (wide LCs)
+def poseidon_r1cs(hashes: int = 1, inputs=(3, 4)):
+    """R1CS + witness shaped like circom's optimised output for circomlib 0.5 `Poseidon(2)` (test/circuits/poseidon):
+    t = 3, 8 full + 57 partial rounds, x^5 S-box = 3 constraints (x2 = x*x, x4 = x2*x2, x5 = x4*x) whose factors are
+    LINEAR COMBINATIONS: the MDS mix and the round constants are folded into the next S-box input, and in the partial
+    rounds the two untouched state elements stay linear, so the combinations grow to ~60 terms.  243 constraints per
+    hash; `hashes` permutations are chained (output 0 feeds input 0).  The real circuit's R1CS / witness cannot be made
+    here (no circom / snarkjs) and circomlib's constants are not in the tree: constants come from splitmix64("plonkit").
+    Returns (circuit.R1CS, witness list): wire 0 = ONE, wire 1 = the public output, then the two private inputs."""
+    from .circuit import R1CS
+    rng = SplitMix64(SEED ^ 0x5EED)
+    rounds = FULL_ROUNDS + PARTIAL_ROUNDS
+    rc = [[rng.field() for _ in range(T)] for _ in range(rounds)]
+    mds = [[rng.field() for _ in range(T)] for _ in range(T)]
+    witness = [1, 0, inputs[0] % R_MOD, inputs[1] % R_MOD]   # ONE, out (filled at the end), in0, in1
+    constraints = []
+
+    def lc_eval(lc):
+        return sum(c * witness[v] for v, c in lc.items()) % R_MOD
+
+    def lc_add_scaled(dst, src, k):
+        for v, c in src.items():
+            dst[v] = (dst.get(v, 0) + k * c) % R_MOD
+
+    def new_wire(val):
+        witness.append(val % R_MOD)
+        return len(witness) - 1
+
+    def mul(a_lc, b_lc):
+        """new wire w with constraint a_lc * b_lc = w"""
+        w = new_wire(lc_eval(a_lc) * lc_eval(b_lc))
+        constraints.append((dict(a_lc), dict(b_lc), {w: 1}))
+        return w
+
+    # state as linear combinations over wires (wire 0 carries constants)
+    state = [{0: 0}, {2: 1}, {3: 1}]
+    for _ in range(hashes):
+        for r in range(rounds):
+            full = r < FULL_ROUNDS // 2 or r >= FULL_ROUNDS // 2 + PARTIAL_ROUNDS
+            # add round constants
+            for i in range(T):
+                state[i] = dict(state[i])
+                state[i][0] = (state[i].get(0, 0) + rc[r][i]) % R_MOD
+            # S-box on the full state or on element 0
+            for i in range(T if full else 1):
+                x = state[i]
+                x2 = mul(x, x)
+                x4 = mul({x2: 1}, {x2: 1})
+                x5 = mul({x4: 1}, x)
+                state[i] = {x5: 1}
+            # MDS mix, kept linear
+            new_state = []
+            for i in range(T):
+                lc = {}
+                for j in range(T):
+                    lc_add_scaled(lc, state[j], mds[i][j])
+                new_state.append({v: c for v, c in lc.items() if c})
+            state = new_state
+        # chain: the next permutation starts from (out0, in-lane 1, in-lane 2) of this one
+    out_val = lc_eval(state[0])
+    witness[1] = out_val
+    # out === state[0]: 1 * LC = out
+    constraints.append(({0: 1}, dict(state[0]), {1: 1}))
+
+    def as_lc(d):
+        return sorted((v, c) for v, c in d.items() if c)
+    cons = [(as_lc(a), as_lc(b), as_lc(c)) for a, b, c in constraints]
+    n_vars = len(witness)
+    return R1CS(num_inputs=2, num_aux=n_vars - 2, num_variables=n_vars, constraints=cons), witness
+
+
+def write_r1cs_bin(r1cs, path, n_pub_out=1, n_pub_in=0):
+    """iden3 `.r1cs` (src/r1cs_file.rs:100-154): header, constraints, identity wire->label map."""
+    import struct
+    prime = R_MOD.to_bytes(32, "little")
+    n_prv = r1cs.num_variables - 1 - n_pub_out - n_pub_in
+    header = struct.pack("<I", 32) + prime + struct.pack("<IIIIQI", r1cs.num_variables, n_pub_out, n_pub_in, n_prv,
+                                                         r1cs.num_variables, len(r1cs.constraints))
+
+    def vec(lc):
+        return struct.pack("<I", len(lc)) + b"".join(struct.pack("<I", v) + (c % R_MOD).to_bytes(32, "little") for v, c in lc)
+    body = b"".join(vec(a) + vec(b) + vec(c) for a, b, c in r1cs.constraints)
+    wmap = b"".join(struct.pack("<Q", i) for i in range(r1cs.num_variables))
+    with open(path, "wb") as f:
+        f.write(b"r1cs" + struct.pack("<II", 1, 3))
+        for st, data in ((1, header), (2, body), (3, wmap)):
+            f.write(struct.pack("<IQ", st, len(data)) + data)
+
+
+def write_wtns(witness, path):
+    """snarkjs `.wtns` (src/reader.rs:124-175)"""
+    import struct
+    body = b"".join((int(v) % R_MOD).to_bytes(32, "little") for v in witness)
+    with open(path, "wb") as f:
+        f.write(b"wtns" + struct.pack("<II", 2, 2) + struct.pack("<IQ", 1, 40) + struct.pack("<I", 32) + R_MOD.to_bytes(32, "little") +
+                struct.pack("<I", len(witness)) + struct.pack("<IQ", 2, len(body)) + body)

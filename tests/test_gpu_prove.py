@@ -162,6 +162,35 @@ def test_full_size_2pow20_random_gate_circuit_bytes_equal_oracle(ctx, orc, srs20
     setup.close()
 
 
+def test_cli_proves_a_poseidon_shaped_r1cs_with_wide_linear_combinations(tmp_path, orc, simple_key):
+    """`plonkit prove` on a circomlib-Poseidon(2)-shaped .r1cs / .wtns pair (244 constraints, combinations up to 61 terms;
+    test/circuits/poseidon's own R1CS cannot be produced here: no circom).  The transpilation of long combinations is BYTE
+    PARITY UNPINNED (own layout), so the check is: the proof verifies against the exported verification key with the
+    trapdoor verifier, and equals the oracle's proof of the same gate tables."""
+    from plonkit_b200 import __main__ as cli
+    from plonkit_b200 import reader
+    r1cs, wit = synth.poseidon_r1cs()
+    synth.write_r1cs_bin(r1cs, str(tmp_path / "circuit.r1cs"))
+    synth.write_wtns(wit, str(tmp_path / "witness.wtns"))
+    key = os.path.join(GOLDEN, "setup_2^12.key")
+    if not os.path.exists(key):
+        key = str(tmp_path / "setup.key")
+        cli.main(["setup", "-p", "12", "-m", key])
+    with pytest.raises(circuit.UnpinnedTranspilation):   # strict by default
+        cli.main(["prove", "-m", key, "-c", str(tmp_path / "circuit.r1cs"), "-w", str(tmp_path / "witness.wtns"), "-p", str(tmp_path / "p0.bin")])
+    common = ["-m", key, "-c", str(tmp_path / "circuit.r1cs"), "--allow-unpinned-transpilation"]
+    cli.main(["export-verification-key"] + common + ["-v", str(tmp_path / "vk.bin")])
+    cli.main(["prove"] + common + ["-w", str(tmp_path / "witness.wtns"), "-p", str(tmp_path / "proof.bin"),
+                                  "-j", str(tmp_path / "proof.json"), "-i", str(tmp_path / "public.json")])
+    proof = (tmp_path / "proof.bin").read_bytes()
+    vk = reader.load_verification_key(str(tmp_path / "vk.bin"))
+    assert orc.verify_trapdoor(proof, vk_commitments(vk), 42)
+    asm = circuit.synthesize(circuit.CircomCircuit(r1cs, wit, strict=False))
+    srs = reader.load_key_monomial_form(key).g1_bases
+    assert proof == orc.prove(asm.n, asm.num_inputs, asm.wire_idx, asm.var_values, asm.selectors, srs[:asm.n], threads=8)
+    assert reader.load_proof(str(tmp_path / "proof.bin")).input_values == [wit[1]]
+
+
 def test_cli_setup_writes_the_reference_key_file(tmp_path):
     """`plonkit setup -p 10` (src/bin/main.rs:334-343 -> gen_key_monomial_form -> Crs::crs_42) == keys/setup/setup_2^10.key,
     G2 part included; and a verification key exported from that key carries the trailing 256 B of G2."""

@@ -153,6 +153,59 @@ def test_unpinned_r1cs_shapes_are_refused():
     assert circuit.synthesize(circuit.CircomCircuit(r, [1, 5, 6, 7])).num_gates == 1
 
 
+def test_general_transpiler_handles_wide_linear_combinations():
+    """strict = False (BYTE PARITY UNPINNED, circuit._transpile): linear combinations of any length are laid out as running
+    sums through d / q_dnext = -1; the pinned shapes come out exactly as in strict mode; every gate table is satisfied by
+    the extended witness and rejects a wrong one."""
+    import random
+    rnd = random.Random(5)
+    # pinned shapes: identical tables in both modes
+    strict = circuit.synthesize(circuit.CircomCircuit(reader.load_r1cs(os.path.join(SIMPLE, "circuit.r1cs.json")),
+                                                      reader.load_witness_from_file(os.path.join(SIMPLE, "witness.json"))))
+    general = circuit.synthesize(circuit.CircomCircuit(reader.load_r1cs(os.path.join(SIMPLE, "circuit.r1cs.json")),
+                                                       reader.load_witness_from_file(os.path.join(SIMPLE, "witness.json")), strict=False))
+    assert (strict.wire_idx == general.wire_idx).all() and (strict.selectors == general.selectors).all()
+    # random constraints  (sum a_i w_i + ka) * (sum b_i w_i + kb) = sum c_i w_i + kc  with 0..12 terms a side
+    nv = 40
+    for trial in range(30):
+        wit = [1] + [rnd.randrange(R_MOD) for _ in range(nv - 1)]
+        cons = []
+        for _ in range(6):
+            def lc(k):
+                return [(rnd.randrange(0, nv - 1), rnd.randrange(1, R_MOD)) for _ in range(k)]
+            A, B = lc(rnd.randrange(0, 13)), lc(rnd.randrange(0, 13))
+            ev = lambda L: sum(c * wit[v] for v, c in L) % R_MOD  # noqa: E731
+            # C = fresh wire holding the product, plus noise terms that cancel, so the constraint holds
+            wit.append(ev(A) * ev(B) % R_MOD)
+            extra = lc(rnd.randrange(0, 10))
+            C = [(len(wit) - 1, 1)] + extra + [(0, (-ev(extra)) % R_MOD)]
+            cons.append((A, B, C))
+        r = circuit.R1CS(num_inputs=3, num_aux=len(wit) - 3, num_variables=len(wit), constraints=cons)
+        asm = circuit.synthesize(circuit.CircomCircuit(r, wit, strict=False))
+        assert circuit.is_satisfied(asm), trial
+        bad = list(wit)
+        bad[-1] = (bad[-1] + 1) % R_MOD
+        assert not circuit.is_satisfied(circuit.synthesize(circuit.CircomCircuit(r, bad, strict=False)))
+        assert circuit.synthesize(circuit.CircomCircuit(r, None, strict=False)).var_values is None  # setup-only synthesis
+    with pytest.raises(ValueError, match="contradiction"):
+        circuit.synthesize(circuit.CircomCircuit(circuit.R1CS(2, 0, 2, [([(0, 2)], [(0, 3)], [(0, 5)])]), [1, 7], strict=False))
+
+
+def test_poseidon_shaped_r1cs_round_trips_and_transpiles(tmp_path):
+    """synth.poseidon_r1cs: circomlib Poseidon(2)-shaped R1CS (244 constraints, combinations up to 61 terms) through the
+    iden3 .r1cs / .wtns writers and the reference-format parsers, refused in strict mode, satisfied in general mode."""
+    r1cs, wit = synth.poseidon_r1cs()
+    assert len(r1cs.constraints) == 244 and max(len(b) for _, b, _ in r1cs.constraints) > 50
+    synth.write_r1cs_bin(r1cs, str(tmp_path / "c.r1cs"))
+    synth.write_wtns(wit, str(tmp_path / "w.wtns"))
+    r2, w2 = reader.load_r1cs(str(tmp_path / "c.r1cs")), reader.load_witness_from_file(str(tmp_path / "w.wtns"))
+    assert r2.constraints == r1cs.constraints and w2 == wit and (r2.num_inputs, r2.num_variables) == (2, r1cs.num_variables)
+    with pytest.raises(circuit.UnpinnedTranspilation):
+        circuit.synthesize(circuit.CircomCircuit(r2, w2))
+    asm = circuit.synthesize(circuit.CircomCircuit(r2, w2, strict=False))
+    assert circuit.is_satisfied(asm) and asm.n == 4096 and asm.num_inputs == 1
+
+
 def test_synthetic_circuits_are_satisfied_and_sized():
     for log_n in (6, 9, 11):
         a = synth.poseidon_chain_assembly(log_n)
