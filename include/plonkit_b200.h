@@ -52,6 +52,12 @@ void pk_constants(uint64_t out[24]);
 /* Makes the first n G1 bases of a Crs resident (Crs::read result, src/reader.rs:74-77) and builds the
  * fixed-base window tables the MSM uses.  window_bits = 0 picks it from n. */
 int pk_srs_load_g1(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits);
+/* The Lagrange-form key of a size-n domain (Crs<Bn256, CrsForLagrangeForm>, src/reader.rs:80-89; n a power of two):
+ * kept resident beside the monomial one.  A setup switched to it with pk_setup_use_lagrange commits the four wire
+ * polynomials from their VALUES (kate_commitment::commit_using_values, the `prove(..., key_lagrange_form)` branch of
+ * src/plonk.rs:138-146) — same proof bytes, no dependence of the first round on the inverse NTTs.  bases_xy = NULL with
+ * n = 0 unloads it. */
+int pk_srs_load_g1_lagrange(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits);
 /* Crs::<Bn256, CrsForMonomialForm>::crs_42(n) generalised to any tau (src/plonk.rs:41,47): out[i] = [tau^i] G. */
 int pk_srs_gen(pk_ctx* ctx, uint64_t n, uint64_t tau, uint64_t* out_xy);
 
@@ -136,6 +142,9 @@ typedef struct pk_proof {
  * Requires pk_srs_load_g1 with at least n bases. */
 int pk_setup_create(pk_ctx* ctx, const pk_assembly* assembly, pk_setup** out);
 void pk_setup_destroy(pk_setup* setup);
+/* on != 0: pk_prove commits the wires from values with the resident Lagrange-form key (which must have exactly the
+ * circuit's domain size); PK_ERR_DEGREE_TOO_LARGE if none is loaded. */
+int pk_setup_use_lagrange(pk_ctx* ctx, pk_setup* setup, int on);
 /* SetupForProver::make_verification_key (src/plonk.rs:122-124): 11 commitments, order q_a,q_b,q_c,q_d,q_m,q_const,
  * q_dnext, sigma_0..sigma_3. */
 int pk_setup_commitments(pk_ctx* ctx, pk_setup* setup, uint64_t out_xy[11][8]);

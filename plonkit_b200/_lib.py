@@ -24,7 +24,8 @@ ERRORS = {
 FMT_CANONICAL, FMT_MONTGOMERY = 0, 1
 
 EXPORTS = [
-    "pk_create", "pk_destroy", "pk_last_error", "pk_constants", "pk_srs_load_g1", "pk_srs_gen", "pk_ntt", "pk_lde4",
+    "pk_create", "pk_destroy", "pk_last_error", "pk_constants", "pk_srs_load_g1", "pk_srs_load_g1_lagrange", "pk_setup_use_lagrange",
+    "pk_srs_gen", "pk_ntt", "pk_lde4",
     "pk_msm_g1", "pk_ec_intt_g1", "pk_setup_create", "pk_setup_destroy", "pk_setup_commitments", "pk_witness_upload",
     "pk_prove", "pk_profile_enable", "pk_profile_reset", "pk_profile_get", "pk_bench_ntt", "pk_bench_msm",
     "pk_bench_fieldmul", "pk_timer_begin", "pk_timer_end", "pk_g1_sum", "pk_dev_fr_convert", "pk_dev_ntt_rows",
@@ -100,6 +101,8 @@ def load():
     lib.pk_constants.argtypes = [vp]
     lib.pk_constants.restype = None
     lib.pk_srs_load_g1.argtypes = [vp, vp, u64, i32]
+    lib.pk_srs_load_g1_lagrange.argtypes = [vp, vp, u64, i32]
+    lib.pk_setup_use_lagrange.argtypes = [vp, vp, i32]
     lib.pk_srs_gen.argtypes = [vp, u64, u64, vp]
     lib.pk_ntt.argtypes = [vp, vp, u32, i32, i32, i32]
     lib.pk_lde4.argtypes = [vp, vp, u32, vp, i32, i32]
@@ -167,6 +170,7 @@ class Context:
         self.device = device
         self.srs_size = 0
         self.srs_tag = None  # which key is resident (plonk.SetupForProver._ensure_srs); None after a direct load
+        self.lagrange_tag = None
         self._children = weakref.WeakSet()  # device-side objects that must be released before the context
 
     def close(self):
@@ -190,9 +194,20 @@ class Context:
     def srs_load_g1(self, bases, window_bits=0, tag=None):
         b = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
         self.srs_tag = None
+        self.lagrange_tag = None  # a Lagrange key sharing the old tables' working set goes with them
         self._check(self._lib.pk_srs_load_g1(self._h, _ptr(b), b.shape[0], window_bits))
         self.srs_size = b.shape[0]
         self.srs_tag = tag
+
+    def srs_load_g1_lagrange(self, bases, window_bits=0, tag=None):
+        """Lagrange-form key of a power-of-two domain, resident beside the monomial one; bases=None unloads it."""
+        self.lagrange_tag = None
+        if bases is None:
+            self._check(self._lib.pk_srs_load_g1_lagrange(self._h, None, 0, 0))
+            return
+        b = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
+        self._check(self._lib.pk_srs_load_g1_lagrange(self._h, _ptr(b), b.shape[0], window_bits))
+        self.lagrange_tag = tag
 
     def srs_gen(self, n, tau=42):
         out = np.zeros((n, 8), dtype=np.uint64)

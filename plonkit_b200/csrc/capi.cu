@@ -17,6 +17,7 @@ void setup_commitments(pk_ctx* ctx, pk_setup* s, uint64_t out_xy[11][8]);
 void witness_upload(pk_ctx* ctx, pk_setup* s, const uint64_t* var_values, uint64_t nvars);
 void prove(pk_ctx* ctx, pk_setup* s, const uint64_t* var_values, uint64_t nvars, pk_proof* proof, uint64_t* inputs_out);
 void setup_free(pk_setup* s);
+void setup_use_lagrange(pk_ctx* ctx, pk_setup* s, bool on);
 void ec_intt(pk_ctx* ctx, uint32_t log_n, uint64_t* out_xy);
 void ec_dev_from_affine(pk_ctx* ctx, const g1_affine_t* in_canonical, g1_xyzz_t* out, size_t n);
 void ec_dev_ntt_rows(pk_ctx* ctx, g1_xyzz_t* data, int log_len, size_t rows, bool inverse);
@@ -102,6 +103,7 @@ void pk_destroy(pk_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     profile_resolve(ctx);
+    delete ctx->srs_lagrange;
     delete ctx->srs;
     delete ctx->domains;
     delete ctx->comm;
@@ -132,6 +134,20 @@ int pk_srs_load_g1(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window
     PK_API_BEGIN(ctx)
     PK_REQUIRE(bases_xy != nullptr, PK_ERR_INVALID, "null bases");
     srs_load(ctx, bases_xy, n, window_bits);
+    PK_API_END(ctx)
+}
+
+int pk_srs_load_g1_lagrange(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits) {
+    PK_API_BEGIN(ctx)
+    if (bases_xy == nullptr && n == 0) {  // unload
+        PK_CUDA(cudaStreamSynchronize(ctx->stream));
+        delete ctx->srs_lagrange;
+        ctx->srs_lagrange = nullptr;
+        return PK_OK;
+    }
+    PK_REQUIRE(bases_xy != nullptr, PK_ERR_INVALID, "null bases");
+    PK_REQUIRE((n & (n - 1)) == 0, PK_ERR_INVALID, "a Lagrange-form key belongs to a power-of-two domain");
+    srs_load(ctx, bases_xy, n, window_bits, true);
     PK_API_END(ctx)
 }
 
@@ -367,6 +383,12 @@ int pk_setup_create(pk_ctx* ctx, const pk_assembly* assembly, pk_setup** out) {
     PK_API_END(ctx)
 }
 void pk_setup_destroy(pk_setup* setup) { setup_free(setup); }
+int pk_setup_use_lagrange(pk_ctx* ctx, pk_setup* setup, int on) {
+    PK_API_BEGIN(ctx)
+    PK_REQUIRE(setup != nullptr, PK_ERR_INVALID, "null setup");
+    setup_use_lagrange(ctx, setup, on != 0);
+    PK_API_END(ctx)
+}
 
 int pk_setup_commitments(pk_ctx* ctx, pk_setup* setup, uint64_t out_xy[11][8]) {
     PK_API_BEGIN(ctx)

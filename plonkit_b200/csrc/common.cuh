@@ -88,6 +88,7 @@ struct pk_ctx {
     std::string last_error;
     pk::Profile prof;
     pk::SrsTables* srs = nullptr;
+    pk::SrsTables* srs_lagrange = nullptr;   // optional Lagrange-form key (wire commitments from values)
     pk::DomainCache* domains = nullptr;
     pk::Comm* comm = nullptr;          // set by pk_comm_attach_*: this context is one rank of a sharded prover
     // small pinned staging area for results (commitments, scalars)

@@ -122,7 +122,7 @@ static void alloc_scratch(const SrsTables* s, MsmScratch& sc, int nb) {
     sc.red.alloc((size_t)MSM_MAX_BATCH * 1024 + MSM_MAX_BATCH);
 }
 
-void srs_load(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits) {
+void srs_load(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits, bool lagrange) {
     PK_REQUIRE(n >= 1, PK_ERR_INVALID, "empty SRS");
     PK_REQUIRE(n <= (uint64_t(1) << 26), PK_ERR_DEGREE_TOO_LARGE, "SRS larger than 2^26 bases (SETUP_MAX_POW2, src/plonk.rs:27)");
     int c = window_bits ? window_bits : pick_window_bits(n);
@@ -132,8 +132,13 @@ void srs_load(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits
     PK_CUDA(cudaStreamSynchronize(ctx->stream));
     // the old tables go first (two resident copies may not fit); the new ones are published only once every
     // allocation and kernel has succeeded, so a failed load leaves "no SRS", never a half-built one
-    delete ctx->srs;
-    ctx->srs = nullptr;
+    SrsTables*& slot = lagrange ? ctx->srs_lagrange : ctx->srs;
+    if (!lagrange && ctx->srs_lagrange && ctx->srs_lagrange->scratch != &ctx->srs_lagrange->own_scratch) {
+        delete ctx->srs_lagrange;  // it borrows the working set of the tables that are about to go
+        ctx->srs_lagrange = nullptr;
+    }
+    delete slot;
+    slot = nullptr;
     std::unique_ptr<SrsTables> holder(new SrsTables());
     SrsTables* s = holder.get();
     // Window widths: the 255 scalar bits (254 + one spare for the signed-digit carry) are split as evenly as possible
@@ -171,10 +176,13 @@ void srs_load(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits
     uint32_t chunk = 64;
     while (M / chunk > (size_t(1) << 19)) chunk *= 2;
     s->chunk1 = chunk;
-    alloc_scratch(s, s->scratch, nb);
+    if (lagrange && ctx->srs && ctx->srs->n == n && ctx->srs->c == s->c && ctx->srs->W == s->W && ctx->srs->chunk1 == s->chunk1)
+        s->scratch = ctx->srs->scratch;  // same plan: one working set serves both keys (they never run concurrently)
+    else
+        alloc_scratch(s, s->own_scratch, nb);
     PK_CUDA(cudaStreamSynchronize(ctx->stream));
     PK_CUDA(cudaGetLastError());
-    ctx->srs = holder.release();
+    slot = holder.release();
 }
 
 // ---------------------------------------------------------------- window scan + sort by bucket (two-level radix partition)
@@ -610,9 +618,9 @@ void affine_to_abi(const g1_affine_t& p, uint64_t out[8]) {
 
 // enqueues one group of <= sc.max_sets scalar sets on stream st; the nb XYZZ results are copied to `dst` (pinned host
 // memory or device memory) in stream order
-static void msm_enqueue_group(pk_ctx* ctx, MsmScratch& sc, cudaStream_t st, const fr_t* const* scalars, int nb, uint64_t n,
+static void msm_enqueue_group(pk_ctx* ctx, SrsTables* s, cudaStream_t st, const fr_t* const* scalars, int nb, uint64_t n,
                               uint64_t base_offset, g1_xyzz_t* dst) {
-    SrsTables* s = ctx->srs;
+    MsmScratch& sc = *s->scratch;
     const uint32_t B = s->B;
     const uint32_t NB = (uint32_t)nb * B;
     ScalarSets sets;
@@ -686,22 +694,23 @@ static void msm_enqueue_group(pk_ctx* ctx, MsmScratch& sc, cudaStream_t st, cons
     PK_CUDA(cudaMemcpyAsync(dst, result, nb * sizeof(g1_xyzz_t), cudaMemcpyDefault, st));
 }
 
-void msm_run_batch(pk_ctx* ctx, const fr_t* const* scalars, int nb, uint64_t n, uint64_t base_offset, g1_affine_t* out) {
-    SrsTables* s = ctx->srs;
+void msm_run_batch(pk_ctx* ctx, const fr_t* const* scalars, int nb, uint64_t n, uint64_t base_offset, g1_affine_t* out,
+                   SrsTables* tables) {
+    SrsTables* s = tables ? tables : ctx->srs;
     PK_REQUIRE(s != nullptr, PK_ERR_DEGREE_TOO_LARGE, "no SRS loaded (pk_srs_load_g1)");
     PK_REQUIRE(base_offset + n <= s->n, PK_ERR_DEGREE_TOO_LARGE, "MSM longer than the resident SRS");
     if (n == 0) {
         for (int k = 0; k < nb; ++k) out[k] = g1_affine_t::infinity();
         return;
     }
-    const int group = s->scratch.max_sets;
+    const int group = s->scratch->max_sets;
     g1_xyzz_t* host_pt = reinterpret_cast<g1_xyzz_t*>(ctx->pinned);
     // (Splitting a group over two streams so that one half's sort overlaps the other half's accumulation was measured
     // at N = 2^20: 4 % slower, the halves pay the latency-bound tail kernels twice.  The overlap that pays is between
     // independent proofs, each on its own context: plonk.ProverPool.)
     for (int k = 0; k < nb; k += group) {
         const int g = nb - k < group ? nb - k : group;
-        msm_enqueue_group(ctx, s->scratch, ctx->stream, scalars + k, g, n, base_offset, host_pt);
+        msm_enqueue_group(ctx, s, ctx->stream, scalars + k, g, n, base_offset, host_pt);
         PK_CUDA(cudaStreamSynchronize(ctx->stream));
         for (int j = 0; j < g; ++j) out[k + j] = host_pt[j].to_affine();
     }
@@ -715,10 +724,10 @@ void msm_run_batch_dev(pk_ctx* ctx, const fr_t* const* scalars, int nb, uint64_t
         PK_CUDA(cudaMemsetAsync(out_dev, 0, nb * sizeof(g1_xyzz_t), ctx->stream));  // ZZ = 0: infinity
         return;
     }
-    const int group = s->scratch.max_sets;
+    const int group = s->scratch->max_sets;
     for (int k = 0; k < nb; k += group) {
         const int g = nb - k < group ? nb - k : group;
-        msm_enqueue_group(ctx, s->scratch, ctx->stream, scalars + k, g, n, base_offset, out_dev + k);
+        msm_enqueue_group(ctx, s, ctx->stream, scalars + k, g, n, base_offset, out_dev + k);
     }
 }
 

@@ -36,15 +36,19 @@ struct SrsTables {
     int lo_bits = 0, hi_bits = 0;  // bucket id = hi * 2^lo_bits + lo (two-level bucket reduction)
     DevBuf<g1_affine_t> table;   // [W][n]: table[w][i] = 2^(c*w) * base_i, affine, Montgomery form
 
-    MsmScratch scratch;
+    MsmScratch own_scratch;
+    MsmScratch* scratch = &own_scratch;  // the Lagrange-form tables borrow the monomial tables' working set when the plans match
     uint32_t chunk1 = 64;                // entries per thread at level 1 (for a single scalar set)
 };
 
-// loads n affine bases (canonical limbs, host) and builds the window tables
-void srs_load(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits);
+// loads n affine bases (canonical limbs, host) and builds the window tables: the monomial-form key (ctx->srs) or, with
+// lagrange = true, the Lagrange-form key of the same size (ctx->srs_lagrange; commit_using_values, src/plonk.rs:138-146)
+void srs_load(pk_ctx* ctx, const uint64_t* bases_xy, uint64_t n, int window_bits, bool lagrange = false);
 // out[k] = sum_i scalars[k][i] * base[base_offset + i] for k < nb <= MSM_MAX_BATCH; scalars on the device in
 // Montgomery form; results affine (Montgomery) on the host.  One pass over the shared kernels for the whole batch.
-void msm_run_batch(pk_ctx* ctx, const fr_t* const* scalars, int nb, uint64_t n, uint64_t base_offset, g1_affine_t* out);
+// `tables`: which resident key (default ctx->srs)
+void msm_run_batch(pk_ctx* ctx, const fr_t* const* scalars, int nb, uint64_t n, uint64_t base_offset, g1_affine_t* out,
+                   SrsTables* tables = nullptr);
 // same, but the nb XYZZ sums stay on the device (out_dev[k]) and nothing is synchronised: the partial sums of a sharded
 // commitment, which are all-gathered and folded before they are normalised
 void msm_run_batch_dev(pk_ctx* ctx, const fr_t* const* scalars, int nb, uint64_t n, uint64_t base_offset, g1_xyzz_t* out_dev);

@@ -27,6 +27,7 @@ struct pk_setup {
     uint32_t num_inputs = 0;
     uint64_t nvars = 0;
     bool have_witness = false;
+    bool use_lagrange = false;   // wire commitments from VALUES with the Lagrange-form key (bellman prove, src/plonk.rs:138-146)
     DevBuf<uint32_t> wire_idx;   // [4][n]
     DevBuf<fr_t> sel_vals;       // [7][n] natural order (gate check)
     DevBuf<fr_t> sigma_vals;     // [4][n] natural order (grand product)
@@ -218,7 +219,16 @@ void prove(pk_ctx* ctx, pk_setup* s, const uint64_t* var_values, uint64_t nvars,
             ntt_inverse_from_bitrev(ctx, s->w_br.p + c * n, s->w_coef.p + c * n, log_n);
             polys[c] = s->w_coef.p + c * n;
         }
-        msm_run_batch(ctx, polys, 4, n, 0, Cw);  // the 4 wire commitments share one pass over the MSM kernels
+        if (s->use_lagrange) {
+            // commit_using_values: sum_i w(omega^i) [L_i(tau)] G over the witness values themselves (natural order)
+            PK_REQUIRE(ctx->srs_lagrange && ctx->srs_lagrange->n == n, PK_ERR_DEGREE_TOO_LARGE,
+                       "no Lagrange-form key of the circuit's domain size is loaded");
+            const fr_t* vals[4];
+            for (int c = 0; c < 4; ++c) vals[c] = s->w_nat.p + c * n;
+            msm_run_batch(ctx, vals, 4, n, 0, Cw, ctx->srs_lagrange);
+        } else {
+            msm_run_batch(ctx, polys, 4, n, 0, Cw);  // the 4 wire commitments share one pass over the MSM kernels
+        }
         for (int c = 0; c < 4; ++c) tr_commit_g1(tr, Cw[c]);
     }
     const fr_t beta = tr_challenge(tr), gamma = tr_challenge(tr);
@@ -388,6 +398,12 @@ void prove(pk_ctx* ctx, pk_setup* s, const uint64_t* var_values, uint64_t nvars,
 }  // namespace pk
 
 namespace pk {
+void setup_use_lagrange(pk_ctx* ctx, pk_setup* s, bool on) {
+    if (on)
+        PK_REQUIRE(ctx->srs_lagrange && ctx->srs_lagrange->n == s->n, PK_ERR_DEGREE_TOO_LARGE,
+                   "no Lagrange-form key of the circuit's domain size is loaded (pk_srs_load_g1_lagrange)");
+    s->use_lagrange = on;
+}
 void setup_free(pk_setup* s) {
     if (!s) return;
     if (s->ctx) { cudaSetDevice(s->ctx->device); cudaStreamSynchronize(s->ctx->stream); }

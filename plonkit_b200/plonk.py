@@ -73,6 +73,10 @@ class SetupForProver:
             raise ValueError("setup power of two is not in the correct range")
         if key_monomial_form.size < asm.n:
             raise SynthesisError(2, "monomial SRS holds %d bases, the circuit needs %d" % (key_monomial_form.size, asm.n))
+        if key_lagrange_form is not None and key_lagrange_form.size != asm.n:
+            # L_i(tau) depends on the domain: a Lagrange key serves exactly one domain size (dump-lagrange sizes it from the
+            # circuit, src/bin/main.rs:360-381)
+            raise SynthesisError(2, "Lagrange SRS holds %d bases, the circuit's domain has %d points" % (key_lagrange_form.size, asm.n))
         self.ctx = ctx or default_context()
         self.key_monomial_form = key_monomial_form
         self.key_lagrange_form = key_lagrange_form
@@ -96,6 +100,10 @@ class SetupForProver:
         tag = (self.key_monomial_form.token, self.n)
         if self.ctx.srs_tag != tag:
             self.ctx.srs_load_g1(self.key_monomial_form.g1_bases[:self.n], tag=tag)
+        if self.key_lagrange_form is not None:
+            ltag = (self.key_lagrange_form.token, self.n)
+            if self.ctx.lagrange_tag != ltag:
+                self.ctx.srs_load_g1_lagrange(self.key_lagrange_form.g1_bases, tag=ltag)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -131,7 +139,11 @@ class SetupForProver:
         self.ctx._check(self.ctx._lib.pk_witness_upload(self.ctx._h, self._h, vals.ctypes.data, vals.shape[0]))
 
     def prove(self, circuit=None, transcript: str = "keccak") -> Proof:
-        """SetupForProver::prove.  circuit=None proves the witness uploaded with upload_witness (device-resident input)."""
+        """SetupForProver::prove.  circuit=None proves the witness uploaded with upload_witness (device-resident input).
+        With a `key_lagrange_form` the wire commitments are taken from the witness values (bellman `prove`, src/plonk.rs:138-146;
+        only 'keccak' exists on that branch, as in the reference) — the proof bytes are the same."""
+        if self.key_lagrange_form is not None and transcript != "keccak":
+            raise NotImplementedError("invalid transcript. use 'keccak'")  # src/plonk.rs:147-149: unimplemented!()
         if transcript == "rescue":
             raise NotImplementedError("the rescue transcript has no in-tree fixture (SURVEY.md §0 item 5); use 'keccak'")
         if transcript != "keccak":
@@ -147,6 +159,7 @@ class SetupForProver:
             nvars = vals.shape[0]
         pr = _lib.PkProof()
         inputs = np.zeros((max(self.num_inputs, 1), 4), dtype=np.uint64)
+        self.ctx._check(self.ctx._lib.pk_setup_use_lagrange(self.ctx._h, self._h, int(self.key_lagrange_form is not None)))
         self.ctx._check(self.ctx._lib.pk_prove(self.ctx._h, self._h, vals.ctypes.data if vals is not None else None, nvars,
                                                ctypes.byref(pr), inputs.ctypes.data))
         return _proof_from_struct(pr, inputs[:self.num_inputs])

@@ -40,6 +40,45 @@ def test_lagrange_srs_matches_oracle(ctx, orc, simple_circuit, simple_key):
     assert (crs.g1_bases == orc.ec_intt(simple_key.g1_bases[:8])).all()
 
 
+def test_prove_with_lagrange_key_gives_the_same_bytes(ctx, orc, simple_circuit, simple_key):
+    """`plonkit prove -l <lagrange key>` (src/plonk.rs:138-146, CI: integration-test.yml:127-133): wire commitments from
+    VALUES with the Lagrange-form key made by dump-lagrange == the monomial path == the reference's proof.bin; a key of the
+    wrong domain size and a non-keccak transcript are refused as in the reference."""
+    from plonkit_b200.reader import Crs
+    base = plonk.SetupForProver.prepare_setup_for_prover(simple_circuit, simple_key, None, ctx=ctx)
+    lag = base.get_srs_lagrange_form_from_monomial_form()
+    setup = plonk.SetupForProver.prepare_setup_for_prover(simple_circuit, simple_key, lag, ctx=ctx)
+    assert setup.prove(simple_circuit, "keccak").to_bytes() == open(os.path.join(SIMPLE, "proof.bin"), "rb").read()
+    with pytest.raises(NotImplementedError):
+        setup.prove(simple_circuit, "rescue")
+    with pytest.raises(_lib.SynthesisError):
+        plonk.SetupForProver.prepare_setup_for_prover(simple_circuit, simple_key, Crs(simple_key.g1_bases[:16], b"", "lagrange"), ctx=ctx)
+    # a larger, witness-heavy circuit: values path == coefficient path == oracle; a setup WITHOUT the Lagrange key on the same
+    # context afterwards still takes the monomial path
+    asm = synth.random_gate_assembly(12, seed=77, num_inputs=2)
+    srs = orc.srs_gen(asm.n, 42, threads=8)
+    key = Crs(srs)
+    mono = plonk.SetupForProver.prepare_setup_for_prover(asm, key, None, ctx=ctx)
+    lag2 = mono.get_srs_lagrange_form_from_monomial_form()
+    want = orc.prove(asm.n, asm.num_inputs, asm.wire_idx, asm.var_values, asm.selectors, srs, threads=8)
+    both = plonk.SetupForProver.prepare_setup_for_prover(asm, key, lag2, ctx=ctx)
+    assert both.prove(asm).to_bytes() == want
+    assert mono.prove(asm).to_bytes() == want
+    for s_ in (base, setup, mono, both):
+        s_.close()
+
+
+def test_cli_prove_with_lagrange_key(tmp_path):
+    """dump-lagrange then prove -l (test/test_poseidon_plonk.sh flow on the `simple` circuit): same proof.bin"""
+    from plonkit_b200 import __main__ as cli
+    key, circ = os.path.join(SIMPLE, "setup_2^10.key"), os.path.join(SIMPLE, "circuit.r1cs.json")
+    lag = tmp_path / "lagrange.key"
+    cli.main(["dump-lagrange", "-m", key, "-l", str(lag), "-c", circ])
+    cli.main(["prove", "-m", key, "-l", str(lag), "-c", circ, "-w", os.path.join(SIMPLE, "witness.json"), "-p", str(tmp_path / "proof.bin"),
+              "-j", str(tmp_path / "proof.json"), "-i", str(tmp_path / "public.json")])
+    assert (tmp_path / "proof.bin").read_bytes() == open(os.path.join(SIMPLE, "proof.bin"), "rb").read()
+
+
 def test_poseidon_shaped_golden_fixture(ctx, simple_key):
     asm = synth.poseidon_chain_assembly(9)
     setup = plonk.SetupForProver.prepare_setup_for_prover(asm, simple_key, None, ctx=ctx)
