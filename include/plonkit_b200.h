@@ -134,13 +134,32 @@ typedef struct pk_proof {
     uint64_t opening_at_z_proof[8];
     uint64_t opening_at_z_omega_proof[8];
     uint64_t challenges[5][4]; /* beta, gamma, alpha, z, v — not part of proof.bin; exposed for known-answer tests */
+    /* only for setups made with pk_setup_create_gated (two gate types): the gate selectors s_main, s_resc at z */
+    uint64_t num_gate_selectors;
+    uint64_t gate_selectors_at_z[2][4];
 } pk_proof;
+
+/* Gate tables of the recursive prover's shape (src/recursive/mod.rs:111-127: a ProvingAssembly over
+ * Width4MainGateWithDNext + the Rescue x^5 custom gate, bellman better_better_cs): the same tables plus a gate type per
+ * row — 0: main gate (selectors apply), 1: Rescue x^5 gate (a = x, b = x^2, c = x^4, d = x^5; selectors ignored).
+ * BYTE PARITY UNPINNED: that prover and its proof layout are not in the reference tree; DESIGN.md section 9 states the
+ * protocol this library runs for it. */
+typedef struct pk_assembly_gated {
+    pk_assembly base;
+    const uint8_t* gate_type;   /* [n] */
+} pk_assembly_gated;
 
 /* SetupForProver::prepare_setup_for_prover (src/plonk.rs:97-119) after synthesis: uploads the gate tables, builds the
  * copy permutation, the 11 setup polynomials (iNTT) and — unlike the reference, which recomputes them in every
  * prove call (precomputations = None, src/plonk.rs:156) — keeps their 4n coset evaluations resident.
  * Requires pk_srs_load_g1 with at least n bases. */
 int pk_setup_create(pk_ctx* ctx, const pk_assembly* assembly, pk_setup** out);
+/* The setup of the recursive prover's proving call (create_recursive_circuit_setup, src/recursive/mod.rs:120-121): 13
+ * setup polynomials (7 main-gate, the gate selectors s_main and s_resc, 4 sigma).  pk_prove on such a setup runs the
+ * two-gate-type protocol (create_proof, :127) and fills gate_selectors_at_z; pk_setup_commitments_gated returns the 13
+ * commitments in that order. */
+int pk_setup_create_gated(pk_ctx* ctx, const pk_assembly_gated* assembly, pk_setup** out);
+int pk_setup_commitments_gated(pk_ctx* ctx, pk_setup* setup, uint64_t out_xy[13][8]);
 void pk_setup_destroy(pk_setup* setup);
 /* on != 0: pk_prove commits the wires from values with the resident Lagrange-form key (which must have exactly the
  * circuit's domain size); PK_ERR_DEGREE_TOO_LARGE if none is loaded. */

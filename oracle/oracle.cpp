@@ -1038,4 +1038,359 @@ int orc_verify_trapdoor(const uint8_t* proof, uint64_t proof_len, const uint64_t
     return chk.is_inf() ? 1 : 0;
 }
 
+
+// ---------------------------------------------------------------- prover with gate selectors and a custom gate
+// PARITY UNPINNED.  recursive::prove (src/recursive/mod.rs:38-136) ends in bellman's better_better_cs
+// `create_proof::<_, RollingKeccakTranscript>` (:127) over a ProvingAssembly with TWO gate types: the width-4 main gate
+// with d_next and the Rescue x^5 custom gate, each row's type chosen by gate-selector polynomials.  That
+// prover, its proof layout and the aggregation circuit live in crates that are not in the reference tree and no fixture
+// pins their bytes, so what follows restates the ROUND STRUCTURE named in SURVEY App. D — state commitments, copy-
+// permutation grand product, per-gate quotient terms behind gate selectors on the LDE-4 coset, openings with the main gate
+// linearised — with this repository's own ordering of the proof elements.  It is checked by its own verifier below (known
+// trapdoor), not against reference bytes.
+//   identity on H:  s_main (q_a a + q_b b + q_c c + q_d d + q_m a b + q_const + q_dnext d(wX)) + PI
+//                   + s_resc (alpha (a^2 - b) + alpha^2 (b^2 - c) + alpha^3 (c a - d))
+//                   + alpha^4 (Z prod(w_i + beta k_i X + gamma) - Z(wX) prod(w_i + beta sigma_i + gamma)) + alpha^5 L_0 (Z - 1)
+//                   = t Z_H
+//   gate_type[row]: 0 = main gate, 1 = Rescue x^5 gate (a = x, b = x^2, c = x^4, d = x^5)
+// Proof bytes: App. B.2 layout with "u64 2 | s_main(z) | s_resc(z)" inserted after the sigma evaluations.
+struct orc_assembly2 {
+    orc_assembly base;
+    const uint8_t* gate_type;  // [N]
+};
+
+static void gate_selector_polys(const orc_assembly2& as, hvec<Fr>& s_main, hvec<Fr>& s_resc, int threads) {
+    const size_t N = as.base.n;
+    s_main.assign(N, Fr::zero());
+    s_resc.assign(N, Fr::zero());
+    for (size_t r = 0; r < N; ++r) (as.gate_type[r] == 1 ? s_resc : s_main)[r] = Fr::one();
+    ifft(s_main, threads);
+    ifft(s_resc, threads);
+}
+
+void orc_setup_commitments2(const orc_assembly2* as, const uint64_t* srs, uint64_t* out /* [13][8] */, int threads) {
+    init_fields();
+    const size_t N = as->base.n;
+    SetupPolys sp;
+    make_setup(as->base, sp, threads);
+    hvec<Fr> s_main, s_resc;
+    gate_selector_polys(*as, s_main, s_resc, threads);
+    hvec<G1Affine> bases = load_points(srs, N, threads);
+    for (int s = 0; s < 7; ++s) store_point(commit(sp.sel[s], bases.data(), threads), out + 8 * s);
+    store_point(commit(s_main, bases.data(), threads), out + 8 * 7);
+    store_point(commit(s_resc, bases.data(), threads), out + 8 * 8);
+    for (int c = 0; c < 4; ++c) store_point(commit(sp.sigma[c], bases.data(), threads), out + 8 * (9 + c));
+}
+
+int64_t orc_prove2(const orc_assembly2* as2, const uint64_t* srs, uint8_t* proof_out, uint64_t* challenges_out, int threads) {
+    init_fields();
+    const orc_assembly* as = &as2->base;
+    const size_t N = as->n;
+    const int log_n = log2_floor(N);
+    const size_t NI = as->num_inputs;
+    const Fr omega = omega_for(log_n);
+    hvec<Fr> om = powers(omega, N);
+    hvec<G1Affine> bases = load_points(srs, N, threads);
+    SetupPolys sp;
+    make_setup(*as, sp, threads);
+    hvec<Fr> s_main, s_resc;
+    gate_selector_polys(*as2, s_main, s_resc, threads);
+
+    hvec<Fr> vars = load_frs(as->var_values, as->nvars, threads);
+    hvec<Fr> wv[4];
+    for (int c = 0; c < 4; ++c) {
+        wv[c].resize(N);
+        for (size_t r = 0; r < N; ++r) wv[c][r] = vars[as->wire_idx[(size_t)c * N + r]];
+    }
+    hvec<Fr> selv[7];
+    for (int s = 0; s < 7; ++s) selv[s] = load_frs(as->selectors + (size_t)s * N * 4, N, threads);
+    hvec<Fr> pi_vals(N, Fr::zero());
+    for (size_t i = 0; i < NI; ++i) pi_vals[i] = wv[0][i];
+    for (size_t r = 0; r + 1 < N; ++r) {
+        if (as2->gate_type[r] == 1) {
+            if (!(wv[0][r].sqr() == wv[1][r]) || !(wv[1][r].sqr() == wv[2][r]) || !(wv[2][r] * wv[0][r] == wv[3][r])) return -1;
+        } else {
+            Fr g = selv[0][r] * wv[0][r] + selv[1][r] * wv[1][r] + selv[2][r] * wv[2][r] + selv[3][r] * wv[3][r] +
+                   selv[4][r] * wv[0][r] * wv[1][r] + selv[5][r] + selv[6][r] * wv[3][r + 1] + pi_vals[r];
+            if (!g.is_zero()) return -1;
+        }
+    }
+    Transcript tr;
+    for (size_t i = 0; i < NI; ++i) tr.update_fr(pi_vals[i]);
+    hvec<Fr> w[4];
+    G1Affine Cw[4];
+    for (int c = 0; c < 4; ++c) {
+        w[c] = wv[c];
+        ifft(w[c], threads);
+        Cw[c] = commit(w[c], bases.data(), threads);
+        tr.update_g1(Cw[c]);
+    }
+    Fr beta = tr.challenge(), gamma = tr.challenge();
+    Fr kk[4];
+    for (int c = 0; c < 4; ++c) kk[c] = Fr::from_u64(NON_RES[c]);
+    hvec<Fr> num(N), den(N);
+    for (size_t j = 0; j < N; ++j) {
+        Fr nn = Fr::one(), dd = Fr::one();
+        for (int c = 0; c < 4; ++c) {
+            nn *= wv[c][j] + beta * kk[c] * om[j] + gamma;
+            dd *= wv[c][j] + beta * sp.sigma_vals[c][j] + gamma;
+        }
+        num[j] = nn; den[j] = dd;
+    }
+    batch_inverse(den.data(), N);
+    hvec<Fr> zv(N);
+    zv[0] = Fr::one();
+    for (size_t j = 0; j + 1 < N; ++j) zv[j + 1] = zv[j] * num[j] * den[j];
+    hvec<Fr> zp = zv;
+    ifft(zp, threads);
+    G1Affine Cz = commit(zp, bases.data(), threads);
+    tr.update_g1(Cz);
+    Fr alpha = tr.challenge();
+    Fr al[6];
+    al[0] = Fr::one();
+    for (int i = 1; i < 6; ++i) al[i] = al[i - 1] * alpha;
+
+    const size_t M = 4 * N;
+    hvec<Fr> lw[4], lsel[7], lsig[4];
+    for (int c = 0; c < 4; ++c) lw[c] = lde4(w[c], threads);
+    for (int s = 0; s < 7; ++s) lsel[s] = lde4(sp.sel[s], threads);
+    for (int c = 0; c < 4; ++c) lsig[c] = lde4(sp.sigma[c], threads);
+    hvec<Fr> lz = lde4(zp, threads), lsm = lde4(s_main, threads), lsr = lde4(s_resc, threads);
+    hvec<Fr> pi_poly = pi_vals;
+    ifft(pi_poly, threads);
+    hvec<Fr> lpi = lde4(pi_poly, threads);
+    hvec<Fr> l0c(N, Fr::from_u64(N).inverse());
+    hvec<Fr> ll0 = lde4(l0c, threads);
+    Fr omega4 = omega_for(log_n + 2);
+    Fr g7 = Fr::from_u64(COSET_GEN);
+    Fr zh_inv[4];
+    {
+        Fr g7n = g7.pow_u64(N), w4n = omega4.pow_u64(N);
+        Fr x = g7n;
+        for (int i = 0; i < 4; ++i) { zh_inv[i] = (x - Fr::one()).inverse(); x *= w4n; }
+    }
+    hvec<Fr> tq(M);
+    parallel_chunks(M, threads, [&](size_t b, size_t e, int) {
+        Fr x = g7 * omega4.pow_u64(b);
+        for (size_t J = b; J < e; ++J) {
+            size_t Jn = (J + 4) % M;
+            const Fr &a = lw[0][J], &bb = lw[1][J], &c = lw[2][J], &d = lw[3][J];
+            Fr gate = lsel[0][J] * a + lsel[1][J] * bb + lsel[2][J] * c + lsel[3][J] * d + lsel[4][J] * a * bb + lsel[5][J] +
+                      lsel[6][J] * lw[3][Jn];
+            Fr resc = al[1] * (a.sqr() - bb) + al[2] * (bb.sqr() - c) + al[3] * (c * a - d);
+            Fr nn = lz[J], dd = lz[Jn];
+            for (int i = 0; i < 4; ++i) {
+                nn *= lw[i][J] + beta * kk[i] * x + gamma;
+                dd *= lw[i][J] + beta * lsig[i][J] + gamma;
+            }
+            Fr tot = lsm[J] * gate + lpi[J] + lsr[J] * resc + al[4] * (nn - dd) + al[5] * ll0[J] * (lz[J] - Fr::one());
+            tq[J] = tot * zh_inv[J % 4];
+            x *= omega4;
+        }
+    });
+    icoset_fft(tq, threads);
+    for (size_t i = M - 3; i < M; ++i) if (!tq[i].is_zero()) return -2;
+    hvec<Fr> tchunk[4];
+    G1Affine Ct[4];
+    for (int i = 0; i < 4; ++i) {
+        tchunk[i].assign(tq.begin() + i * N, tq.begin() + (i + 1) * N);
+        Ct[i] = commit(tchunk[i], bases.data(), threads);
+        tr.update_g1(Ct[i]);
+    }
+    Fr zeta = tr.challenge();
+
+    Fr zeta_omega = zeta * omega;
+    Fr wz[4], sz[3];
+    for (int c = 0; c < 4; ++c) wz[c] = eval_poly(w[c], zeta, threads);
+    Fr dzw = eval_poly(w[3], zeta_omega, threads);
+    Fr smz = eval_poly(s_main, zeta, threads), srz = eval_poly(s_resc, zeta, threads);
+    for (int c = 0; c < 3; ++c) sz[c] = eval_poly(sp.sigma[c], zeta, threads);
+    Fr zzw = eval_poly(zp, zeta_omega, threads);
+    Fr tz = eval_poly(tq, zeta, threads);
+    Fr zeta_n = zeta.pow_u64(N);
+    Fr l0z = (zeta_n - Fr::one()) * (Fr::from_u64(N) * (zeta - Fr::one())).inverse();
+    Fr zfac = al[5] * l0z, sfac = al[4] * beta * zzw;
+    {
+        Fr p = al[4];
+        for (int i = 0; i < 4; ++i) p *= wz[i] + beta * kk[i] * zeta + gamma;
+        zfac += p;
+        for (int i = 0; i < 3; ++i) sfac *= wz[i] + beta * sz[i] + gamma;
+    }
+    hvec<Fr> rp(N);
+    Fr ab = wz[0] * wz[1];
+    for (size_t i = 0; i < N; ++i)
+        rp[i] = smz * (sp.sel[5][i] + sp.sel[0][i] * wz[0] + sp.sel[1][i] * wz[1] + sp.sel[2][i] * wz[2] + sp.sel[3][i] * wz[3] +
+                       sp.sel[4][i] * ab + sp.sel[6][i] * dzw) +
+                zp[i] * zfac - sp.sigma[3][i] * sfac;
+    Fr rz = eval_poly(rp, zeta, threads);
+    for (int c = 0; c < 4; ++c) tr.update_fr(wz[c]);
+    tr.update_fr(dzw);
+    tr.update_fr(smz);
+    tr.update_fr(srz);
+    for (int c = 0; c < 3; ++c) tr.update_fr(sz[c]);
+    tr.update_fr(tz);
+    tr.update_fr(rz);
+    tr.update_fr(zzw);
+    Fr v = tr.challenge();
+
+    hvec<Fr> agg(N), agg2(N);
+    Fr vp[13];
+    vp[0] = Fr::one();
+    for (int i = 1; i <= 12; ++i) vp[i] = vp[i - 1] * v;
+    Fr zn2 = zeta_n.sqr(), zn3 = zn2 * zeta_n;
+    for (size_t i = 0; i < N; ++i) {
+        agg[i] = tchunk[0][i] + zeta_n * tchunk[1][i] + zn2 * tchunk[2][i] + zn3 * tchunk[3][i] + vp[1] * rp[i] + vp[2] * w[0][i] +
+                 vp[3] * w[1][i] + vp[4] * w[2][i] + vp[5] * w[3][i] + vp[6] * s_main[i] + vp[7] * s_resc[i] +
+                 vp[8] * sp.sigma[0][i] + vp[9] * sp.sigma[1][i] + vp[10] * sp.sigma[2][i];
+        agg2[i] = vp[11] * zp[i] + vp[12] * w[3][i];
+    }
+    hvec<Fr> q1 = divide_by_linear(agg, zeta), q2 = divide_by_linear(agg2, zeta_omega);
+    G1Affine W1 = commit(q1, bases.data(), threads), W2 = commit(q2, bases.data(), threads);
+    if (challenges_out) {
+        beta.to_canonical(challenges_out); gamma.to_canonical(challenges_out + 4); alpha.to_canonical(challenges_out + 8);
+        zeta.to_canonical(challenges_out + 12); v.to_canonical(challenges_out + 16);
+    }
+    uint8_t* p = proof_out;
+    write_u64_be(N - 1, p); p += 8;
+    write_u64_be(NI, p); p += 8;
+    for (size_t i = 0; i < NI; ++i) { write_fr_be(pi_vals[i], p); p += 32; }
+    write_u64_be(4, p); p += 8;
+    for (int c = 0; c < 4; ++c) { write_g1_be(Cw[c], p); p += 64; }
+    write_g1_be(Cz, p); p += 64;
+    write_u64_be(4, p); p += 8;
+    for (int c = 0; c < 4; ++c) { write_g1_be(Ct[c], p); p += 64; }
+    write_u64_be(4, p); p += 8;
+    for (int c = 0; c < 4; ++c) { write_fr_be(wz[c], p); p += 32; }
+    write_u64_be(1, p); p += 8;
+    write_fr_be(dzw, p); p += 32;
+    write_fr_be(zzw, p); p += 32;
+    write_fr_be(tz, p); p += 32;
+    write_fr_be(rz, p); p += 32;
+    write_u64_be(3, p); p += 8;
+    for (int c = 0; c < 3; ++c) { write_fr_be(sz[c], p); p += 32; }
+    write_u64_be(2, p); p += 8;
+    write_fr_be(smz, p); p += 32;
+    write_fr_be(srz, p); p += 32;
+    write_g1_be(W1, p); p += 64;
+    write_g1_be(W2, p); p += 64;
+    return (int64_t)(p - proof_out);
+}
+
+// verifier of orc_prove2's proofs under a known trapdoor; vk_commitments [13][8]: 7 main-gate setup polynomials, s_main,
+// s_resc, 4 sigma (order of orc_setup_commitments2).  1 = accept, 0 = reject, negative = malformed.
+int orc_verify_trapdoor2(const uint8_t* proof, uint64_t proof_len, const uint64_t* vk_commitments, uint64_t tau) {
+    init_fields();
+    if (proof_len < 16) return -1;
+    const uint8_t* p = proof;
+    u64 n_gates = read_u64_be(p); p += 8;
+    u64 ni = read_u64_be(p); p += 8;
+    if (proof_len != 16 + 32 * ni + 1096 + 72) return -1;
+    size_t N = n_gates + 1;
+    int log_n = log2_floor(N);
+    if ((size_t(1) << log_n) != N) return -1;
+    std::vector<Fr> inputs(ni);
+    for (u64 i = 0; i < ni; ++i) { inputs[i] = read_fr_be(p); p += 32; }
+    p += 8;
+    G1Affine Cw[4]; for (int i = 0; i < 4; ++i) { Cw[i] = read_g1_be(p); p += 64; }
+    G1Affine Cz = read_g1_be(p); p += 64;
+    p += 8;
+    G1Affine Ct[4]; for (int i = 0; i < 4; ++i) { Ct[i] = read_g1_be(p); p += 64; }
+    p += 8;
+    Fr wz[4]; for (int i = 0; i < 4; ++i) { wz[i] = read_fr_be(p); p += 32; }
+    p += 8;
+    Fr dzw = read_fr_be(p); p += 32;
+    Fr zzw = read_fr_be(p); p += 32;
+    Fr tz = read_fr_be(p); p += 32;
+    Fr rz = read_fr_be(p); p += 32;
+    p += 8;
+    Fr sz[3]; for (int i = 0; i < 3; ++i) { sz[i] = read_fr_be(p); p += 32; }
+    p += 8;
+    Fr smz = read_fr_be(p); p += 32;
+    Fr srz = read_fr_be(p); p += 32;
+    G1Affine W1 = read_g1_be(p); p += 64;
+    G1Affine W2 = read_g1_be(p); p += 64;
+    hvec<G1Affine> vk = load_points(vk_commitments, 13, 1);
+    for (auto& q : vk) if (!q.on_curve()) return -1;
+    G1Affine all[] = {Cw[0], Cw[1], Cw[2], Cw[3], Cz, Ct[0], Ct[1], Ct[2], Ct[3], W1, W2};
+    for (auto& q : all) if (!q.on_curve()) return 0;
+
+    Transcript tr;
+    for (u64 i = 0; i < ni; ++i) tr.update_fr(inputs[i]);
+    for (int i = 0; i < 4; ++i) tr.update_g1(Cw[i]);
+    Fr beta = tr.challenge(), gamma = tr.challenge();
+    tr.update_g1(Cz);
+    Fr alpha = tr.challenge();
+    for (int i = 0; i < 4; ++i) tr.update_g1(Ct[i]);
+    Fr zeta = tr.challenge();
+    for (int i = 0; i < 4; ++i) tr.update_fr(wz[i]);
+    tr.update_fr(dzw); tr.update_fr(smz); tr.update_fr(srz);
+    for (int i = 0; i < 3; ++i) tr.update_fr(sz[i]);
+    tr.update_fr(tz); tr.update_fr(rz); tr.update_fr(zzw);
+    Fr v = tr.challenge();
+    tr.update_g1(W1); tr.update_g1(W2);
+    Fr u = tr.challenge();
+    Fr al[6];
+    al[0] = Fr::one();
+    for (int i = 1; i < 6; ++i) al[i] = al[i - 1] * alpha;
+
+    Fr omega = omega_for(log_n);
+    Fr zeta_n = zeta.pow_u64(N);
+    Fr zh = zeta_n - Fr::one();
+    if (zh.is_zero()) return 0;
+    Fr n_inv = Fr::from_u64(N).inverse();
+    auto lagrange = [&](u64 i) { Fr wi = omega.pow_u64(i); return wi * zh * n_inv * (zeta - wi).inverse(); };
+    Fr l0 = lagrange(0);
+    Fr kk[4]; for (int c = 0; c < 4; ++c) kk[c] = Fr::from_u64(NON_RES[c]);
+    // quotient identity at zeta
+    Fr rhs = rz;
+    for (u64 i = 0; i < ni; ++i) rhs += lagrange(i) * inputs[i];
+    rhs += srz * (al[1] * (wz[0].sqr() - wz[1]) + al[2] * (wz[1].sqr() - wz[2]) + al[3] * (wz[2] * wz[0] - wz[3]));
+    Fr zpart = zzw * al[4];
+    for (int i = 0; i < 3; ++i) zpart *= sz[i] * beta + gamma + wz[i];
+    zpart *= gamma + wz[3];
+    rhs -= zpart;
+    rhs -= l0 * al[5];
+    if (!(zh * tz == rhs)) return 0;
+    // [r]
+    G1 main = G1::from_affine(vk[5]);
+    for (int i = 0; i < 4; ++i) main = main.add(pmul(vk[i], wz[i]));
+    main = main.add(pmul(vk[4], wz[0] * wz[1]));
+    main = main.add(pmul(vk[6], dzw));
+    u64 smc[4]; smz.to_canonical(smc);
+    G1 r_com = main.mul(smc);
+    Fr gpz = al[4];
+    for (int i = 0; i < 4; ++i) gpz *= zeta * kk[i] * beta + gamma + wz[i];
+    gpz += l0 * al[5];
+    Fr lastp = beta * zzw * al[4];
+    for (int i = 0; i < 3; ++i) lastp *= beta * sz[i] + gamma + wz[i];
+    r_com = r_com.add(pmul(Cz, gpz)).add(pmul(vk[12], lastp).neg());
+    // batched opening
+    Fr vp[13];
+    vp[0] = Fr::one();
+    for (int i = 1; i <= 12; ++i) vp[i] = vp[i - 1] * v;
+    G1 F = G1::from_affine(Ct[0]);
+    Fr zp = Fr::one();
+    for (int i = 1; i < 4; ++i) { zp *= zeta_n; F = F.add(pmul(Ct[i], zp)); }
+    u64 vc[4]; v.to_canonical(vc);
+    F = F.add(r_com.mul(vc));
+    for (int i = 0; i < 4; ++i) F = F.add(pmul(Cw[i], vp[2 + i]));
+    F = F.add(pmul(vk[7], vp[6])).add(pmul(vk[8], vp[7]));
+    for (int i = 0; i < 3; ++i) F = F.add(pmul(vk[9 + i], vp[8 + i]));
+    Fr E = tz + v * rz;
+    for (int i = 0; i < 4; ++i) E += wz[i] * vp[2 + i];
+    E += smz * vp[6] + srz * vp[7];
+    for (int i = 0; i < 3; ++i) E += sz[i] * vp[8 + i];
+    G1 F2 = pmul(Cz, vp[11]).add(pmul(Cw[3], vp[12]));
+    Fr E2 = zzw * vp[11] + dzw * vp[12];
+    // (F - E G + zeta W1) + u (F2 - E2 G + zeta omega W2) == tau (W1 + u W2)
+    G1 lhs = F.add(pmul(G1Affine::generator(), E).neg()).add(pmul(W1, zeta));
+    G1 lhs2 = F2.add(pmul(G1Affine::generator(), E2).neg()).add(pmul(W2, zeta * omega));
+    u64 uc[4]; u.to_canonical(uc);
+    lhs = lhs.add(lhs2.mul(uc));
+    G1 rhs_pt = G1::from_affine(W1).add(pmul(W2, u));
+    u64 tc[4] = {tau, 0, 0, 0};
+    G1 chk = lhs.add(rhs_pt.mul(tc).neg());
+    return chk.is_inf() ? 1 : 0;
+}
+
 }  // extern "C"

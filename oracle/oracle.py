@@ -39,6 +39,10 @@ class Assembly(ctypes.Structure):
     ]
 
 
+class Assembly2(ctypes.Structure):
+    _fields_ = [("base", Assembly), ("gate_type", ctypes.c_void_p)]
+
+
 def lib():
     global _LIB
     if _LIB is None:
@@ -49,6 +53,8 @@ def lib():
         _LIB.orc_prove.restype = ctypes.c_int64
         _LIB.orc_on_curve.restype = ctypes.c_int
         _LIB.orc_verify_trapdoor.restype = ctypes.c_int
+        _LIB.orc_prove2.restype = ctypes.c_int64
+        _LIB.orc_verify_trapdoor2.restype = ctypes.c_int
         _LIB.orc_init()
     return _LIB
 
@@ -250,6 +256,46 @@ def verify_trapdoor(proof_bytes: bytes, vk_commitments, tau=42) -> bool:
     """contrib/template.sol verifier with the pairing check replaced by the G1 identity A + tau*B == 0 (known tau)."""
     vk = np.ascontiguousarray(vk_commitments, dtype=np.uint64).reshape(11, 8)
     rc = lib().orc_verify_trapdoor(proof_bytes, ctypes.c_uint64(len(proof_bytes)), _p(vk), ctypes.c_uint64(tau))
+    if rc < 0:
+        raise ValueError("malformed proof / vk")
+    return rc == 1
+
+
+# ---- prover with gate selectors and the Rescue x^5 custom gate (oracle.cpp orc_prove2; PARITY UNPINNED, see there)
+def _assembly2(n, num_inputs, wire_idx, var_values, selectors, gate_type):
+    a, keep = _assembly(n, num_inputs, wire_idx, var_values, selectors)
+    gt = np.ascontiguousarray(gate_type, dtype=np.uint8).reshape(n)
+    a2 = Assembly2()
+    a2.base = a
+    a2.gate_type = gt.ctypes.data
+    return a2, keep + [gt]
+
+
+def setup_commitments2(n, num_inputs, wire_idx, selectors, gate_type, srs, nvars=None, threads=1):
+    a2, keep = _assembly2(n, num_inputs, wire_idx, None, selectors, gate_type)
+    if nvars is not None:
+        a2.base.nvars = nvars
+    srs = np.ascontiguousarray(srs, dtype=np.uint64).reshape(-1, 8)
+    out = np.zeros((13, 8), dtype=np.uint64)
+    lib().orc_setup_commitments2(ctypes.byref(a2), _p(srs), _p(out), threads)
+    return out
+
+
+def prove2(n, num_inputs, wire_idx, var_values, selectors, gate_type, srs, threads=1):
+    a2, keep = _assembly2(n, num_inputs, wire_idx, var_values, selectors, gate_type)
+    srs = np.ascontiguousarray(srs, dtype=np.uint64).reshape(-1, 8)
+    assert srs.shape[0] >= n
+    buf = ctypes.create_string_buffer(16 + 32 * num_inputs + 1096 + 72 + 64)
+    ch = np.zeros((5, 4), dtype=np.uint64)
+    ln = lib().orc_prove2(ctypes.byref(a2), _p(srs), buf, _p(ch), threads)
+    if ln < 0:
+        raise RuntimeError({-1: "circuit not satisfied", -2: "quotient is not a polynomial"}.get(ln, "oracle error %d" % ln))
+    return buf.raw[:ln]
+
+
+def verify_trapdoor2(proof_bytes: bytes, vk_commitments, tau=42) -> bool:
+    vk = np.ascontiguousarray(vk_commitments, dtype=np.uint64).reshape(13, 8)
+    rc = lib().orc_verify_trapdoor2(proof_bytes, ctypes.c_uint64(len(proof_bytes)), _p(vk), ctypes.c_uint64(tau))
     if rc < 0:
         raise ValueError("malformed proof / vk")
     return rc == 1

@@ -25,7 +25,7 @@ FMT_CANONICAL, FMT_MONTGOMERY = 0, 1
 
 EXPORTS = [
     "pk_create", "pk_destroy", "pk_last_error", "pk_constants", "pk_srs_load_g1", "pk_srs_load_g1_lagrange", "pk_setup_use_lagrange",
-    "pk_srs_gen", "pk_ntt", "pk_lde4",
+    "pk_srs_gen", "pk_setup_create_gated", "pk_setup_commitments_gated", "pk_ntt", "pk_lde4",
     "pk_msm_g1", "pk_ec_intt_g1", "pk_setup_create", "pk_setup_destroy", "pk_setup_commitments", "pk_witness_upload",
     "pk_prove", "pk_profile_enable", "pk_profile_reset", "pk_profile_get", "pk_bench_ntt", "pk_bench_msm",
     "pk_bench_fieldmul", "pk_timer_begin", "pk_timer_end", "pk_g1_sum", "pk_dev_fr_convert", "pk_dev_ntt_rows",
@@ -69,7 +69,13 @@ class PkProof(ctypes.Structure):
         ("opening_at_z_proof", ctypes.c_uint64 * 8),
         ("opening_at_z_omega_proof", ctypes.c_uint64 * 8),
         ("challenges", ctypes.c_uint64 * 20),
+        ("num_gate_selectors", ctypes.c_uint64),
+        ("gate_selectors_at_z", ctypes.c_uint64 * 8),
     ]
+
+
+class PkAssemblyGated(ctypes.Structure):
+    _fields_ = [("base", PkAssembly), ("gate_type", ctypes.c_void_p)]
 
 
 class PkProfile(ctypes.Structure):
@@ -111,6 +117,8 @@ def load():
     lib.pk_setup_create.argtypes = [vp, ctypes.POINTER(PkAssembly), ctypes.POINTER(vp)]
     lib.pk_setup_destroy.argtypes = [vp]
     lib.pk_setup_destroy.restype = None
+    lib.pk_setup_create_gated.argtypes = [vp, ctypes.POINTER(PkAssemblyGated), ctypes.POINTER(vp)]
+    lib.pk_setup_commitments_gated.argtypes = [vp, vp, vp]
     lib.pk_setup_commitments.argtypes = [vp, vp, vp]
     lib.pk_witness_upload.argtypes = [vp, vp, vp, u64]
     lib.pk_prove.argtypes = [vp, vp, vp, u64, ctypes.POINTER(PkProof), vp]

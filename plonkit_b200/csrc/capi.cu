@@ -14,6 +14,8 @@ struct pk_comm_group { pk::LocalGroup g; explicit pk_comm_group(int w) : g(w) {}
 namespace pk {
 void setup_create(pk_ctx* ctx, const pk_assembly* as, pk_setup** out);
 void setup_commitments(pk_ctx* ctx, pk_setup* s, uint64_t out_xy[11][8]);
+void setup_create_gated(pk_ctx* ctx, const pk_assembly_gated* as, pk_setup** out);
+void setup_commitments_gated(pk_ctx* ctx, pk_setup* s, uint64_t out_xy[13][8]);
 void witness_upload(pk_ctx* ctx, pk_setup* s, const uint64_t* var_values, uint64_t nvars);
 void prove(pk_ctx* ctx, pk_setup* s, const uint64_t* var_values, uint64_t nvars, pk_proof* proof, uint64_t* inputs_out);
 void setup_free(pk_setup* s);
@@ -380,6 +382,17 @@ int pk_ec_intt_g1(pk_ctx* ctx, uint32_t log_n, uint64_t* out_xy) {
 int pk_setup_create(pk_ctx* ctx, const pk_assembly* assembly, pk_setup** out) {
     PK_API_BEGIN(ctx)
     setup_create(ctx, assembly, out);
+    PK_API_END(ctx)
+}
+int pk_setup_create_gated(pk_ctx* ctx, const pk_assembly_gated* assembly, pk_setup** out) {
+    PK_API_BEGIN(ctx)
+    setup_create_gated(ctx, assembly, out);
+    PK_API_END(ctx)
+}
+int pk_setup_commitments_gated(pk_ctx* ctx, pk_setup* setup, uint64_t out_xy[13][8]) {
+    PK_API_BEGIN(ctx)
+    PK_REQUIRE(setup != nullptr && out_xy != nullptr, PK_ERR_INVALID, "null argument");
+    setup_commitments_gated(ctx, setup, out_xy);
     PK_API_END(ctx)
 }
 void pk_setup_destroy(pk_setup* setup) { setup_free(setup); }

@@ -1,9 +1,8 @@
 // Scalar multiplication k * P for the EC (i)NTT and the SRS generator, with the GLV
 // endomorphism of BN254: k = k1 + k2 * LAMBDA (|k1|, |k2| < 2^128) and phi(P) = (BETA x, y) = LAMBDA * P, so
 //     k * P = k1 * P + k2 * phi(P)
-// runs as ONE interleaved double-and-add over 128 bits with the table {P, phi(P), P + phi(P)}: ~128 doublings and ~97
-// additions instead of 254 and ~127 (2.5 K vs 4.1 K field products).  bellman's `mul_assign` walks all 254 bits; the
-// result is the same group element either way.
+// runs over ~128 bits instead of 254.  bellman's `mul_assign` walks all 254 bits; the result is the same group element
+// either way.
 #pragma once
 #include "ec.cuh"
 #include "glv_constants.cuh"
@@ -78,8 +77,45 @@ PK_HD void decompose(const uint32_t* k, uint32_t* k1, bool& neg1, uint32_t* k2, 
 
 }  // namespace glv
 
-// k * P for a canonical scalar k < r (any XYZZ point P, infinity included)
+// k * P for a canonical scalar k < r (any XYZZ point P, infinity included).
+// GLV split, then a JOINT FIXED 2-BIT WINDOW over the two ~128-bit halves: the table holds a P1 + b P2 for a, b in 0..3
+// (P1 = +-P, P2 = +-phi(P); 15 points, built with 2 doublings and 11 additions) and every window costs two doublings and
+// ONE addition.  65 windows: 130 doublings + 65 additions + the table = ~2.25 K field products, and — what matters on a
+// SIMT machine — the schedule is the same for every lane: the bit-by-bit version below executes its addition in almost
+// every iteration of a warp (any lane with a set bit pays for all), ~3.0 K products of warp time per multiplication.
 PK_HD g1_xyzz_t scalar_mul(const g1_xyzz_t& P, const fr_t& k_canonical) {
+    if (P.is_inf() || k_canonical.is_zero()) return g1_xyzz_t::infinity();
+    uint32_t k1[5], k2[5];
+    bool n1, n2;
+    glv::decompose(k_canonical.v, k1, n1, k2, n2);
+    g1_xyzz_t T[16];
+    T[0] = g1_xyzz_t::infinity();
+    T[1] = n1 ? P.neg() : P;
+    fq_t beta;
+    for (int i = 0; i < 8; ++i) beta.v[i] = glvc::BETA_MONT(i);
+    T[4] = P;
+    T[4].X = P.X * beta;                 // phi(P): x = X / ZZ is scaled by beta
+    if (n2) T[4] = T[4].neg();
+    T[2] = T[1].dbl();
+    T[3] = T[2].add(T[1]);
+    T[8] = T[4].dbl();
+    T[12] = T[8].add(T[4]);
+    for (int b = 1; b < 4; ++b)
+        for (int a = 1; a < 4; ++a) T[a + 4 * b] = T[a].add(T[4 * b]);
+    g1_xyzz_t r = g1_xyzz_t::infinity();
+    for (int w = 64; w >= 0; --w) {
+        r = r.dbl().dbl();
+        const int bit = 2 * w;
+        const uint32_t a = (k1[bit >> 5] >> (bit & 31)) & 3u, b = (k2[bit >> 5] >> (bit & 31)) & 3u;
+        const uint32_t idx = a | (b << 2);
+        if (idx) r = r.add(T[idx]);
+    }
+    return r;
+}
+
+// the same product by one interleaved double-and-add over the 130 bits of the two halves with the table
+// {P1, P2, P1 + P2}: fewer field products on paper (~2.5 K), but data-dependent per lane; kept as a cross-check
+PK_HD g1_xyzz_t scalar_mul_bitwise(const g1_xyzz_t& P, const fr_t& k_canonical) {
     if (P.is_inf() || k_canonical.is_zero()) return g1_xyzz_t::infinity();
     uint32_t k1[5], k2[5];
     bool n1, n2;
@@ -89,7 +125,7 @@ PK_HD g1_xyzz_t scalar_mul(const g1_xyzz_t& P, const fr_t& k_canonical) {
     fq_t beta;
     for (int i = 0; i < 8; ++i) beta.v[i] = glvc::BETA_MONT(i);
     T[1] = P;
-    T[1].X = P.X * beta;                 // phi(P): x = X / ZZ is scaled by beta
+    T[1].X = P.X * beta;
     if (n2) T[1] = T[1].neg();
     T[2] = T[0].add(T[1]);
     g1_xyzz_t r = g1_xyzz_t::infinity();

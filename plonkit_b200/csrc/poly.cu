@@ -56,7 +56,7 @@ void poly_powers_from(pk_ctx* ctx, fr_t* out, const fr_t& base, size_t first, si
 }
 void poly_powers(pk_ctx* ctx, fr_t* out, const fr_t& base, size_t n) { poly_powers_from(ctx, out, base, 0, n); }
 
-struct LinArgs { const fr_t* in[12]; fr_t coef[12]; int n_terms; };
+struct LinArgs { const fr_t* in[16]; fr_t coef[16]; int n_terms; };
 __global__ void lincomb_kernel(fr_t* out, LinArgs a, size_t n) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -65,7 +65,7 @@ __global__ void lincomb_kernel(fr_t* out, LinArgs a, size_t n) {
     st_fp(out + i, acc);
 }
 void poly_lincomb(pk_ctx* ctx, fr_t* out, int nterms, const fr_t* const* in, const fr_t* coef, size_t n) {
-    PK_REQUIRE(nterms >= 1 && nterms <= 12, PK_ERR_INVALID, "lincomb arity");
+    PK_REQUIRE(nterms >= 1 && nterms <= 16, PK_ERR_INVALID, "lincomb arity");
     LinArgs a;
     for (int k = 0; k < nterms; ++k) { a.in[k] = in[k]; a.coef[k] = coef[k]; }
     a.n_terms = nterms;
@@ -325,6 +325,35 @@ __global__ void gate_check_kernel(const fr_t* w, const fr_t* sel, uint32_t ni, i
     if (r < ni) acc = acc + a;
     if (!acc.is_zero()) atomicOr(flag, 1u);
 }
+__global__ void gate_check_gated_kernel(const fr_t* w, const fr_t* sel, const uint8_t* gate_type, uint32_t ni, int log_n, uint32_t* flag) {
+    size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t n = size_t(1) << log_n;
+    if (r + 1 >= n) return;
+    fr_t a = ld_fp(w + r), b = ld_fp(w + n + r), c = ld_fp(w + 2 * n + r), d = ld_fp(w + 3 * n + r);
+    bool ok;
+    if (gate_type[r] == 1) {
+        ok = (a * a == b) && (b * b == c) && (c * a == d);
+    } else {
+        fr_t dn = ld_fp(w + 3 * n + r + 1);
+        fr_t acc = ld_fp(sel + r) * a + ld_fp(sel + n + r) * b + ld_fp(sel + 2 * n + r) * c + ld_fp(sel + 3 * n + r) * d +
+                   ld_fp(sel + 4 * n + r) * (a * b) + ld_fp(sel + 5 * n + r) + ld_fp(sel + 6 * n + r) * dn;
+        if (r < ni) acc = acc + a;
+        ok = acc.is_zero();
+    }
+    if (!ok) atomicOr(flag, 1u);
+}
+bool gate_check_gated(pk_ctx* ctx, const fr_t* vals_nat, const fr_t* sel_vals, const uint8_t* gate_type, uint32_t num_inputs, int log_n) {
+    PolyScratch* sc = poly_scratch(ctx);
+    sc->flag.ensure(1);
+    PK_CUDA(cudaMemsetAsync(sc->flag.p, 0, 4, ctx->stream));
+    size_t n = size_t(1) << log_n;
+    gate_check_gated_kernel<<<grid1d(n, 256), 256, 0, ctx->stream>>>(vals_nat, sel_vals, gate_type, num_inputs, log_n, sc->flag.p);
+    ctx->prof.kernel_launches++;
+    uint32_t* h = reinterpret_cast<uint32_t*>(ctx->pinned);
+    PK_CUDA(cudaMemcpyAsync(h, sc->flag.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return *h == 0;
+}
 bool gate_check(pk_ctx* ctx, const fr_t* vals_nat, const fr_t* sel_vals, uint32_t num_inputs, int log_n) {
     PolyScratch* sc = poly_scratch(ctx);
     sc->flag.ensure(1);
@@ -420,7 +449,7 @@ void z_finish(pk_ctx* ctx, const fr_t* pn, const fr_t* sd, const fr_t& tinv, fr_
 // ---------------------------------------------------------------- quotient numerator / Z_H on the coset, slot layout
 struct QuotKernelArgs {
     QuotientArgs a;
-    fr_t alpha2;
+    fr_t alpha2, alpha3, alpha4, alpha5;
     fr_t bg[4];      // beta * g_s
     fr_t zhinv[4];   // 1 / (g_s^N - 1)
     const fr_t* tw;
@@ -456,7 +485,17 @@ __global__ void __launch_bounds__(256) quotient_kernel(QuotKernelArgs q) {
     fr_t num = zv * (ag + bx) * (bgm + times_k(bx, 1)) * (cg + times_k(bx, 2)) * (dg + times_k(bx, 3));
     fr_t den = zn * (ag + q.a.beta * ld_fp(q.a.sig[0] + idx)) * (bgm + q.a.beta * ld_fp(q.a.sig[1] + idx)) *
                (cg + q.a.beta * ld_fp(q.a.sig[2] + idx)) * (dg + q.a.beta * ld_fp(q.a.sig[3] + idx));
-    fr_t tot = gate + q.a.alpha * (num - den) + q.alpha2 * ld_fp(q.a.l0 + idx) * (zv - fr_t::one());
+    fr_t tot;
+    if (q.a.gsel[0] == nullptr) {
+        tot = gate + q.a.alpha * (num - den) + q.alpha2 * ld_fp(q.a.l0 + idx) * (zv - fr_t::one());
+    } else {
+        // `gate` = main-gate terms + PI; the public-input part stays outside the selector product
+        const fr_t pi_part = q.a.num_direct_inputs < 0 ? ld_fp(q.a.pi + idx) : fr_t::zero();
+        const fr_t main = gate - pi_part;
+        const fr_t resc = q.a.alpha * (a * a - b) + q.alpha2 * (b * b - c) + q.alpha3 * (c * a - d);
+        tot = ld_fp(q.a.gsel[0] + idx) * main + pi_part + ld_fp(q.a.gsel[1] + idx) * resc + q.alpha4 * (num - den) +
+              q.alpha5 * ld_fp(q.a.l0 + idx) * (zv - fr_t::one());
+    }
     st_fp(q.a.out + idx, tot * q.zhinv[s]);
 }
 void quotient_slots(pk_ctx* ctx, const QuotientArgs& a) {
@@ -473,6 +512,10 @@ void quotient_slots(pk_ctx* ctx, const QuotientArgs& a) {
                    "a partial quotient range needs the shifted LDEs and the public-input LDE");
     }
     q.alpha2 = a.alpha.sqr();
+    q.alpha3 = q.alpha2 * a.alpha;
+    q.alpha4 = q.alpha2.sqr();
+    q.alpha5 = q.alpha4 * a.alpha;
+    if (a.gsel[0]) PK_REQUIRE(a.num_direct_inputs < 0, PK_ERR_INVALID, "the two-gate quotient takes the public-input LDE");
     fr_t g7;
     for (int i = 0; i < 8; ++i) g7.v[i] = FrRoots::gen7(i);
     fr_t w4 = host_root_of_unity(log_n + 2);

@@ -18,7 +18,7 @@ void fr_mul_pointwise(pk_ctx* ctx, const fr_t* a, const fr_t* b, fr_t* out, size
 // out[j] = base^j
 void poly_powers(pk_ctx* ctx, fr_t* out, const fr_t& base, size_t n);
 void poly_powers_from(pk_ctx* ctx, fr_t* out, const fr_t& base, size_t first, size_t n);  // out[i] = base^(first + i)
-// out[i] = sum_k coef[k] * in[k][i]  (nterms <= 12); out may alias an input
+// out[i] = sum_k coef[k] * in[k][i]  (nterms <= 16); out may alias an input
 void poly_lincomb(pk_ctx* ctx, fr_t* out, int nterms, const fr_t* const* in, const fr_t* coef, size_t n);
 // results[k] = sum_i polys[k][i] * pows[k][i]   (npoly <= 16), results on the host (synchronises the stream)
 void poly_dot_batch(pk_ctx* ctx, int npoly, const fr_t* const* polys, const fr_t* const* pows, size_t n, fr_t* results_host);
@@ -73,7 +73,13 @@ struct QuotientArgs {
     size_t range_lo = 0, range_len = 0;
     const fr_t* w3_next = nullptr;
     const fr_t* z_next = nullptr;
+    // Two gate types (the recursive prover's shape): gsel[0] = s_main, gsel[1] = s_resc on the coset.  The numerator is
+    // s_main * (main gate) + PI + s_resc * (alpha (a^2 - b) + alpha^2 (b^2 - c) + alpha^3 (c a - d)) + alpha^4 (copy
+    // permutation) + alpha^5 L_0 (Z - 1).  gsel[0] == nullptr: the single-gate protocol (alpha, alpha^2).
+    const fr_t* gsel[2] = {nullptr, nullptr};
 };
+// main-gate identity on rows of type 0, the Rescue x^5 relations on rows of type 1 (gate_type on the device)
+bool gate_check_gated(pk_ctx* ctx, const fr_t* vals_nat, const fr_t* sel_vals, const uint8_t* gate_type, uint32_t num_inputs, int log_n);
 void quotient_slots(pk_ctx* ctx, const QuotientArgs& a);
 
 }  // namespace pk

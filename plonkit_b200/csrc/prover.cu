@@ -28,6 +28,11 @@ struct pk_setup {
     uint64_t nvars = 0;
     bool have_witness = false;
     bool use_lagrange = false;   // wire commitments from VALUES with the Lagrange-form key (bellman prove, src/plonk.rs:138-146)
+    // two gate types (the recursive prover's shape, src/recursive/mod.rs:111-127): main gate + Rescue x^5 custom gate
+    bool gated = false;
+    DevBuf<uint8_t> gate_type;   // [n]
+    DevBuf<fr_t> gsel_coef;      // [2][n]  s_main, s_resc (monomial)
+    DevBuf<fr_t> gsel_lde;       // [2][4n]
     DevBuf<uint32_t> wire_idx;   // [4][n]
     DevBuf<fr_t> sel_vals;       // [7][n] natural order (gate check)
     DevBuf<fr_t> sigma_vals;     // [4][n] natural order (grand product)
@@ -103,7 +108,13 @@ static void setup_poly(pk_ctx* ctx, const fr_t* vals_nat, fr_t* coef, fr_t* lde,
     lde4_slots(ctx, coef, lde, log_n);
 }
 
-void setup_create(pk_ctx* ctx, const pk_assembly* as, pk_setup** out) {
+static void setup_create_impl(pk_ctx* ctx, const pk_assembly* as, const uint8_t* gate_type, pk_setup** out);
+void setup_create(pk_ctx* ctx, const pk_assembly* as, pk_setup** out) { setup_create_impl(ctx, as, nullptr, out); }
+void setup_create_gated(pk_ctx* ctx, const pk_assembly_gated* as, pk_setup** out) {
+    PK_REQUIRE(as && as->gate_type, PK_ERR_INVALID, "null gate types");
+    setup_create_impl(ctx, &as->base, as->gate_type, out);
+}
+static void setup_create_impl(pk_ctx* ctx, const pk_assembly* as, const uint8_t* gate_type, pk_setup** out) {
     PK_REQUIRE(as && out, PK_ERR_INVALID, "null argument");
     const uint64_t n = as->n;
     PK_REQUIRE(n >= 2 && (n & (n - 1)) == 0, PK_ERR_INVALID, "domain size must be a power of two >= 2");
@@ -138,6 +149,22 @@ void setup_create(pk_ctx* ctx, const pk_assembly* as, pk_setup** out) {
             setup_poly(ctx, s->sel_vals.p + k * n, s->sel_coef.p + k * n, s->sel_lde.p + 4 * k * n, s->tmp_a.p, log_n);
         for (int k = 0; k < 4; ++k)
             setup_poly(ctx, s->sigma_vals.p + k * n, s->sigma_coef.p + k * n, s->sigma_lde.p + 4 * k * n, s->tmp_a.p, log_n);
+        if (gate_type) {
+            // gate selectors: s_main = 1 on main-gate rows (padding included), s_resc = 1 on Rescue x^5 rows
+            s->gated = true;
+            s->gate_type.alloc(n); s->gsel_coef.alloc(2 * n); s->gsel_lde.alloc(8 * n);
+            std::vector<fr_t> vals(2 * n, fr_t::zero());
+            for (uint64_t r = 0; r < n; ++r) {
+                PK_REQUIRE(gate_type[r] <= 1, PK_ERR_INVALID, "unknown gate type");
+                vals[(gate_type[r] == 1 ? n : 0) + r] = fr_t::one();
+            }
+            PK_CUDA(cudaMemcpyAsync(s->gate_type.p, gate_type, n, cudaMemcpyHostToDevice, st));
+            PK_CUDA(cudaMemcpyAsync(s->tmp_b.p, vals.data(), n * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+            setup_poly(ctx, s->tmp_b.p, s->gsel_coef.p, s->gsel_lde.p, s->tmp_a.p, log_n);
+            PK_CUDA(cudaMemcpyAsync(s->tmp_b.p, vals.data() + n, n * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+            setup_poly(ctx, s->tmp_b.p, s->gsel_coef.p + n, s->gsel_lde.p + 4 * n, s->tmp_a.p, log_n);
+            PK_CUDA(cudaStreamSynchronize(st));  // `vals` is pageable host memory: done with it before it goes away
+        }
         PK_CUDA(cudaStreamSynchronize(st));
         PK_CUDA(cudaGetLastError());
     } catch (...) {
@@ -154,6 +181,17 @@ void setup_commitments(pk_ctx* ctx, pk_setup* s, uint64_t out_xy[11][8]) {
     g1_affine_t out[11];
     msm_run_batch(ctx, polys, 11, s->n, 0, out);
     for (int k = 0; k < 11; ++k) affine_to_abi(out[k], out_xy[k]);
+}
+
+void setup_commitments_gated(pk_ctx* ctx, pk_setup* s, uint64_t out_xy[13][8]) {
+    PK_REQUIRE(s->gated, PK_ERR_INVALID, "setup has a single gate type (use pk_setup_commitments)");
+    const fr_t* polys[13];
+    for (int k = 0; k < 7; ++k) polys[k] = s->sel_coef.p + k * s->n;
+    polys[7] = s->gsel_coef.p; polys[8] = s->gsel_coef.p + s->n;
+    for (int k = 0; k < 4; ++k) polys[9 + k] = s->sigma_coef.p + k * s->n;
+    g1_affine_t out[13];
+    msm_run_batch(ctx, polys, 13, s->n, 0, out);
+    for (int k = 0; k < 13; ++k) affine_to_abi(out[k], out_xy[k]);
 }
 
 void witness_upload(pk_ctx* ctx, pk_setup* s, const uint64_t* var_values, uint64_t nvars) {
@@ -199,7 +237,9 @@ void prove(pk_ctx* ctx, pk_setup* s, const uint64_t* var_values, uint64_t nvars,
 
     // ---- witness -> wire values; is_satisfied_using_one_shot_check (src/plonk.rs:137)
     wire_gather(ctx, s->vars.p, s->wire_idx.p, s->w_nat.p, s->w_br.p, log_n);
-    PK_REQUIRE(gate_check(ctx, s->w_nat.p, s->sel_vals.p, ni, log_n), PK_ERR_UNSATISFIED, "witness does not satisfy the circuit");
+    const bool sat = s->gated ? gate_check_gated(ctx, s->w_nat.p, s->sel_vals.p, s->gate_type.p, ni, log_n)
+                              : gate_check(ctx, s->w_nat.p, s->sel_vals.p, ni, log_n);
+    PK_REQUIRE(sat, PK_ERR_UNSATISFIED, "witness does not satisfy the circuit");
     std::vector<fr_t> inputs(ni);
     if (ni) {
         PK_CUDA(cudaMemcpyAsync(inputs.data(), s->w_nat.p, ni * sizeof(fr_t), cudaMemcpyDeviceToHost, st));
@@ -254,7 +294,7 @@ void prove(pk_ctx* ctx, pk_setup* s, const uint64_t* var_values, uint64_t nvars,
     lde4_slots(ctx, s->z_coef.p, s->z_lde.p, log_n);
     CosetTables* ct = get_coset_tables(ctx, log_n);
     QuotientArgs qa;
-    if (ni <= 8) {
+    if (ni <= 8 && !s->gated) {
         // PI(X) = sum_i in_i L_0(X w^-i): read off the resident L_0 table inside the quotient kernel, no NTT
         qa.num_direct_inputs = (int)ni;
         for (uint32_t i = 0; i < ni; ++i) qa.inputs[i] = inputs[i];
@@ -269,6 +309,7 @@ void prove(pk_ctx* ctx, pk_setup* s, const uint64_t* var_values, uint64_t nvars,
     for (int k = 0; k < 7; ++k) qa.sel[k] = s->sel_lde.p + 4 * k * n;
     qa.z = s->z_lde.p; qa.pi = s->pi_lde.p; qa.l0 = ct->l0.p; qa.out = s->t4.p;
     qa.beta = beta; qa.gamma = gamma; qa.alpha = alpha; qa.log_n = log_n;
+    if (s->gated) { qa.gsel[0] = s->gsel_lde.p; qa.gsel[1] = s->gsel_lde.p + 4 * n; }
     quotient_slots(ctx, qa);
     icoset4n_from_slots(ctx, s->t4.p, s->t4.p, log_n);
     {
@@ -292,18 +333,26 @@ void prove(pk_ctx* ctx, pk_setup* s, const uint64_t* var_values, uint64_t nvars,
     const fr_t zeta_omega = zeta * omega;
     poly_powers(ctx, s->zpow.p, zeta, n);
     poly_powers(ctx, s->zwpow.p, zeta_omega, n);
-    fr_t ev[13];
+    fr_t ev[15];
     {
-        const fr_t* polys[13];
-        const fr_t* pows[13];
+        const fr_t* polys[15];
+        const fr_t* pows[15];
         for (int c = 0; c < 4; ++c) polys[c] = s->w_coef.p + c * n;
         for (int c = 0; c < 3; ++c) polys[4 + c] = s->sigma_coef.p + c * n;
         for (int i = 0; i < 4; ++i) polys[7 + i] = s->t4.p + i * n;
         for (int k = 0; k < 11; ++k) pows[k] = s->zpow.p;
         polys[11] = s->w_coef.p + 3 * n; pows[11] = s->zwpow.p;
         polys[12] = s->z_coef.p; pows[12] = s->zwpow.p;
-        poly_dot_batch(ctx, 13, polys, pows, n, ev);
+        if (s->gated) {
+            polys[13] = s->gsel_coef.p; polys[14] = s->gsel_coef.p + n;
+            pows[13] = pows[14] = s->zpow.p;
+        }
+        poly_dot_batch(ctx, s->gated ? 15 : 13, polys, pows, n, ev);
     }
+    const fr_t smz = s->gated ? ev[13] : fr_t::one(), srz = s->gated ? ev[14] : fr_t::zero();
+    // powers of alpha of the copy-permutation and L_0 terms: (alpha, alpha^2), or (alpha^4, alpha^5) behind the custom gate's three
+    const fr_t a_perm = s->gated ? alpha.sqr().sqr() : alpha;
+    const fr_t a_l0 = s->gated ? a_perm * alpha : alpha.sqr();
     const fr_t* wz = ev;          // a,b,c,d at zeta
     const fr_t* sz = ev + 4;      // sigma_0..2 at zeta
     const fr_t dzw = ev[11], zzw = ev[12];
@@ -314,16 +363,17 @@ void prove(pk_ctx* ctx, pk_setup* s, const uint64_t* var_values, uint64_t nvars,
     const fr_t n_fr = fr_t::from_u32(2).pow_u64(log_n);
     const fr_t l0z = (zeta_n - fr_t::one()) * (n_fr * (zeta - fr_t::one())).inverse();
     static const uint32_t KK[4] = {1, 5, 7, 10};
-    fr_t zfac = alpha;
+    fr_t zfac = a_perm;
     for (int i = 0; i < 4; ++i) zfac = zfac * (wz[i] + beta * fr_t::from_u32(KK[i]) * zeta + gamma);
-    zfac = zfac + alpha.sqr() * l0z;
-    fr_t sfac = alpha * beta * zzw;
+    zfac = zfac + a_l0 * l0z;
+    fr_t sfac = a_perm * beta * zzw;
     for (int i = 0; i < 3; ++i) sfac = sfac * (wz[i] + beta * sz[i] + gamma);
     {
-        // r(X) = q_const + sum q_i w_i(z) + q_m a(z) b(z) + q_dnext d(z w) + Z(X) zfac - sigma_3(X) sfac
+        // r(X) = s_main(z) [q_const + sum q_i w_i(z) + q_m a(z) b(z) + q_dnext d(z w)] + Z(X) zfac - sigma_3(X) sfac
+        // (s_main(z) = 1 without gate selectors)
         const fr_t* in[9] = {s->sel_coef.p + 5 * n, s->sel_coef.p, s->sel_coef.p + n, s->sel_coef.p + 2 * n, s->sel_coef.p + 3 * n,
                              s->sel_coef.p + 4 * n, s->sel_coef.p + 6 * n, s->z_coef.p, s->sigma_coef.p + 3 * n};
-        fr_t coef[9] = {fr_t::one(), wz[0], wz[1], wz[2], wz[3], wz[0] * wz[1], dzw, zfac, sfac.neg()};
+        fr_t coef[9] = {smz, smz * wz[0], smz * wz[1], smz * wz[2], smz * wz[3], smz * wz[0] * wz[1], smz * dzw, zfac, sfac.neg()};
         poly_lincomb(ctx, s->r_coef.p, 9, in, coef, n);
     }
     fr_t rz;
@@ -334,6 +384,7 @@ void prove(pk_ctx* ctx, pk_setup* s, const uint64_t* var_values, uint64_t nvars,
     }
     for (int c = 0; c < 4; ++c) tr_commit_fr(tr, wz[c]);
     tr_commit_fr(tr, dzw);
+    if (s->gated) { tr_commit_fr(tr, smz); tr_commit_fr(tr, srz); }
     for (int c = 0; c < 3; ++c) tr_commit_fr(tr, sz[c]);
     tr_commit_fr(tr, tz);
     tr_commit_fr(tr, rz);
@@ -342,18 +393,24 @@ void prove(pk_ctx* ctx, pk_setup* s, const uint64_t* var_values, uint64_t nvars,
     clk.mark();  // phase 4
 
     // ---- round 5: opening proofs
-    fr_t vp[11];
+    fr_t vp[13];
     vp[0] = fr_t::one();
-    for (int i = 1; i <= 10; ++i) vp[i] = vp[i - 1] * v;
-    {
+    for (int i = 1; i <= 12; ++i) vp[i] = vp[i - 1] * v;
+    if (!s->gated) {
         const fr_t* in[12] = {s->t4.p, s->t4.p + n, s->t4.p + 2 * n, s->t4.p + 3 * n, s->r_coef.p, s->w_coef.p, s->w_coef.p + n,
                               s->w_coef.p + 2 * n, s->w_coef.p + 3 * n, s->sigma_coef.p, s->sigma_coef.p + n, s->sigma_coef.p + 2 * n};
         fr_t coef[12] = {fr_t::one(), zeta_n, zn2, zn3, vp[1], vp[2], vp[3], vp[4], vp[5], vp[6], vp[7], vp[8]};
         poly_lincomb(ctx, s->tmp_a.p, 12, in, coef, n);
+    } else {  // the two gate selectors are opened at z as well: v^6, v^7 between the wires and the sigmas
+        const fr_t* in[14] = {s->t4.p, s->t4.p + n, s->t4.p + 2 * n, s->t4.p + 3 * n, s->r_coef.p, s->w_coef.p, s->w_coef.p + n,
+                              s->w_coef.p + 2 * n, s->w_coef.p + 3 * n, s->gsel_coef.p, s->gsel_coef.p + n, s->sigma_coef.p,
+                              s->sigma_coef.p + n, s->sigma_coef.p + 2 * n};
+        fr_t coef[14] = {fr_t::one(), zeta_n, zn2, zn3, vp[1], vp[2], vp[3], vp[4], vp[5], vp[6], vp[7], vp[8], vp[9], vp[10]};
+        poly_lincomb(ctx, s->tmp_a.p, 14, in, coef, n);
     }
     {
         const fr_t* in[2] = {s->z_coef.p, s->w_coef.p + 3 * n};
-        fr_t coef[2] = {vp[9], vp[10]};
+        fr_t coef[2] = {s->gated ? vp[11] : vp[9], s->gated ? vp[12] : vp[10]};
         poly_lincomb(ctx, s->tmp_b.p, 2, in, coef, n);
     }
     PK_REQUIRE(!zeta.is_zero(), PK_ERR_DIVISION_BY_ZERO, "challenge z is zero");
@@ -393,6 +450,11 @@ void prove(pk_ctx* ctx, pk_setup* s, const uint64_t* var_values, uint64_t nvars,
     fr_to_abi(alpha, proof->challenges[2]);
     fr_to_abi(zeta, proof->challenges[3]);
     fr_to_abi(v, proof->challenges[4]);
+    if (s->gated) {
+        proof->num_gate_selectors = 2;
+        fr_to_abi(smz, proof->gate_selectors_at_z[0]);
+        fr_to_abi(srz, proof->gate_selectors_at_z[1]);
+    }
 }
 
 }  // namespace pk

@@ -128,6 +128,8 @@ class Proof:
     permutation_polynomials_at_z: List[int]
     opening_at_z_proof: np.ndarray             # (8,)
     opening_at_z_omega_proof: np.ndarray       # (8,)
+    # proofs of the two-gate-type prover (plonkit_b200.recursive; layout unpinned) also open the gate selectors at z
+    gate_selectors_at_z: Optional[List[int]] = None
 
     def write(self, f):
         def frs(vals):
@@ -141,6 +143,8 @@ class Proof:
         f.write(struct.pack(">Q", 1) + frs(self.wire_values_at_z_omega))
         f.write(frs([self.grand_product_at_z_omega, self.quotient_polynomial_at_z, self.linearization_polynomial_at_z]))
         f.write(struct.pack(">Q", 3) + frs(self.permutation_polynomials_at_z))
+        if self.gate_selectors_at_z is not None:
+            f.write(struct.pack(">Q", len(self.gate_selectors_at_z)) + frs(self.gate_selectors_at_z))
         f.write(g1_to_bytes(self.opening_at_z_proof))
         f.write(g1_to_bytes(self.opening_at_z_omega_proof))
 

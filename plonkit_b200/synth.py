@@ -326,3 +326,51 @@ def write_wtns(witness, path):
     with open(path, "wb") as f:
         f.write(b"wtns" + struct.pack("<II", 2, 2) + struct.pack("<IQ", 1, 40) + struct.pack("<I", 32) + R_MOD.to_bytes(32, "little") +
                 struct.pack("<I", len(witness)) + struct.pack("<IQ", 2, len(body)) + body)
+
+
+# ---------------------------------------------------------------- circuits with the Rescue x^5 custom gate
+def rescue_chain_assembly(log_n: int, inputs=(3, 4, 5)):
+    """A circuit of the recursive prover's shape (src/recursive/mod.rs:111-127: ProvingAssembly over Width4MainGateWithDNext +
+    the Rescue x^5 custom gate): the poseidon-shaped chain above with every S-box as ONE custom-gate row (a = x, b = x^2,
+    c = x^4, d = x^5) instead of three multiplication gates; the MDS rows stay main-gate rows.  2^log_n - 1 gates, one public
+    input.  Returns (Assembly, gate_type) with gate_type[row] = 1 on custom-gate rows."""
+    n = 1 << log_n
+    n_gates = n - 1
+    rng = SplitMix64(SEED ^ 0x7E5C)
+    rounds = FULL_ROUNDS + PARTIAL_ROUNDS
+    rc = [[rng.field() for _ in range(T)] for _ in range(rounds)]
+    mds = [[rng.field() for _ in range(T)] for _ in range(T)]
+    M1 = R_MOD - 1
+    vals = [0] + [v % R_MOD for v in inputs]
+    rows = [(1, 0, 0, 0, [M1, 0, 0, 0, 0, 0, 0], 0)]
+    state = [1, 2, 3]
+    r = 0
+    while len(rows) < n_gates:
+        full = (r % rounds) < FULL_ROUNDS // 2 or (r % rounds) >= FULL_ROUNDS // 2 + PARTIAL_ROUNDS
+        for i in range(T if full else 1):
+            if len(rows) >= n_gates:
+                break
+            x = vals[state[i]]
+            x2 = x * x % R_MOD
+            x4 = x2 * x2 % R_MOD
+            x5 = x4 * x % R_MOD
+            base = len(vals)
+            vals.extend([x2, x4, x5])
+            rows.append((state[i], base, base + 1, base + 2, [0] * 7, 1))
+            state[i] = base + 2
+        new_state = []
+        for i in range(T):
+            if len(rows) >= n_gates:
+                break
+            k = rc[r % rounds][i]
+            vals.append((mds[i][0] * vals[state[0]] + mds[i][1] * vals[state[1]] + mds[i][2] * vals[state[2]] + k) % R_MOD)
+            rows.append((state[0], state[1], state[2], len(vals) - 1, [mds[i][0], mds[i][1], mds[i][2], M1, 0, k, 0], 0))
+            new_state.append(len(vals) - 1)
+        if len(new_state) == T:
+            state = new_state
+        r += 1
+    from .circuit import assembly_from_rows
+    asm = assembly_from_rows([row[:5] for row in rows], vals, 1)
+    gate_type = np.zeros(n, dtype=np.uint8)
+    gate_type[:len(rows)] = [row[5] for row in rows]
+    return asm, gate_type

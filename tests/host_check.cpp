@@ -69,7 +69,8 @@ void hc_lazy_field(const uint32_t* a, const uint32_t* b, uint32_t* o, int n) {
         memcpy(o + 8 * i, r.v, 32);
     }
 }
-// GLV: out_k = (|k1| (5 limbs), sign1, |k2| (5 limbs), sign2); out_pt[0] = k * p (GLV), out_pt[1] = k * p (plain 254-bit walk)
+// GLV: out_k = (|k1| (5 limbs), sign1, |k2| (5 limbs), sign2); out_pt[0] = k * p (GLV, joint 2-bit window), out_pt[1] = k * p
+// (plain 254-bit walk), out_pt[2] = k * p (GLV, bit by bit)
 void hc_glv(const uint64_t* p, const uint32_t* k_canonical, uint32_t* out_k, uint64_t* out_pt) {
     bool n1, n2;
     glv::decompose(k_canonical, out_k, n1, out_k + 6, n2);
@@ -80,6 +81,7 @@ void hc_glv(const uint64_t* p, const uint32_t* k_canonical, uint32_t* out_k, uin
     g1_xyzz_t Q = P3.add(P.dbl().neg());                 // == P with ZZ != 1
     store_pt(scalar_mul(Q, k).to_affine(), out_pt);
     store_pt(scalar_mul_plain(Q, k).to_affine(), out_pt + 8);
+    store_pt(scalar_mul_bitwise(Q, k).to_affine(), out_pt + 16);
 }
 void hc_keccak(const uint8_t* d, uint64_t n, uint8_t* out) { Keccak256 h; h.update(d, n); h.finish(out); }
 // transcript: commit `n` 32-byte big-endian values, then draw `m` challenges (canonical LE limbs out)

@@ -259,3 +259,36 @@ def test_cli_prove_and_export_vk_write_the_golden_files(tmp_path):
     assert json.load(open(tmp_path / "public.json")) == ["0x23"] and len(json.load(open(tmp_path / "proof.json"))) == 33
     with pytest.raises(SystemExit, match="duplicate proof file"):
         cli.main(["prove", "-m", key, "-c", circ, "-w", os.path.join(SIMPLE, "witness.json"), "-p", str(proof)])
+
+
+@pytest.mark.parametrize("log_n", [6, 10, 13])
+def test_two_gate_type_prover_matches_its_oracle_and_verifies(ctx, orc, log_n):
+    """The recursive prover's proving call (src/recursive/mod.rs:120-127: main gate + Rescue x^5 custom gate behind gate
+    selectors) on a synthetic circuit of that shape.  BYTE PARITY UNPINNED (no reference fixture, the prover's crates are
+    not in the tree): the CUDA proof must equal the oracle's restatement of the same protocol byte for byte, the restated
+    verifier (known trapdoor) must accept it against the exported 13-commitment key, and reject a tampered proof; a witness
+    that breaks a custom-gate row is refused like an unsatisfied main-gate row."""
+    from plonkit_b200 import recursive
+    from plonkit_b200.reader import Crs
+    asm, gate_type = synth.rescue_chain_assembly(log_n)
+    assert gate_type.sum() > 0 and asm.n == 1 << log_n
+    srs = orc.srs_gen(asm.n, 42, threads=8)
+    setup = recursive.RecursiveSetupForProver(asm, gate_type, Crs(srs), ctx=ctx)
+    proof = setup.create_proof(asm.var_values).to_bytes()
+    assert proof == orc.prove2(asm.n, asm.num_inputs, asm.wire_idx, asm.var_values, asm.selectors, gate_type, srs, threads=8)
+    vk = setup.export_vk()
+    assert (vk.commitments == orc.setup_commitments2(asm.n, asm.num_inputs, asm.wire_idx, asm.selectors, gate_type, srs,
+                                                      nvars=asm.nvars, threads=8)).all()
+    assert orc.verify_trapdoor2(proof, vk.commitments, 42)
+    bad = bytearray(proof)
+    bad[-200] ^= 1
+    assert not orc.verify_trapdoor2(bytes(bad), vk.commitments, 42)
+    vals = asm.var_values.copy()
+    row = int(np.nonzero(gate_type)[0][0])
+    vals[asm.wire_idx[1, row]] = ints_to_limbs([5])[0]      # x^2 wire of a custom-gate row
+    with pytest.raises(_lib.SynthesisError) as e:
+        setup.create_proof(vals)
+    assert e.value.code == 4
+    setup.close()
+    with pytest.raises(NotImplementedError):
+        recursive.prove(None, [], None)

@@ -355,13 +355,13 @@ def test_glv_decomposition_and_scalar_multiplication(hc, orc, simple_key):
         p = simple_key.g1_bases[3 + n % 50] if n != 5 else inf
         kk = ints_to_limbs([k]).view(np.uint32)
         out_k = np.zeros(12, dtype=np.uint32)
-        out_pt = np.zeros((2, 8), dtype=np.uint64)
+        out_pt = np.zeros((3, 8), dtype=np.uint64)
         hc.hc_glv(_p(np.ascontiguousarray(p)), _p(kk), _p(out_k), _p(out_pt))
         k1 = sum(int(out_k[i]) << (32 * i) for i in range(5)) * (-1 if out_k[5] else 1)
         k2 = sum(int(out_k[6 + i]) << (32 * i) for i in range(5)) * (-1 if out_k[11] else 1)
         assert (k1 + k2 * lam - k) % R_MOD == 0 and abs(k1) < (1 << 129) and abs(k2) < (1 << 129)
         want = orc.g1_mul(p, k)
-        assert (out_pt[0] == want).all() and (out_pt[1] == want).all(), hex(k)
+        assert (out_pt[0] == want).all() and (out_pt[1] == want).all() and (out_pt[2] == want).all(), hex(k)
 
 
 def test_host_keccak_and_transcript_match_oracle(hc, orc):
