@@ -8,7 +8,7 @@ width-4 main gate with d_next and the Rescue x^5 custom gate.  Part (2) is where
 this module runs on the CUDA library, taking the synthesised assembly (gate tables + a gate type per row) as input.
 
 BYTE PARITY UNPINNED: neither that prover nor its proof layout is in the reference tree and no fixture exists.  The
-protocol implemented (DESIGN.md section 9; oracle/oracle.cpp orc_prove2) follows the round structure of SURVEY.md App. D;
+protocol implemented (DESIGN.md section 9) follows the round structure of SURVEY.md App. D;
 proofs are checked by this repository's own restated verifier under the known trapdoor, not against reference bytes.
 """
 import ctypes
