@@ -71,8 +71,11 @@ struct LocalComm : Comm {
         g->ptr[rank] = send;
         g->barrier();
         enable_peers();
-        for (int q = 0; q < world; ++q)
-            PK_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(recv) + (size_t)q * bytes, g->ptr[q], bytes, cudaMemcpyDefault, st));
+        for (int q = 0; q < world; ++q) {
+            uint8_t* dst = static_cast<uint8_t*>(recv) + (size_t)q * bytes;
+            if (dst != g->ptr[q])  // in place (send == recv + rank * bytes): this rank's block is already there
+                PK_CUDA(cudaMemcpyAsync(dst, g->ptr[q], bytes, cudaMemcpyDefault, st));
+        }
         PK_CUDA(cudaStreamSynchronize(st));
         g->barrier();
     }

@@ -21,7 +21,8 @@ namespace pk {
 struct Comm {
     int rank = 0, world = 1;
     virtual ~Comm() {}
-    // recv[q * bytes ...] = the `bytes` at `send` on rank q, for every q (send may not alias recv)
+    // recv[q * bytes ...] = the `bytes` at `send` on rank q, for every q; send is either disjoint from recv or exactly
+    // recv + rank * bytes (in place)
     virtual void all_gather(const void* send, void* recv, size_t bytes, cudaStream_t st) = 0;
     // `count` all-gathers at once: recv[c] + q * bytes = send[c] of rank q
     virtual void all_gather_multi(const void* const* send, void* const* recv, int count, size_t bytes, cudaStream_t st) = 0;

@@ -18,8 +18,8 @@
 //   * grand product, evaluations, linearisation and opening polynomials: sharded by rows / coefficient chunk; what a
 //     scan or a sum needs from the other chunks (prefix products, partial sums, division carries) travels as a few
 //     32-byte scalars per rank, and the finished chunk of Z is all-gathered (n 32 B) for its inverse NTT.
-//   * the five size-n inverse NTTs (wires, Z) and the witness gather are replicated: every rank holds the witness and
-//     needs all coefficients for its LDEs anyway; every rank derives the same transcript, no broadcast.
+//   * the four wire inverse NTTs are shared out by polynomial and all-gathered (4n 32 B); the witness gather and the
+//     inverse NTT of Z are replicated.  Every rank holds the witness and derives the same transcript: no broadcast.
 //
 // Every rank returns the same proof.  The collectives come from comm.cuh (NCCL between processes, peer copies
 // between the threads of one process).
@@ -307,11 +307,14 @@ void dist_prove(pk_ctx* ctx, pk_dist_setup* s, const uint64_t* var_values, uint6
     // ---- round 1
     g1_affine_t Cw[4];
     {
+        // the four wire inverse NTTs are shared out by polynomial: rank r transforms the wire(s) that overlap block r of the
+        // [4][n] coefficient array and the blocks are all-gathered in place (4n 32 B in total)
         const fr_t* polys[4];
-        for (int c = 0; c < 4; ++c) {
+        const uint64_t blk = 4 * n / G, b0 = (uint64_t)s->rank * blk;
+        for (int c = (int)(b0 / n); c <= (int)((b0 + blk - 1) / n); ++c)
             ntt_inverse_from_bitrev(ctx, s->w_br.p + c * n, s->w_coef.p + c * n, log_n);
-            polys[c] = s->w_coef.p + c * n;
-        }
+        ctx->comm->all_gather(s->w_coef.p + b0, s->w_coef.p, blk * sizeof(fr_t), st);
+        for (int c = 0; c < 4; ++c) polys[c] = s->w_coef.p + c * n;
         dist_commit(s, polys, 4, Cw);
         for (int c = 0; c < 4; ++c) d_commit_g1(tr, Cw[c]);
     }
@@ -357,9 +360,15 @@ void dist_prove(pk_ctx* ctx, pk_dist_setup* s, const uint64_t* var_values, uint6
     range_lde(s, s->tmp_a.p, s->znext_lde.p);
     omega_scale(ctx, s->w_coef.p + 3 * n, s->tmp_a.p, log_n);
     range_lde(s, s->tmp_a.p, s->dnext_lde.p);
-    PK_CUDA(cudaMemsetAsync(s->tmp_c.p, 0, n * sizeof(fr_t), st));
-    pi_scatter(ctx, s->w_nat.p, s->tmp_c.p, ni, log_n);
-    ntt_inverse_from_bitrev(ctx, s->tmp_c.p, s->pi_coef.p, log_n);
+    if (ni <= 1) {
+        // PI(X) = in_0 L_0(X) = (in_0 / n) sum_j X^j: no transform needed for the common single-input circuit
+        const fr_t c0 = ni ? inputs[0] * fr_t::from_u32(2).inverse().pow_u64(log_n) : fr_t::zero();
+        fr_fill(ctx, s->pi_coef.p, c0, n);
+    } else {
+        PK_CUDA(cudaMemsetAsync(s->tmp_c.p, 0, n * sizeof(fr_t), st));
+        pi_scatter(ctx, s->w_nat.p, s->tmp_c.p, ni, log_n);
+        ntt_inverse_from_bitrev(ctx, s->tmp_c.p, s->pi_coef.p, log_n);
+    }
     range_lde(s, s->pi_coef.p, s->pi_lde.p);
     QuotientArgs qa;
     qa.num_direct_inputs = -1;

@@ -281,7 +281,7 @@ def test_two_gate_type_prover_matches_its_oracle_and_verifies(ctx, orc, log_n):
                                                       nvars=asm.nvars, threads=8)).all()
     assert orc.verify_trapdoor2(proof, vk.commitments, 42)
     bad = bytearray(proof)
-    bad[-200] ^= 1
+    bad[-150] ^= 1          # inside s_resc(z)
     assert not orc.verify_trapdoor2(bytes(bad), vk.commitments, 42)
     vals = asm.var_values.copy()
     row = int(np.nonzero(gate_type)[0][0])
