@@ -207,6 +207,9 @@ typedef struct pk_profile {
     double ntt_ms;
     uint64_t ntt_elements;          /* elements x passes */
     double phase_ms[8];             /* last pk_prove: round1..round5, setup-dependent, h2d, total (CUDA events) */
+    /* last pk_dist_prove: the three bulk collectives (CUDA events on the library stream; while profiling is on) */
+    double comm_ms[3];              /* [0] all-gather of wire / Z coefficients, [1] all-to-all of the quotient, [2] all-gather of its coefficients */
+    uint64_t comm_bytes[3];         /* bytes this rank RECEIVES from its peers in each of them */
 } pk_profile;
 void pk_profile_enable(pk_ctx* ctx, int on);
 void pk_profile_reset(pk_ctx* ctx);

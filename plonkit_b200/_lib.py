@@ -83,6 +83,7 @@ class PkProfile(ctypes.Structure):
         ("kernel_launches", ctypes.c_uint64), ("msm_accum_launches", ctypes.c_uint64), ("msm_accum_ms", ctypes.c_double),
         ("msm_accum_points", ctypes.c_uint64), ("ntt_launches", ctypes.c_uint64), ("ntt_ms", ctypes.c_double),
         ("ntt_elements", ctypes.c_uint64), ("phase_ms", ctypes.c_double * 8),
+        ("comm_ms", ctypes.c_double * 3), ("comm_bytes", ctypes.c_uint64 * 3),
     ]
 
 
@@ -323,8 +324,9 @@ class Context:
     def profile(self):
         p = PkProfile()
         self._lib.pk_profile_get(self._h, ctypes.byref(p))
-        d = {k: getattr(p, k) for k, _ in PkProfile._fields_ if k != "phase_ms"}
+        d = {k: getattr(p, k) for k, _ in PkProfile._fields_ if k not in ("phase_ms", "comm_ms", "comm_bytes")}
         d["phase_ms"] = list(p.phase_ms)
+        d["comm_ms"], d["comm_bytes"] = list(p.comm_ms), list(p.comm_bytes)
         return d
 
     def timer_begin(self):

@@ -525,6 +525,7 @@ void pk_profile_get(const pk_ctx* cctx, pk_profile* out) {
     out->ntt_ms = ctx->prof.ntt_ms;
     out->ntt_elements = ctx->prof.ntt_elements;
     for (int i = 0; i < 8; ++i) out->phase_ms[i] = ctx->prof.phase_ms[i];
+    for (int i = 0; i < 3; ++i) { out->comm_ms[i] = ctx->prof.comm_ms[i]; out->comm_bytes[i] = ctx->prof.comm_bytes[i]; }
 }
 
 static std::map<pk_ctx*, std::pair<cudaEvent_t, cudaEvent_t>> g_timers;

@@ -70,6 +70,8 @@ struct Profile {
     uint64_t ntt_launches = 0, ntt_elements = 0;
     double ntt_ms = 0;
     double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double comm_ms[3] = {0, 0, 0};
+    uint64_t comm_bytes[3] = {0, 0, 0};
     // pending event pairs (resolved lazily after a sync)
     struct Pending { cudaEvent_t a, b; int kind; uint64_t units; };
     std::vector<Pending> pending;

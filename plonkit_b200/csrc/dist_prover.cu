@@ -122,6 +122,30 @@ static void dist_commit(pk_dist_setup* s, const fr_t* const* polys, int nb, g1_a
     for (int k = 0; k < nb; ++k) out[k] = host[k].to_affine();
 }
 
+// CUDA-event bracket around one bulk collective (profiling only): comm_ms[slot] += its device time
+struct CommTimer {
+    pk_ctx* ctx;
+    int slot;
+    cudaEvent_t a = nullptr, b = nullptr;
+    CommTimer(pk_ctx* c, int sl, uint64_t bytes) : ctx(c), slot(sl) {
+        if (!ctx->prof.enabled) return;
+        ctx->prof.comm_bytes[slot] += bytes;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, ctx->stream);
+    }
+    ~CommTimer() {
+        if (!a) return;
+        cudaEventRecord(b, ctx->stream);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        ctx->prof.comm_ms[slot] += ms;
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+    }
+};
+
 // all-gather of the (<= 16) field elements in s->xs; host copy [G][16] returned (synchronises)
 static std::vector<fr_t> gather_scalars(pk_dist_setup* s) {
     pk_ctx* ctx = s->ctx;
@@ -285,6 +309,7 @@ void dist_prove(pk_ctx* ctx, pk_dist_setup* s, const uint64_t* var_values, uint6
     int evk = 0;
     auto mark = [&] { cudaEventRecord(ev[evk++], st); };
     mark();
+    for (int i = 0; i < 3; ++i) { ctx->prof.comm_ms[i] = 0; ctx->prof.comm_bytes[i] = 0; }
     if (var_values) dist_witness_upload(ctx, s, var_values, nvars);
     PK_REQUIRE(s->have_witness, PK_ERR_ASSIGNMENT_MISSING, "no witness uploaded");
     mark();
@@ -313,7 +338,10 @@ void dist_prove(pk_ctx* ctx, pk_dist_setup* s, const uint64_t* var_values, uint6
         const uint64_t blk = 4 * n / G, b0 = (uint64_t)s->rank * blk;
         for (int c = (int)(b0 / n); c <= (int)((b0 + blk - 1) / n); ++c)
             ntt_inverse_from_bitrev(ctx, s->w_br.p + c * n, s->w_coef.p + c * n, log_n);
-        ctx->comm->all_gather(s->w_coef.p + b0, s->w_coef.p, blk * sizeof(fr_t), st);
+        {
+            CommTimer t(ctx, 0, (uint64_t)(G - 1) * blk * sizeof(fr_t));
+            ctx->comm->all_gather(s->w_coef.p + b0, s->w_coef.p, blk * sizeof(fr_t), st);
+        }
         for (int c = 0; c < 4; ++c) polys[c] = s->w_coef.p + c * n;
         dist_commit(s, polys, 4, Cw);
         for (int c = 0; c < 4; ++c) d_commit_g1(tr, Cw[c]);
@@ -340,7 +368,10 @@ void dist_prove(pk_ctx* ctx, pk_dist_setup* s, const uint64_t* var_values, uint6
         }
         PK_REQUIRE(!total_den.is_zero(), PK_ERR_DIVISION_BY_ZERO, "zero denominator in the permutation grand product");
         z_finish_chunk(ctx, s->tmp_a.p, s->tmp_b.p, below * above * total_den.inverse(), s->zchunk.p, clo, cn);
-        ctx->comm->all_gather(s->zchunk.p, s->tmp_c.p, cn * sizeof(fr_t), st);
+        {
+            CommTimer t(ctx, 0, (uint64_t)(G - 1) * cn * sizeof(fr_t));
+            ctx->comm->all_gather(s->zchunk.p, s->tmp_c.p, cn * sizeof(fr_t), st);
+        }
         bitrev_permute(ctx, s->tmp_c.p, s->tmp_a.p, log_n);
         ntt_inverse_from_bitrev(ctx, s->tmp_a.p, s->z_coef.p, log_n);
     }
@@ -382,12 +413,16 @@ void dist_prove(pk_ctx* ctx, pk_dist_setup* s, const uint64_t* var_values, uint6
     // size-4n inverse: local stages, all-to-all, cross stages (+ scaling), all-gather of the coefficients
     ntt_inverse_local_stages(ctx, s->t_part.p, s->t_part.p, ilog2(m), log_n + 2);
     const uint64_t per = m / G;
-    ctx->comm->all_to_all(s->t_part.p, s->a2a.p, per * sizeof(fr_t), st);
+    {
+        CommTimer t(ctx, 1, (uint64_t)(G - 1) * per * sizeof(fr_t));
+        ctx->comm->all_to_all(s->t_part.p, s->a2a.p, per * sizeof(fr_t), st);
+    }
     ntt_inverse_cross_stages(ctx, s->a2a.p, s->t_part.p, s->kscale.p, s->cscale, G, log_n + 2, (size_t)s->rank * per);
     {
         const void* send[8];
         void* recv[8];
         for (int c = 0; c < G; ++c) { send[c] = s->t_part.p + (size_t)c * per; recv[c] = s->t4.p + (size_t)c * m; }
+        CommTimer t(ctx, 2, (uint64_t)(G - 1) * G * per * sizeof(fr_t));
         ctx->comm->all_gather_multi(send, recv, G, per * sizeof(fr_t), st);
     }
     {

@@ -65,12 +65,20 @@ def main():
     ms = torch.tensor([ctx.timer_end() / args.iters], dtype=torch.float64, device="cuda:%d" % local)
     td.all_reduce(ms, op=td.ReduceOp.MAX)
     phases = ctx.profile()["phase_ms"]
+    ctx.profile_enable(True)     # one more proof with CUDA events around the bulk collectives
+    sp.prove(None)
+    prof = ctx.profile()
+    ctx.profile_enable(False)
     ok = torch.tensor([int(want is None or got == want)], device="cuda:%d" % local)
     td.all_reduce(ok, op=td.ReduceOp.MIN)
     if rank == 0:
         print("2^%d gates on %d GPUs: sharded == single GPU: %s" % (args.log_n, world, bool(ok.item()) if want is not None else "skipped"))
         print("sharded proof %.2f ms (max over ranks)%s" % (ms.item(), "" if want is None else "; single GPU %.2f ms; speed-up %.2fx" % (ms_single, ms_single / ms.item())))
         print("phase ms (rank 0): h2d %.2f | wires %.2f | Z %.2f | quotient %.2f | evals %.2f | openings %.2f" % tuple(phases[:6]))
+        names = ("all-gather wire+Z coefficients", "all-to-all quotient", "all-gather quotient coefficients")
+        for k in range(3):
+            ms_k, by = prof["comm_ms"][k], prof["comm_bytes"][k]
+            print("  %-34s %8.3f ms  %9.1f MB received per rank  -> %6.1f GB/s per rank" % (names[k], ms_k, by / 1e6, by / 1e6 / max(ms_k, 1e-9)))
     sp.close()
     td.barrier(device_ids=[local])
     td.destroy_process_group()
