@@ -101,6 +101,27 @@ struct LocalComm : Comm {
         PK_CUDA(cudaStreamSynchronize(st));
         g->barrier();
     }
+    bool map_peers(void* mine, size_t, void** out, cudaStream_t st) override {
+        PK_CUDA(cudaStreamSynchronize(st));
+        g->map_ptr[rank] = mine;
+        g->barrier();
+        enable_peers();
+        bool ok = true;
+        for (int q = 0; q < world; ++q) {   // same process: the peer's pointer is valid here once peer access is on
+            out[q] = g->map_ptr[q];
+            if (g->device[q] != g->device[rank]) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, g->device[rank], g->device[q]);
+                ok = ok && can;
+            }
+        }
+        g->barrier();
+        return ok;  // the device topology is the same from every rank's side on an NVSwitch box
+    }
+    void stream_barrier(cudaStream_t st) override {
+        PK_CUDA(cudaStreamSynchronize(st));
+        g->barrier();
+    }
     void begin() override { g->entry_barrier(); }
     void abort() override { g->abort(); }
 };
@@ -120,6 +141,7 @@ struct NcclApi {
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -144,6 +166,7 @@ static NcclApi& nccl_api() {
     api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
     api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
     api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
     api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
     api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
@@ -159,8 +182,52 @@ static NcclApi& nccl_api() {
 
 struct NcclComm : Comm {
     ncclComm_t comm = nullptr;
+    uint8_t* scratch = nullptr;          // device: [world][64] IPC handles / flags, and the barrier word
+    std::vector<void*> opened;           // cudaIpcOpenMemHandle results to close
     ~NcclComm() override {
+        for (void* p : opened) cudaIpcCloseMemHandle(p);
+        if (scratch) cudaFree(scratch);
         if (comm) nccl_api().CommDestroy(comm);
+    }
+    // one process per GPU: the peers' buffers are mapped through CUDA IPC handles, exchanged with an all-gather
+    bool map_peers(void* mine, size_t, void** out, cudaStream_t st) override {
+        if (!scratch) PK_CUDA(cudaMalloc(&scratch, (size_t)(world + 1) * 64 + 64));
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+        cudaIpcMemHandle_t h;
+        memset(&h, 0, sizeof(h));
+        bool ok = cudaIpcGetMemHandle(&h, mine) == cudaSuccess;
+        if (!ok) cudaGetLastError();
+        uint8_t* send = scratch + (size_t)world * 64;
+        PK_CUDA(cudaMemcpyAsync(send, &h, 64, cudaMemcpyHostToDevice, st));
+        PK_NCCL(nccl_api().AllGather(send, scratch, 64, ncclUint8, comm, st));
+        std::vector<cudaIpcMemHandle_t> all(world);
+        PK_CUDA(cudaMemcpyAsync(all.data(), scratch, (size_t)world * 64, cudaMemcpyDeviceToHost, st));
+        PK_CUDA(cudaStreamSynchronize(st));
+        for (int q = 0; q < world; ++q) {
+            if (q == rank) { out[q] = mine; continue; }
+            void* p = nullptr;
+            if (ok && cudaIpcOpenMemHandle(&p, all[q], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) {
+                opened.push_back(p);
+                out[q] = p;
+            } else {
+                cudaGetLastError();
+                ok = false;
+                out[q] = nullptr;
+            }
+        }
+        // agreement: every rank must take the same path
+        int32_t flag = ok ? 1 : 0, result = 0;
+        int32_t* word = reinterpret_cast<int32_t*>(scratch + (size_t)world * 64 + 64 - 8);
+        PK_CUDA(cudaMemcpyAsync(word, &flag, 4, cudaMemcpyHostToDevice, st));
+        PK_NCCL(nccl_api().AllReduce(word, word, 1, ncclInt32, ncclMin, comm, st));
+        PK_CUDA(cudaMemcpyAsync(&result, word, 4, cudaMemcpyDeviceToHost, st));
+        PK_CUDA(cudaStreamSynchronize(st));
+        return result == 1;
+    }
+    void stream_barrier(cudaStream_t st) override {
+        if (!scratch) PK_CUDA(cudaMalloc(&scratch, (size_t)(world + 1) * 64 + 64));
+        int32_t* word = reinterpret_cast<int32_t*>(scratch + (size_t)world * 64 + 64 - 16);
+        PK_NCCL(nccl_api().AllReduce(word, word, 1, ncclInt32, ncclSum, comm, st));  // stream-ordered on every rank
     }
     void all_gather(const void* send, void* recv, size_t bytes, cudaStream_t st) override {
         PK_NCCL(nccl_api().AllGather(send, recv, bytes, ncclUint8, comm, st));

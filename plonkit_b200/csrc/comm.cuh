@@ -28,6 +28,13 @@ struct Comm {
     virtual void all_gather_multi(const void* const* send, void* const* recv, int count, size_t bytes, cudaStream_t st) = 0;
     // block q (bytes each) of send goes to rank q; block q of recv comes from rank q
     virtual void all_to_all(const void* send, void* recv, size_t bytes, cudaStream_t st) = 0;
+    // Direct access to the peers' memory (NVLink / NVSwitch peer mappings): out[q] = an address in THIS rank's address
+    // space through which kernels of this rank can store into the `bytes`-long buffer `mine` of rank q (out[rank] = mine).
+    // Collective; returns false on every rank if any pair of ranks cannot map each other (the caller then stays on the
+    // collectives above).  The mappings live as long as the communicator.
+    virtual bool map_peers(void* mine, size_t bytes, void** out, cudaStream_t st) = 0;
+    // all ranks' work enqueued so far (peer stores included) is complete and visible before any rank's later work starts
+    virtual void stream_barrier(cudaStream_t st) = 0;
     // first thing in every collective API call: all ranks meet; a failure of the previous call is forgotten here
     virtual void begin() {}
     // called by a rank that is about to fail, so that peers blocked in a collective fail too instead of hanging
@@ -42,10 +49,11 @@ struct LocalGroup {
     int arrived = 0, entry_arrived = 0;
     uint64_t generation = 0, entry_generation = 0;
     bool aborted = false;
+    std::vector<void*> map_ptr;           // [world] published buffers (map_peers)
     std::vector<const void*> ptr;         // [world] published send pointers
     std::vector<const void* const*> ptrs; // [world] published pointer lists (all_gather_multi)
     std::vector<int> device;              // [world]
-    explicit LocalGroup(int w) : world(w), ptr(w, nullptr), ptrs(w, nullptr), device(w, -1) {}
+    explicit LocalGroup(int w) : world(w), map_ptr(w, nullptr), ptr(w, nullptr), ptrs(w, nullptr), device(w, -1) {}
     void barrier();  // throws PkError if the group was aborted
     void entry_barrier();  // all ranks meet at the start of a call; clears an abort left by the previous call
     void abort();

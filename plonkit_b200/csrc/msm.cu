@@ -657,17 +657,7 @@ static void msm_enqueue_group(pk_ctx* ctx, SrsTables* s, cudaStream_t st, const 
         p.out_pts = sc.ppts[0].p;
         {
             ScopedKernelTimer timer(ctx, 0, (uint64_t)nb * n, st);
-            // PK_ACC_PAD_KB: unused dynamic shared memory per block, an occupancy throttle (57 -> 3 resident blocks per SM
-            // instead of 4), leaving registers and shared memory for the kernels of other proofs in flight
-            static const int pad_kb = [] { const char* e = getenv("PK_ACC_PAD_KB"); return e ? atoi(e) : 0; }();
-            if (pad_kb > 48) {
-                static bool attr_set = false;
-                if (!attr_set) {
-                    PK_CUDA(cudaFuncSetAttribute(msm_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_kb * 1024));
-                    attr_set = true;
-                }
-            }
-            msm_accum_kernel<<<grid1d(nchunks, ACC_THREADS), ACC_THREADS, (size_t)pad_kb * 1024, st>>>(p);
+            msm_accum_kernel<<<grid1d(nchunks, ACC_THREADS), ACC_THREADS, 0, st>>>(p);
             ctx->prof.msm_accum_launches++;
         }
         LevelParams lp;

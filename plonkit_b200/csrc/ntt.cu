@@ -121,9 +121,33 @@ struct NttPass {
     int c_log;           // log2 of contiguous columns per tile (c_log <= bl)
     int tw_shift;        // tw_log - L
     size_t src_stride, dst_stride, pre_stride;
+    // Fused exchange (sharded prover): the pass's results go straight into the peers' memory over NVLink instead of dst.
+    //   peer_mode 1 (all-gather): element g -> peer[q] + peer_off + g for EVERY rank q
+    //   peer_mode 2 (all-to-all): element g -> peer[g >> per_log] + (rank << per_log) + (g & (2^per_log - 1))
+    int peer_mode, peer_world, peer_rank, per_log;
+    size_t peer_off;
+    fr_t* peer[8];
 };
+struct PeerStore { int mode = 0, world = 1, rank = 0, per_log = 0; size_t off = 0; fr_t* peer[8] = {}; };
+__device__ __forceinline__ void ntt_store(const NttPass& p, fr_t* dst, size_t g, const fr_t& x) {
+    if (p.peer_mode == 0) {
+        st_fp(dst + g, x);
+    } else if (p.peer_mode == 1) {
+        for (int q = 0; q < p.peer_world; ++q) st_fp(p.peer[q] + p.peer_off + g, x);
+    } else {
+        const size_t q = g >> p.per_log;
+        st_fp(p.peer[q] + ((size_t)p.peer_rank << p.per_log) + (g & ((size_t(1) << p.per_log) - 1)), x);
+    }
+}
 
+// Shared-memory index swizzle: the low three index bits are complemented when bit 3 is set.  In the stages whose butterfly
+// span is 1, 2 or 4 elements the eight lanes of a 128-byte wavefront touch indices whose low three bits take only four
+// values (the span bit is fixed); bit 3 varies instead, and the swizzle folds it back in: eight distinct 16-byte bank
+// groups again (1.6 M bank conflicts per contiguous pass without it, ncu).  It is a bijection, and a no-op for accesses
+// whose low three bits already vary.
+__device__ __forceinline__ unsigned swz(unsigned l) { return l ^ (((l >> 3) & 1u) * 7u); }
 __device__ __forceinline__ fr_t lds_fr(const uint4* s_lo, const uint4* s_hi, unsigned l) {
+    l = swz(l);
     uint4 a = s_lo[l], b = s_hi[l];
     fr_t r;
     r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
@@ -131,6 +155,7 @@ __device__ __forceinline__ fr_t lds_fr(const uint4* s_lo, const uint4* s_hi, uns
     return r;
 }
 __device__ __forceinline__ void sts_fr(uint4* s_lo, uint4* s_hi, unsigned l, const fr_t& x) {
+    l = swz(l);
     s_lo[l] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
     s_hi[l] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
 }
@@ -206,7 +231,7 @@ template <bool DIT> __global__ void __launch_bounds__(512) ntt_pass_kernel(NttPa
             fr_t x = lds_fr(s_lo, s_hi, l);
             if (p.post) x = x * ldg_fp(p.post + g);
             else if (p.use_post_const) x = x * p.post_const;
-            st_fp(dst + g, x);
+            ntt_store(p, dst, g, x);
         }
     }
 }
@@ -341,7 +366,7 @@ template <bool DIT> __global__ void __launch_bounds__(512) ntt_pass_tma_kernel(N
             fr_t x = lds_fr_nat(sm, l);
             if (p.post) x = x * ldg_fp(p.post + g);
             else if (p.use_post_const) x = x * p.post_const;
-            st_fp(dst + g, x);
+            ntt_store(p, dst, g, x);
         }
     }
 }
@@ -401,7 +426,8 @@ static PassPlan plan_passes(int L, bool dit) {
 // whose upper stages cross GPUs (sharded prover).
 template <bool DIT>
 static void run_passes(pk_ctx* ctx, const fr_t* src, fr_t* dst, int L, const fr_t* pre, const fr_t* post, const fr_t* post_const,
-                       int batch, size_t src_stride, size_t dst_stride, size_t pre_stride, int L_tw = 0) {
+                       int batch, size_t src_stride, size_t dst_stride, size_t pre_stride, int L_tw = 0,
+                       const PeerStore* peers = nullptr) {
     PK_REQUIRE(L >= 0 && L <= 28, PK_ERR_DEGREE_TOO_LARGE, "domain larger than 2^28");
     size_t n = size_t(1) << L;
     if (L == 0) {  // size-1 transform is the identity (all scale factors are 1)
@@ -430,6 +456,11 @@ static void run_passes(pk_ctx* ctx, const fr_t* src, fr_t* dst, int L, const fr_
         p.post = last ? post : nullptr;
         if (last && !post && post_const) { p.use_post_const = 1; p.post_const = *post_const; }
         p.L = L_tw; p.bl = pl.bl[i]; p.k = pl.k[i]; p.c_log = pl.c_log[i];
+        if (last && peers && peers->mode) {  // the LAST pass writes into the peers' memory
+            p.peer_mode = peers->mode; p.peer_world = peers->world; p.peer_rank = peers->rank; p.per_log = peers->per_log;
+            p.peer_off = peers->off;
+            for (int q = 0; q < 8; ++q) p.peer[q] = peers->peer[q];
+        }
         unsigned E = 1u << (p.k + p.c_log);
         unsigned threads = E >> 1; if (threads < 1) threads = 1;
         dim3 grid((unsigned)(n / E), batch);
@@ -503,6 +534,26 @@ void ntt_inverse_local_stages(pk_ctx* ctx, const fr_t* src, fr_t* dst, int log_b
     }
     run_passes<true>(ctx, src, dst, log_block, nullptr, nullptr, nullptr, 1, 0, 0, 0, log_total);
 }
+// the same stages with the all-to-all FUSED into the last pass: element k of this rank's block is stored straight into
+// rank (k >> per_log)'s receive buffer at [rank][k mod 2^per_log] (peer[q] = that buffer as mapped into this process)
+void ntt_inverse_local_stages_scatter(pk_ctx* ctx, const fr_t* src, fr_t* scratch, int log_block, int log_total, fr_t* const* peer,
+                                      int world, int rank, int per_log) {
+    PK_REQUIRE(log_block >= 1 && world <= 8, PK_ERR_INVALID, "bad fused all-to-all geometry");
+    PeerStore ps;
+    ps.mode = 2; ps.world = world; ps.rank = rank; ps.per_log = per_log;
+    for (int q = 0; q < world; ++q) ps.peer[q] = peer[q];
+    run_passes<true>(ctx, src, scratch, log_block, nullptr, nullptr, nullptr, 1, 0, 0, 0, log_total, &ps);
+}
+// inverse NTT (bit-reversed in, natural out, scaled by 1/n) whose result is stored into EVERY rank's copy of the output
+// array (peer[q] + off): the all-gather of the coefficients fused into the transform's last pass
+void ntt_inverse_from_bitrev_bcast(pk_ctx* ctx, const fr_t* src, fr_t* scratch, int log_n, fr_t* const* peer, int world, size_t off) {
+    PK_REQUIRE(log_n >= 1 && world <= 8, PK_ERR_INVALID, "bad fused all-gather geometry");
+    PeerStore ps;
+    ps.mode = 1; ps.world = world; ps.off = off;
+    for (int q = 0; q < world; ++q) ps.peer[q] = peer[q];
+    fr_t ninv = fr_t::from_u32(2).inverse().pow_u64(log_n);
+    run_passes<true>(ctx, src, scratch, log_n, nullptr, nullptr, &ninv, 1, 0, 0, 0, 0, &ps);
+}
 
 // ---------------------------------------------------------------- pieces of the coset-sharded quotient (sharded prover)
 // b[i] = c^i * sum_{u < F} a[i + u * n/F] * kappa^u  (i < n/F): the polynomial a (n coefficients) restricted to the coset
@@ -539,7 +590,11 @@ void omega_scale(pk_ctx* ctx, const fr_t* a, fr_t* out, int log_n) {
 // G ranks: in[c][k'] = element k0 + k' of rank c's block after its local stages (what the all-to-all delivers), block
 // length m = 2^L / G.  One thread owns the G values of one k, runs the stages in registers and writes
 // out[c][k'] = coefficient (c * m + k0 + k') times g7inv^index / 2^L  (kscale[k'] = g7inv^(k0 + k') / 2^L, cscale[c] = g7inv^(c m)).
-struct CrossArgs { fr_t cscale[8]; };
+struct CrossArgs {
+    fr_t cscale[8];
+    fr_t* peer[8];      // fused all-gather: peer[q] = rank q's full coefficient array (nullptr: write `out` only)
+    int peer_world;
+};
 template <int G> __global__ void __launch_bounds__(128) ntt_cross_kernel(const fr_t* in, fr_t* out, const fr_t* kscale, CrossArgs ca,
                                                                          const fr_t* tw, int tw_shift, int L, size_t m, size_t k0,
                                                                          size_t per) {
@@ -568,16 +623,23 @@ template <int G> __global__ void __launch_bounds__(128) ntt_cross_kernel(const f
     }
     const fr_t ks = ldg_fp(kscale + kk);
 #pragma unroll
-    for (int c = 0; c < G; ++c) st_fp(out + (size_t)c * per + kk, v[c] * ks * ca.cscale[c]);
+    for (int c = 0; c < G; ++c) {
+        const fr_t r = v[c] * ks * ca.cscale[c];
+        if (ca.peer_world == 0) st_fp(out + (size_t)c * per + kk, r);
+        else
+            for (int q = 0; q < ca.peer_world; ++q) st_fp(ca.peer[q] + (size_t)c * m + k, r);  // coefficient index c m + k
+    }
 }
 void ntt_inverse_cross_stages(pk_ctx* ctx, const fr_t* in, fr_t* out, const fr_t* kscale, const fr_t* cscale, int G, int log_total,
-                              size_t k0) {
+                              size_t k0, fr_t* const* peer) {
     PK_REQUIRE(G == 1 || G == 2 || G == 4 || G == 8, PK_ERR_INVALID, "the sharded prover runs on 1, 2, 4 or 8 ranks");
     ensure_twiddles(ctx, log_total);
     DomainCache* dc = ctx->domains;
     const size_t m = (size_t(1) << log_total) / G, per = m / G;
     CrossArgs ca;
     for (int c = 0; c < 8; ++c) ca.cscale[c] = c < G ? cscale[c] : fr_t::one();
+    ca.peer_world = peer ? G : 0;
+    for (int q = 0; q < 8; ++q) ca.peer[q] = (peer && q < G) ? peer[q] : nullptr;
     const int ts = dc->tw_log - log_total;
     dim3 grid = grid1d(per, 128);
     if (G == 1) ntt_cross_kernel<1><<<grid, 128, 0, ctx->stream>>>(in, out, kscale, ca, dc->tw.p, ts, log_total, m, k0, per);

@@ -1,6 +1,6 @@
 """Condenses `ncu --page raw --csv` exports (one file per kernel family, gpurun_out/raw_<kernel>_r01.csv) into
-profiles/ncu_summary_r01.json: per captured launch the duration, DRAM bytes, and the pipe / issue utilisation figures
-DESIGN.md and bench.py's roofline.traffic quote.   python tools/ncu_summary.py gpurun_out/raw_*_r01.csv"""
+a summary JSON: per captured launch the duration, DRAM bytes, and the pipe / issue utilisation figures DESIGN.md and
+bench.py's roofline.traffic quote.   python tools/ncu_summary.py [--out profiles/ncu_summary_r02.json] gpurun_out/raw_*.csv"""
 import csv, json, os, sys
 
 KEYS = {
@@ -42,11 +42,15 @@ def num(x):
 
 def main():
     out = {}
-    for path in sys.argv[1:]:
+    args = sys.argv[1:]
+    dest = "profiles/ncu_summary_r01.json"
+    if args and args[0] == "--out":
+        dest, args = args[1], args[2:]
+    for path in args:
         rows = list(csv.reader(open(path)))
         hdr = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
         names, units = rows[hdr], rows[hdr + 1]
-        fam = os.path.basename(path).replace("raw_", "").replace("_r01.csv", "")
+        fam = os.path.basename(path).replace("raw_", "").replace("_r01.csv", "").replace(".csv", "")
         out[fam] = []
         for r in rows[hdr + 2:]:
             if len(r) != len(names):
@@ -64,7 +68,7 @@ def main():
                     else:
                         d[KEYS[n]] = v
             out[fam].append(d)
-    json.dump(out, open("profiles/ncu_summary_r01.json", "w"), indent=1)
+    json.dump(out, open(dest, "w"), indent=1)
     for fam, ls in out.items():
         for d in ls:
             print(fam, {k: (round(v, 3) if isinstance(v, float) else v) for k, v in d.items() if k not in ("kernel", "time_unit_raw")})
