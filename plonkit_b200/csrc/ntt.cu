@@ -140,14 +140,10 @@ __device__ __forceinline__ void ntt_store(const NttPass& p, fr_t* dst, size_t g,
     }
 }
 
-// Shared-memory index swizzle: the low three index bits are complemented when bit 3 is set.  In the stages whose butterfly
-// span is 1, 2 or 4 elements the eight lanes of a 128-byte wavefront touch indices whose low three bits take only four
-// values (the span bit is fixed); bit 3 varies instead, and the swizzle folds it back in: eight distinct 16-byte bank
-// groups again (1.6 M bank conflicts per contiguous pass without it, ncu).  It is a bijection, and a no-op for accesses
-// whose low three bits already vary.
-__device__ __forceinline__ unsigned swz(unsigned l) { return l ^ (((l >> 3) & 1u) * 7u); }
+// (An index swizzle l ^ (bit3(l) ? 7 : 0), which removes the 1.6 M bank conflicts of the span-1/2/4 stages of the contiguous
+// pass, was measured: 2^20 0.213 vs 0.204 ms, 2^24 3.74 vs 3.54 ms — its two extra ALU operations per access cost more
+// issue slots than the conflicts cost shared-memory cycles.  Not used.)
 __device__ __forceinline__ fr_t lds_fr(const uint4* s_lo, const uint4* s_hi, unsigned l) {
-    l = swz(l);
     uint4 a = s_lo[l], b = s_hi[l];
     fr_t r;
     r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
@@ -155,7 +151,6 @@ __device__ __forceinline__ fr_t lds_fr(const uint4* s_lo, const uint4* s_hi, uns
     return r;
 }
 __device__ __forceinline__ void sts_fr(uint4* s_lo, uint4* s_hi, unsigned l, const fr_t& x) {
-    l = swz(l);
     s_lo[l] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
     s_hi[l] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
 }
