@@ -60,12 +60,10 @@ struct pk_dist_setup {
     DevBuf<g1_xyzz_t> part_pts, all_pts;       // [16], [G][16]
     DevBuf<fr_t> xs, xr;                       // [16], [G][16]: partial scalars of a sharded scan / evaluation and their all-gather
     DevBuf<fr_t> zchunk;                       // [cn]
-    // Fused exchanges: when every rank can map its peers' buffers (NVLink peer access in one process, CUDA IPC between
-    // processes), the last pass of a transform stores straight into the peers' memory instead of a collective afterwards
+    // Fused all-to-all: when every rank can map its peers' receive buffers (NVLink peer access in one process, CUDA IPC
+    // between processes), the last block-local pass of the quotient's inverse NTT stores straight into the peers' memory
     bool fused = false;
-    fr_t* peer_w[8] = {};                      // every rank's w_coef  [4][n]
     fr_t* peer_a2a[8] = {};                    // every rank's a2a     [G][m/G]
-    fr_t* peer_t4[8] = {};                     // every rank's t4      [4n]
 };
 
 namespace pk {
@@ -280,13 +278,8 @@ void dist_setup_create(pk_ctx* ctx, const pk_assembly* as, pk_dist_setup** out) 
         static const int want_fused = [] { const char* e = getenv("PK_DIST_FUSED"); return e ? atoi(e) : 1; }();
         if (want_fused && G > 1) {
             void* tmp[8];
-            bool ok = ctx->comm->map_peers(s->w_coef.p, 4 * n * sizeof(fr_t), tmp, st);
-            for (int q = 0; q < G; ++q) s->peer_w[q] = static_cast<fr_t*>(tmp[q]);
-            bool ok2 = ctx->comm->map_peers(s->a2a.p, s->m * sizeof(fr_t), tmp, st);
+            s->fused = ctx->comm->map_peers(s->a2a.p, s->m * sizeof(fr_t), tmp, st);
             for (int q = 0; q < G; ++q) s->peer_a2a[q] = static_cast<fr_t*>(tmp[q]);
-            bool ok3 = ctx->comm->map_peers(s->t4.p, 4 * n * sizeof(fr_t), tmp, st);
-            for (int q = 0; q < G; ++q) s->peer_t4[q] = static_cast<fr_t*>(tmp[q]);
-            s->fused = ok && ok2 && ok3;
         }
     } catch (...) {
         delete s;
@@ -357,24 +350,9 @@ void dist_prove(pk_ctx* ctx, pk_dist_setup* s, const uint64_t* var_values, uint6
         // [4][n] coefficient array and the blocks are all-gathered in place (4n 32 B in total)
         const fr_t* polys[4];
         const uint64_t blk = 4 * n / G, b0 = (uint64_t)s->rank * blk;
-        if (s->fused) {
-            // fused: the last pass of each inverse NTT stores its result into EVERY rank's coefficient array over NVLink
-            // (for G > 4 two ranks compute the same wire and each publishes its half of it)
-            for (int c = (int)(b0 / n); c <= (int)((b0 + blk - 1) / n); ++c) {
-                if (blk >= n) {
-                    ntt_inverse_from_bitrev_bcast(ctx, s->w_br.p + c * n, s->tmp_a.p, log_n, s->peer_w, G, (size_t)c * n);
-                } else {
-                    ntt_inverse_from_bitrev(ctx, s->w_br.p + c * n, s->tmp_a.p, log_n);
-                    const size_t off = b0 - (size_t)c * n;   // this rank's slice of wire c
-                    for (int q = 0; q < G; ++q)
-                        PK_CUDA(cudaMemcpyAsync(s->peer_w[q] + b0, s->tmp_a.p + off, blk * sizeof(fr_t), cudaMemcpyDefault, st));
-                }
-            }
-            CommTimer t(ctx, 0, (uint64_t)(G - 1) * blk * sizeof(fr_t));
-            ctx->comm->stream_barrier(st);
-        } else {
-            for (int c = (int)(b0 / n); c <= (int)((b0 + blk - 1) / n); ++c)
-                ntt_inverse_from_bitrev(ctx, s->w_br.p + c * n, s->w_coef.p + c * n, log_n);
+        for (int c = (int)(b0 / n); c <= (int)((b0 + blk - 1) / n); ++c)
+            ntt_inverse_from_bitrev(ctx, s->w_br.p + c * n, s->w_coef.p + c * n, log_n);
+        {
             CommTimer t(ctx, 0, (uint64_t)(G - 1) * blk * sizeof(fr_t));
             ctx->comm->all_gather(s->w_coef.p + b0, s->w_coef.p, blk * sizeof(fr_t), st);
         }
@@ -449,23 +427,20 @@ void dist_prove(pk_ctx* ctx, pk_dist_setup* s, const uint64_t* var_values, uint6
     // size-4n inverse: local stages, all-to-all, cross stages (+ scaling), all-gather of the coefficients
     const uint64_t per = m / G;
     if (s->fused) {
-        // the all-to-all rides on the last local pass (stores into the peers' receive buffers), the all-gather of the
-        // coefficients on the cross-stage kernel (stores into every rank's t4): two kernels, two stream barriers, no copy
+        // the all-to-all rides on the last local pass: every element is stored straight into the receive buffer of the one
+        // rank that needs it (peer stores over NVLink, no amplification), then one stream barrier
         ntt_inverse_local_stages_scatter(ctx, s->t_part.p, s->t_part.p, ilog2(m), log_n + 2, s->peer_a2a, G, s->rank, ilog2(per));
-        {
-            CommTimer t(ctx, 1, (uint64_t)(G - 1) * per * sizeof(fr_t));
-            ctx->comm->stream_barrier(st);
-        }
-        ntt_inverse_cross_stages(ctx, s->a2a.p, s->t_part.p, s->kscale.p, s->cscale, G, log_n + 2, (size_t)s->rank * per, s->peer_t4);
-        CommTimer t(ctx, 2, (uint64_t)(G - 1) * G * per * sizeof(fr_t));
+        CommTimer t(ctx, 1, (uint64_t)(G - 1) * per * sizeof(fr_t));
         ctx->comm->stream_barrier(st);
     } else {
         ntt_inverse_local_stages(ctx, s->t_part.p, s->t_part.p, ilog2(m), log_n + 2);
-        {
-            CommTimer t(ctx, 1, (uint64_t)(G - 1) * per * sizeof(fr_t));
-            ctx->comm->all_to_all(s->t_part.p, s->a2a.p, per * sizeof(fr_t), st);
-        }
-        ntt_inverse_cross_stages(ctx, s->a2a.p, s->t_part.p, s->kscale.p, s->cscale, G, log_n + 2, (size_t)s->rank * per);
+        CommTimer t(ctx, 1, (uint64_t)(G - 1) * per * sizeof(fr_t));
+        ctx->comm->all_to_all(s->t_part.p, s->a2a.p, per * sizeof(fr_t), st);
+    }
+    ntt_inverse_cross_stages(ctx, s->a2a.p, s->t_part.p, s->kscale.p, s->cscale, G, log_n + 2, (size_t)s->rank * per);
+    {
+        // the coefficients are needed by every rank: an all-gather (NCCL replicates in the switch; storing them G times
+        // from the kernel was measured and is slower)
         const void* send[8];
         void* recv[8];
         for (int c = 0; c < G; ++c) { send[c] = s->t_part.p + (size_t)c * per; recv[c] = s->t4.p + (size_t)c * m; }

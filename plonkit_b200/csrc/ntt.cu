@@ -121,19 +121,15 @@ struct NttPass {
     int c_log;           // log2 of contiguous columns per tile (c_log <= bl)
     int tw_shift;        // tw_log - L
     size_t src_stride, dst_stride, pre_stride;
-    // Fused exchange (sharded prover): the pass's results go straight into the peers' memory over NVLink instead of dst.
-    //   peer_mode 1 (all-gather): element g -> peer[q] + peer_off + g for EVERY rank q
-    //   peer_mode 2 (all-to-all): element g -> peer[g >> per_log] + (rank << per_log) + (g & (2^per_log - 1))
-    int peer_mode, peer_world, peer_rank, per_log;
-    size_t peer_off;
+    // Fused all-to-all (sharded prover): the pass's results go straight into the peers' memory over NVLink instead of dst:
+    // element g -> peer[g >> per_log] + (rank << per_log) + (g & (2^per_log - 1))
+    int peer_mode, peer_rank, per_log;
     fr_t* peer[8];
 };
-struct PeerStore { int mode = 0, world = 1, rank = 0, per_log = 0; size_t off = 0; fr_t* peer[8] = {}; };
+struct PeerStore { int mode = 0, rank = 0, per_log = 0; fr_t* peer[8] = {}; };
 __device__ __forceinline__ void ntt_store(const NttPass& p, fr_t* dst, size_t g, const fr_t& x) {
     if (p.peer_mode == 0) {
         st_fp(dst + g, x);
-    } else if (p.peer_mode == 1) {
-        for (int q = 0; q < p.peer_world; ++q) st_fp(p.peer[q] + p.peer_off + g, x);
     } else {
         const size_t q = g >> p.per_log;
         st_fp(p.peer[q] + ((size_t)p.peer_rank << p.per_log) + (g & ((size_t(1) << p.per_log) - 1)), x);
@@ -452,8 +448,7 @@ static void run_passes(pk_ctx* ctx, const fr_t* src, fr_t* dst, int L, const fr_
         if (last && !post && post_const) { p.use_post_const = 1; p.post_const = *post_const; }
         p.L = L_tw; p.bl = pl.bl[i]; p.k = pl.k[i]; p.c_log = pl.c_log[i];
         if (last && peers && peers->mode) {  // the LAST pass writes into the peers' memory
-            p.peer_mode = peers->mode; p.peer_world = peers->world; p.peer_rank = peers->rank; p.per_log = peers->per_log;
-            p.peer_off = peers->off;
+            p.peer_mode = peers->mode; p.peer_rank = peers->rank; p.per_log = peers->per_log;
             for (int q = 0; q < 8; ++q) p.peer[q] = peers->peer[q];
         }
         unsigned E = 1u << (p.k + p.c_log);
@@ -535,21 +530,10 @@ void ntt_inverse_local_stages_scatter(pk_ctx* ctx, const fr_t* src, fr_t* scratc
                                       int world, int rank, int per_log) {
     PK_REQUIRE(log_block >= 1 && world <= 8, PK_ERR_INVALID, "bad fused all-to-all geometry");
     PeerStore ps;
-    ps.mode = 2; ps.world = world; ps.rank = rank; ps.per_log = per_log;
+    ps.mode = 1; ps.rank = rank; ps.per_log = per_log;
     for (int q = 0; q < world; ++q) ps.peer[q] = peer[q];
     run_passes<true>(ctx, src, scratch, log_block, nullptr, nullptr, nullptr, 1, 0, 0, 0, log_total, &ps);
 }
-// inverse NTT (bit-reversed in, natural out, scaled by 1/n) whose result is stored into EVERY rank's copy of the output
-// array (peer[q] + off): the all-gather of the coefficients fused into the transform's last pass
-void ntt_inverse_from_bitrev_bcast(pk_ctx* ctx, const fr_t* src, fr_t* scratch, int log_n, fr_t* const* peer, int world, size_t off) {
-    PK_REQUIRE(log_n >= 1 && world <= 8, PK_ERR_INVALID, "bad fused all-gather geometry");
-    PeerStore ps;
-    ps.mode = 1; ps.world = world; ps.off = off;
-    for (int q = 0; q < world; ++q) ps.peer[q] = peer[q];
-    fr_t ninv = fr_t::from_u32(2).inverse().pow_u64(log_n);
-    run_passes<true>(ctx, src, scratch, log_n, nullptr, nullptr, &ninv, 1, 0, 0, 0, 0, &ps);
-}
-
 // ---------------------------------------------------------------- pieces of the coset-sharded quotient (sharded prover)
 // b[i] = c^i * sum_{u < F} a[i + u * n/F] * kappa^u  (i < n/F): the polynomial a (n coefficients) restricted to the coset
 // c * H_{n/F}, on which X^(n/F) is the constant kappa = c^(n/F); cpow[i] = c^i.  A forward NTT of size n/F finishes the
@@ -585,11 +569,7 @@ void omega_scale(pk_ctx* ctx, const fr_t* a, fr_t* out, int log_n) {
 // G ranks: in[c][k'] = element k0 + k' of rank c's block after its local stages (what the all-to-all delivers), block
 // length m = 2^L / G.  One thread owns the G values of one k, runs the stages in registers and writes
 // out[c][k'] = coefficient (c * m + k0 + k') times g7inv^index / 2^L  (kscale[k'] = g7inv^(k0 + k') / 2^L, cscale[c] = g7inv^(c m)).
-struct CrossArgs {
-    fr_t cscale[8];
-    fr_t* peer[8];      // fused all-gather: peer[q] = rank q's full coefficient array (nullptr: write `out` only)
-    int peer_world;
-};
+struct CrossArgs { fr_t cscale[8]; };
 template <int G> __global__ void __launch_bounds__(128) ntt_cross_kernel(const fr_t* in, fr_t* out, const fr_t* kscale, CrossArgs ca,
                                                                          const fr_t* tw, int tw_shift, int L, size_t m, size_t k0,
                                                                          size_t per) {
@@ -618,23 +598,16 @@ template <int G> __global__ void __launch_bounds__(128) ntt_cross_kernel(const f
     }
     const fr_t ks = ldg_fp(kscale + kk);
 #pragma unroll
-    for (int c = 0; c < G; ++c) {
-        const fr_t r = v[c] * ks * ca.cscale[c];
-        if (ca.peer_world == 0) st_fp(out + (size_t)c * per + kk, r);
-        else
-            for (int q = 0; q < ca.peer_world; ++q) st_fp(ca.peer[q] + (size_t)c * m + k, r);  // coefficient index c m + k
-    }
+    for (int c = 0; c < G; ++c) st_fp(out + (size_t)c * per + kk, v[c] * ks * ca.cscale[c]);
 }
 void ntt_inverse_cross_stages(pk_ctx* ctx, const fr_t* in, fr_t* out, const fr_t* kscale, const fr_t* cscale, int G, int log_total,
-                              size_t k0, fr_t* const* peer) {
+                              size_t k0) {
     PK_REQUIRE(G == 1 || G == 2 || G == 4 || G == 8, PK_ERR_INVALID, "the sharded prover runs on 1, 2, 4 or 8 ranks");
     ensure_twiddles(ctx, log_total);
     DomainCache* dc = ctx->domains;
     const size_t m = (size_t(1) << log_total) / G, per = m / G;
     CrossArgs ca;
     for (int c = 0; c < 8; ++c) ca.cscale[c] = c < G ? cscale[c] : fr_t::one();
-    ca.peer_world = peer ? G : 0;
-    for (int q = 0; q < 8; ++q) ca.peer[q] = (peer && q < G) ? peer[q] : nullptr;
     const int ts = dc->tw_log - log_total;
     dim3 grid = grid1d(per, 128);
     if (G == 1) ntt_cross_kernel<1><<<grid, 128, 0, ctx->stream>>>(in, out, kscale, ca, dc->tw.p, ts, log_total, m, k0, per);

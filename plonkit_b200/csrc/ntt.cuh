@@ -46,13 +46,11 @@ void icoset4n_from_slots(pk_ctx* ctx, const fr_t* vals4n, fr_t* coeffs4n, int lo
 // bit-reversed input; no scaling
 void ntt_inverse_local_stages(pk_ctx* ctx, const fr_t* src, fr_t* dst, int log_block, int log_total);
 // the upper log2(G) stages after the all-to-all, with the coset / size scaling fused (see ntt.cu)
-// peer != nullptr: every result is stored into all ranks' coefficient arrays (fused all-gather), `out` is not written
 void ntt_inverse_cross_stages(pk_ctx* ctx, const fr_t* in, fr_t* out, const fr_t* kscale, const fr_t* cscale, int G, int log_total,
-                              size_t k0, fr_t* const* peer = nullptr);
-// fused compute + exchange variants: the last pass stores into the peers' memory (see ntt.cu)
+                              size_t k0);
+// the block-local stages with the all-to-all fused in: the last pass stores into the peers' receive buffers (see ntt.cu)
 void ntt_inverse_local_stages_scatter(pk_ctx* ctx, const fr_t* src, fr_t* scratch, int log_block, int log_total, fr_t* const* peer,
                                       int world, int rank, int per_log);
-void ntt_inverse_from_bitrev_bcast(pk_ctx* ctx, const fr_t* src, fr_t* scratch, int log_n, fr_t* const* peer, int world, size_t off);
 // b[i] = cpow[i] * sum_u a[i + u nf] kappa^u, i < nf: restriction of a to the coset c H_nf (cpow[i] = c^i, kappa = c^nf)
 void coset_fold(pk_ctx* ctx, const fr_t* a, const fr_t* cpow, const fr_t& kappa, int F, size_t nf, fr_t* b);
 // out[i] = a[i] w_n^i: coefficients of a(w X)
