@@ -434,7 +434,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--inflight", type=int, default=3, help="independent provers (proofs in flight) per GPU")
     ap.add_argument("--no-shard", action="store_true", help="N > 1: skip the sharded single-proof (latency) leg")
-    ap.add_argument("--ref-budget-s", type=float, default=300.0, help="--impl reference: wall-clock budget for the CPU proofs")
+    ap.add_argument("--ref-budget-s", type=float, default=360.0, help="--impl reference: wall-clock budget for the CPU proofs")
     args = ap.parse_args()
     if args.warmup < 1:
         args.warmup = 1

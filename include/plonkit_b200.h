@@ -224,6 +224,9 @@ int pk_timer_end(pk_ctx* ctx, double* ms);
 int pk_bench_ntt(pk_ctx* ctx, uint32_t log_n, int iters, double* ms_per_iter);
 int pk_bench_msm(pk_ctx* ctx, uint64_t n, int iters, double* ms_per_iter);
 int pk_bench_fieldmul(pk_ctx* ctx, int which /*0 Fr, 1 Fq*/, double* gmuls_per_s);
+/* device-resident MSM timing with a scalar pattern: 0 pseudo-random, 1 witness-like (40 % zero, 10 % one, 50 % random:
+ * what the Lagrange path feeds), 2 all ones */
+int pk_bench_msm_pattern(pk_ctx* ctx, uint64_t n, int pattern, int iters, double* ms_per_iter);
 
 #ifdef __cplusplus
 }

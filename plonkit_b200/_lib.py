@@ -28,7 +28,7 @@ EXPORTS = [
     "pk_srs_gen", "pk_setup_create_gated", "pk_setup_commitments_gated", "pk_ntt", "pk_lde4",
     "pk_msm_g1", "pk_ec_intt_g1", "pk_setup_create", "pk_setup_destroy", "pk_setup_commitments", "pk_witness_upload",
     "pk_prove", "pk_profile_enable", "pk_profile_reset", "pk_profile_get", "pk_bench_ntt", "pk_bench_msm",
-    "pk_bench_fieldmul", "pk_timer_begin", "pk_timer_end", "pk_g1_sum", "pk_dev_fr_convert", "pk_dev_ntt_rows",
+    "pk_bench_fieldmul", "pk_bench_msm_pattern", "pk_timer_begin", "pk_timer_end", "pk_g1_sum", "pk_dev_fr_convert", "pk_dev_ntt_rows",
     "pk_dev_twiddle", "pk_poly_evaluate_at", "pk_poly_divide_by_linear", "pk_poly_shifted_grand_product",
     "pk_poly_batch_inversion", "pk_dev_ec_from_affine", "pk_dev_ec_ntt_rows", "pk_dev_ec_twiddle", "pk_dev_ec_to_affine",
     "pk_comm_group_create", "pk_comm_group_destroy", "pk_comm_attach_group", "pk_comm_nccl_unique_id", "pk_comm_attach_nccl",
@@ -132,6 +132,7 @@ def load():
     lib.pk_bench_ntt.argtypes = [vp, u32, i32, ctypes.POINTER(ctypes.c_double)]
     lib.pk_bench_msm.argtypes = [vp, u64, i32, ctypes.POINTER(ctypes.c_double)]
     lib.pk_bench_fieldmul.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double)]
+    lib.pk_bench_msm_pattern.argtypes = [vp, u64, i32, i32, ctypes.POINTER(ctypes.c_double)]
     lib.pk_g1_sum.argtypes = [vp, u64, vp]
     lib.pk_dev_fr_convert.argtypes = [vp, vp, u64, i32]
     lib.pk_dev_ntt_rows.argtypes = [vp, vp, u32, u64, i32]
@@ -345,6 +346,11 @@ class Context:
     def bench_msm(self, n, iters=3):
         ms = ctypes.c_double()
         self._check(self._lib.pk_bench_msm(self._h, n, iters, ctypes.byref(ms)))
+        return ms.value
+
+    def bench_msm_pattern(self, n, pattern, iters=3):
+        ms = ctypes.c_double()
+        self._check(self._lib.pk_bench_msm_pattern(self._h, n, pattern, iters, ctypes.byref(ms)))
         return ms.value
 
     def bench_fieldmul(self, which=0):

@@ -607,6 +607,39 @@ int pk_bench_msm(pk_ctx* ctx, uint64_t n, int iters, double* ms_per_iter) {
 
 }  // extern "C"
 
+// scalars for pk_bench_msm_pattern: 1 = the witness-like mix of SURVEY 8(d) (40 % zero, 10 % one, 50 % uniform), 2 = all ones
+__global__ void msm_pattern_kernel(fr_t* s, size_t n, int pattern) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t h = (uint32_t)i * 2654435761u;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    const uint32_t r = h % 10;
+    if (pattern == 2 || (pattern == 1 && r == 4)) st_fp(s + i, fr_t::one());
+    else if (pattern == 1 && r < 4) st_fp(s + i, fr_t::zero());
+}
+extern "C" int pk_bench_msm_pattern(pk_ctx* ctx, uint64_t n, int pattern, int iters, double* ms_per_iter) {
+    PK_API_BEGIN(ctx)
+    PK_REQUIRE(ms_per_iter && iters > 0 && n >= 1 && pattern >= 0 && pattern <= 2, PK_ERR_INVALID, "bad argument");
+    PK_REQUIRE(ctx->srs && ctx->srs->n >= n, PK_ERR_DEGREE_TOO_LARGE, "MSM longer than the resident SRS");
+    DevBuf<fr_t> s(n);
+    poly_powers(ctx, s.p, fr_t::from_u32(0x6b697431u).sqr().sqr(), n);
+    if (pattern) msm_pattern_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(s.p, n, pattern);
+    msm_run(ctx, s.p, n, 0);
+    cudaEvent_t e0, e1;
+    PK_CUDA(cudaEventCreate(&e0));
+    PK_CUDA(cudaEventCreate(&e1));
+    PK_CUDA(cudaEventRecord(e0, ctx->stream));
+    for (int i = 0; i < iters; ++i) msm_run(ctx, s.p, n, 0);
+    PK_CUDA(cudaEventRecord(e1, ctx->stream));
+    PK_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    PK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_per_iter = ms / iters;
+    PK_API_END(ctx)
+}
+
 // field-multiplier throughput microbenchmark: the integer roofline the NTT/MSM kernels live under
 template <class F> __global__ void fieldmul_bench_kernel(F* out, int iters) {
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
