@@ -97,3 +97,22 @@ def test_sharded_prover_over_nccl_two_processes():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "sharded == single GPU: True" in r.stdout
+
+
+def test_sharded_prover_threads_on_distinct_gpus(orc):
+    """The in-process transport across REAL devices (peer copies and peer stores over NVLink): one rank per GPU as threads of
+    this process.  Needs >= 2 GPUs; on the one-GPU box the same transport runs with every rank on device 0 (tests above)."""
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 8 if ngpu >= 8 else (4 if ngpu >= 4 else 2)
+    asm = synth.poseidon_chain_assembly(16)
+    srs = orc.srs_gen(asm.n, 42, threads=16)
+    want = orc.prove(asm.n, asm.num_inputs, asm.wire_idx, asm.var_values, asm.selectors, srs, threads=16)
+    sp = plonk.ShardedProver(asm, Crs(srs), world, devices=list(range(world)))
+    try:
+        assert sp.prove(asm).to_bytes() == want
+        assert sp.prove(asm).to_bytes() == want      # second proof: the peers' receive buffers are reused
+    finally:
+        sp.close()
