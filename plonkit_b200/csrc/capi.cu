@@ -90,6 +90,9 @@ int pk_create(int device, pk_ctx** out) {
         PK_CUDA(cudaGetDeviceProperties(&prop, device));
         ctx->sm_count = prop.multiProcessorCount;
         PK_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        PK_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+        PK_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        PK_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
         ctx->pinned_bytes = 1 << 16;
         PK_CUDA(cudaMallocHost(&ctx->pinned, ctx->pinned_bytes));
     } catch (const PkError&) {
@@ -115,6 +118,9 @@ void pk_destroy(pk_ctx* ctx) {
         if (it != g_extras.end()) { delete it->second; g_extras.erase(it); }
     }
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -86,6 +86,11 @@ struct Comm;        // comm.cuh
 struct pk_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    // side stream: work of a proof that does not depend on the commitment in flight (the coset LDEs of polynomials that
+    // are already in coefficient form) runs here, beside the MSM kernels on `stream`, and is joined before its first use
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool side_pending = false;
     int sm_count = 148;
     std::string last_error;
     pk::Profile prof;
@@ -122,6 +127,28 @@ struct ScopedKernelTimer {
     }
 };
 void profile_resolve(pk_ctx* ctx);  // capi.cu
+
+// Scope in which the library's launches go to the side stream: it starts after everything enqueued on the main stream so
+// far; side_join() makes the main stream wait for everything the side stream was given.
+struct SideStreamScope {
+    pk_ctx* ctx;
+    cudaStream_t main;
+    explicit SideStreamScope(pk_ctx* c) : ctx(c), main(c->stream) {
+        cudaEventRecord(ctx->ev_fork, main);
+        cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0);
+        ctx->stream = ctx->side;
+    }
+    ~SideStreamScope() {
+        cudaEventRecord(ctx->ev_join, ctx->side);
+        ctx->stream = main;
+        ctx->side_pending = true;
+    }
+};
+static inline void side_join(pk_ctx* ctx) {
+    if (!ctx->side_pending) return;
+    cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
+    ctx->side_pending = false;
+}
 
 static inline int ilog2(uint64_t x) { int l = 0; while ((uint64_t(1) << (l + 1)) <= x) ++l; return l; }
 

@@ -357,6 +357,10 @@ void dist_prove(pk_ctx* ctx, pk_dist_setup* s, const uint64_t* var_values, uint6
             ctx->comm->all_gather(s->w_coef.p + b0, s->w_coef.p, blk * sizeof(fr_t), st);
         }
         for (int c = 0; c < 4; ++c) polys[c] = s->w_coef.p + c * n;
+        {
+            SideStreamScope side(ctx);  // this rank's range of the wire LDEs, beside the commitment kernels
+            for (int c = 0; c < 4; ++c) range_lde(s, s->w_coef.p + c * n, s->w_lde.p + c * m);
+        }
         dist_commit(s, polys, 4, Cw);
         for (int c = 0; c < 4; ++c) d_commit_g1(tr, Cw[c]);
     }
@@ -391,6 +395,10 @@ void dist_prove(pk_ctx* ctx, pk_dist_setup* s, const uint64_t* var_values, uint6
     }
     g1_affine_t Cz;
     {
+        {
+            SideStreamScope side(ctx);
+            range_lde(s, s->z_coef.p, s->z_lde.p);
+        }
         const fr_t* polys[1] = {s->z_coef.p};
         dist_commit(s, polys, 1, &Cz);
     }
@@ -399,8 +407,7 @@ void dist_prove(pk_ctx* ctx, pk_dist_setup* s, const uint64_t* var_values, uint6
     mark();
 
     // ---- round 3: the quotient on this rank's range of the coset domain
-    for (int c = 0; c < 4; ++c) range_lde(s, s->w_coef.p + c * n, s->w_lde.p + c * m);
-    range_lde(s, s->z_coef.p, s->z_lde.p);
+    side_join(ctx);  // the LDEs of the wires and of Z were started beside rounds 1 and 2
     omega_scale(ctx, s->z_coef.p, s->tmp_a.p, log_n);
     range_lde(s, s->tmp_a.p, s->znext_lde.p);
     omega_scale(ctx, s->w_coef.p + 3 * n, s->tmp_a.p, log_n);
@@ -593,7 +600,11 @@ void dist_prove(pk_ctx* ctx, pk_dist_setup* s, const uint64_t* var_values, uint6
 
 void dist_setup_free(pk_dist_setup* s) {
     if (!s) return;
-    if (s->ctx) { cudaSetDevice(s->ctx->device); cudaStreamSynchronize(s->ctx->stream); }
+    if (s->ctx) {
+        cudaSetDevice(s->ctx->device);
+        cudaStreamSynchronize(s->ctx->stream);
+        if (s->ctx->side) cudaStreamSynchronize(s->ctx->side);  // LDEs of an aborted proof may still be in flight there
+    }
     delete s;
 }
 

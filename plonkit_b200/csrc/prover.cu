@@ -259,6 +259,12 @@ void prove(pk_ctx* ctx, pk_setup* s, const uint64_t* var_values, uint64_t nvars,
             ntt_inverse_from_bitrev(ctx, s->w_br.p + c * n, s->w_coef.p + c * n, log_n);
             polys[c] = s->w_coef.p + c * n;
         }
+        {
+            // the wire LDEs of round 3 need only the coefficients: they run on the side stream beside the commitment
+            // kernels (whose sort / reduction phases leave the multiplier pipe idle)
+            SideStreamScope side(ctx);
+            for (int c = 0; c < 4; ++c) lde4_slots(ctx, s->w_coef.p + c * n, s->w_lde.p + 4 * c * n, log_n);
+        }
         if (s->use_lagrange) {
             // commit_using_values: sum_i w(omega^i) [L_i(tau)] G over the witness values themselves (natural order)
             PK_REQUIRE(ctx->srs_lagrange && ctx->srs_lagrange->n == n, PK_ERR_DEGREE_TOO_LARGE,
@@ -284,14 +290,17 @@ void prove(pk_ctx* ctx, pk_setup* s, const uint64_t* var_values, uint64_t nvars,
     PK_REQUIRE(!total_den.is_zero(), PK_ERR_DIVISION_BY_ZERO, "zero denominator in the permutation grand product");
     z_finish(ctx, s->tmp_a.p, s->tmp_b.p, total_den.inverse(), s->tmp_c.p, log_n);
     ntt_inverse_from_bitrev(ctx, s->tmp_c.p, s->z_coef.p, log_n);
+    {
+        SideStreamScope side(ctx);
+        lde4_slots(ctx, s->z_coef.p, s->z_lde.p, log_n);
+    }
     const g1_affine_t Cz = msm_run(ctx, s->z_coef.p, n, 0);
     tr_commit_g1(tr, Cz);
     const fr_t alpha = tr_challenge(tr);
     clk.mark();  // phase 2
 
-    // ---- round 3: quotient on the coset 7*H_4n
-    for (int c = 0; c < 4; ++c) lde4_slots(ctx, s->w_coef.p + c * n, s->w_lde.p + 4 * c * n, log_n);
-    lde4_slots(ctx, s->z_coef.p, s->z_lde.p, log_n);
+    // ---- round 3: quotient on the coset 7*H_4n (the LDEs of the wires and of Z were started beside rounds 1 and 2)
+    side_join(ctx);
     CosetTables* ct = get_coset_tables(ctx, log_n);
     QuotientArgs qa;
     if (ni <= 8 && !s->gated) {
@@ -468,7 +477,11 @@ void setup_use_lagrange(pk_ctx* ctx, pk_setup* s, bool on) {
 }
 void setup_free(pk_setup* s) {
     if (!s) return;
-    if (s->ctx) { cudaSetDevice(s->ctx->device); cudaStreamSynchronize(s->ctx->stream); }
+    if (s->ctx) {
+        cudaSetDevice(s->ctx->device);
+        cudaStreamSynchronize(s->ctx->stream);
+        if (s->ctx->side) cudaStreamSynchronize(s->ctx->side);  // LDEs of an aborted proof may still be in flight there
+    }
     delete s;
 }
 }  // namespace pk
