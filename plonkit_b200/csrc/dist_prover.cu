@@ -60,6 +60,7 @@ struct pk_dist_setup {
     DevBuf<g1_xyzz_t> part_pts, all_pts;       // [16], [G][16]
     DevBuf<fr_t> xs, xr;                       // [16], [G][16]: partial scalars of a sharded scan / evaluation and their all-gather
     DevBuf<fr_t> zchunk;                       // [cn]
+    DevBuf<fr_t> shifted;                      // [n]: coefficients of d(wX) / Z(wX) on their way into an LDE (side stream)
     // Fused all-to-all: when every rank can map its peers' receive buffers (NVLink peer access in one process, CUDA IPC
     // between processes), the last block-local pass of the quotient's inverse NTT stores straight into the peers' memory
     bool fused = false;
@@ -233,7 +234,7 @@ void dist_setup_create(pk_ctx* ctx, const pk_assembly* as, pk_dist_setup** out) 
         s->tmp_a.alloc(n); s->tmp_b.alloc(n); s->tmp_c.alloc(n); s->fold.alloc(s->nf);
         s->zpow.alloc(n); s->zinvpow.alloc(n); s->zwpow.alloc(n); s->zwinvpow.alloc(n); s->r_coef.alloc(n);
         s->part_pts.alloc(16); s->all_pts.alloc((size_t)G * 16);
-        s->xs.alloc(16); s->xr.alloc((size_t)G * 16); s->zchunk.alloc(s->cn);
+        s->xs.alloc(16); s->xr.alloc((size_t)G * 16); s->zchunk.alloc(s->cn); s->shifted.alloc(n);
 
         // coset shifts of this rank's parts.  Slot sl of the layout is the coset g_sl H_n with g_sl = 7 w_4n^brev2(sl);
         // part q of a slot split 2^sub ways holds the natural indices j = brev_sub(q) mod 2^sub, i.e. the coset
@@ -358,8 +359,22 @@ void dist_prove(pk_ctx* ctx, pk_dist_setup* s, const uint64_t* var_values, uint6
         }
         for (int c = 0; c < 4; ++c) polys[c] = s->w_coef.p + c * n;
         {
-            SideStreamScope side(ctx);  // this rank's range of the wire LDEs, beside the commitment kernels
+            // this rank's range of the LDEs that need only the wire coefficients and the public inputs — the four wires,
+            // d(wX), PI — on the side stream, beside the commitment kernels
+            SideStreamScope side(ctx);
             for (int c = 0; c < 4; ++c) range_lde(s, s->w_coef.p + c * n, s->w_lde.p + c * m);
+            omega_scale(ctx, s->w_coef.p + 3 * n, s->shifted.p, log_n);
+            range_lde(s, s->shifted.p, s->dnext_lde.p);
+            if (ni <= 1) {
+                // PI(X) = in_0 L_0(X) = (in_0 / n) sum_j X^j: no transform needed for the common single-input circuit
+                const fr_t c0 = ni ? inputs[0] * fr_t::from_u32(2).inverse().pow_u64(log_n) : fr_t::zero();
+                fr_fill(ctx, s->pi_coef.p, c0, n);
+            } else {
+                PK_CUDA(cudaMemsetAsync(s->pi_coef.p, 0, n * sizeof(fr_t), ctx->stream));
+                pi_scatter(ctx, s->w_nat.p, s->pi_coef.p, ni, log_n);
+                ntt_inverse_from_bitrev(ctx, s->pi_coef.p, s->pi_coef.p, log_n);
+            }
+            range_lde(s, s->pi_coef.p, s->pi_lde.p);
         }
         dist_commit(s, polys, 4, Cw);
         for (int c = 0; c < 4; ++c) d_commit_g1(tr, Cw[c]);
@@ -396,8 +411,10 @@ void dist_prove(pk_ctx* ctx, pk_dist_setup* s, const uint64_t* var_values, uint6
     g1_affine_t Cz;
     {
         {
-            SideStreamScope side(ctx);
+            SideStreamScope side(ctx);  // Z and Z(wX) on this rank's range, beside the commitment of Z
             range_lde(s, s->z_coef.p, s->z_lde.p);
+            omega_scale(ctx, s->z_coef.p, s->shifted.p, log_n);
+            range_lde(s, s->shifted.p, s->znext_lde.p);
         }
         const fr_t* polys[1] = {s->z_coef.p};
         dist_commit(s, polys, 1, &Cz);
@@ -407,21 +424,7 @@ void dist_prove(pk_ctx* ctx, pk_dist_setup* s, const uint64_t* var_values, uint6
     mark();
 
     // ---- round 3: the quotient on this rank's range of the coset domain
-    side_join(ctx);  // the LDEs of the wires and of Z were started beside rounds 1 and 2
-    omega_scale(ctx, s->z_coef.p, s->tmp_a.p, log_n);
-    range_lde(s, s->tmp_a.p, s->znext_lde.p);
-    omega_scale(ctx, s->w_coef.p + 3 * n, s->tmp_a.p, log_n);
-    range_lde(s, s->tmp_a.p, s->dnext_lde.p);
-    if (ni <= 1) {
-        // PI(X) = in_0 L_0(X) = (in_0 / n) sum_j X^j: no transform needed for the common single-input circuit
-        const fr_t c0 = ni ? inputs[0] * fr_t::from_u32(2).inverse().pow_u64(log_n) : fr_t::zero();
-        fr_fill(ctx, s->pi_coef.p, c0, n);
-    } else {
-        PK_CUDA(cudaMemsetAsync(s->tmp_c.p, 0, n * sizeof(fr_t), st));
-        pi_scatter(ctx, s->w_nat.p, s->tmp_c.p, ni, log_n);
-        ntt_inverse_from_bitrev(ctx, s->tmp_c.p, s->pi_coef.p, log_n);
-    }
-    range_lde(s, s->pi_coef.p, s->pi_lde.p);
+    side_join(ctx);  // every LDE of this round was started beside the commitments of rounds 1 and 2
     QuotientArgs qa;
     qa.num_direct_inputs = -1;
     for (int c = 0; c < 4; ++c) { qa.w[c] = s->w_lde.p + c * m; qa.sig[c] = s->sigma_lde.p + c * m; }
