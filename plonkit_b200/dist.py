@@ -1,10 +1,12 @@
-"""Multi-GPU sharding of the commitment step (SURVEY.md §8e, row "MSM").
+"""Multi-GPU building blocks driven from Python (torch.distributed; NCCL over NVLink on the GPU box, gloo in the CPU tests).
 
-One process per GPU (torch.distributed; NCCL over NVLink on the GPU box, gloo in the CPU tests).  Every rank keeps
-the fixed-base window tables of ITS contiguous chunk of the SRS only, computes the partial multi-scalar
-multiplication of that chunk on its GPU, and the 64-byte affine partial sums are all-gathered and folded locally
-(`pk_g1_sum`): EC addition is not an NCCL reduce-op, so the "all-reduce" of the north star is all-gather + fold.
-Traffic per commitment: world_size x 64 B.
+The PROVER's multi-GPU path is not here: one proof cut across the GPUs of a node is `plonk.ShardedSetupForProver` /
+`plonk.ShardedProver` over the C ABI's `pk_dist_*` calls (csrc/dist_prover.cu), whose collectives the library issues itself.
+
+What lives here is `dump-lagrange` across GPUs — `DistributedEcIntt` / `lagrange_key_distributed`: `Crs::from_powers`
+(src/plonk.rs:179-185) as a four-step EC inverse NTT with one all-to-all of XYZZ points — and the two round-1 primitives it
+grew out of, kept as tested building blocks: `ShardedCommitter` (commitment with the SRS sharded by base chunk, partial sums
+all-gathered and folded with `pk_g1_sum`) and `DistributedNtt` (four-step field NTT with one all-to-all).
 """
 import numpy as np
 
