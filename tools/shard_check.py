@@ -77,11 +77,12 @@ def main():
         print("phase ms (rank 0): h2d %.2f | wires %.2f | Z %.2f | quotient %.2f | evals %.2f | openings %.2f" % tuple(phases[:6]))
         names = ("all-gather wire+Z coefficients", "all-to-all quotient", "all-gather quotient coefficients")
         fused = os.environ.get("PK_DIST_FUSED", "1") != "0"
-        print("exchanges %s:" % ("FUSED into the producing kernels (peer stores over NVLink); the time below is what stays exposed: "
-                                 "the stream barrier after the kernel" if fused else "as collectives after the producing kernels"))
+        print("bulk exchanges (CUDA events on the library stream; the all-to-all is %s):"
+              % ("FUSED into the last block-local NTT pass as peer stores over NVLink - what is timed is the stream barrier after it"
+                 if fused else "a collective after the NTT pass"))
         for k in range(3):
             ms_k, by = prof["comm_ms"][k], prof["comm_bytes"][k]
-            rate = "" if fused else "  -> %6.1f GB/s per rank" % (by / 1e6 / max(ms_k, 1e-9))
+            rate = "" if (fused and k == 1) else "  -> %6.1f GB/s per rank" % (by / 1e6 / max(ms_k, 1e-9))
             print("  %-34s %8.3f ms  %9.1f MB received per rank%s" % (names[k], ms_k, by / 1e6, rate))
     sp.close()
     td.barrier(device_ids=[local])
