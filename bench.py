@@ -80,21 +80,33 @@ def dist_setup(n_gpus):
         import torch
         import torch.distributed as td_
         torch.cuda.set_device(local)
-        # NCCL / c10d print a version banner on stdout when the communicator is created; stdout must carry exactly one
-        # JSON line, so fd 1 points at stderr until the first collective has run
+        # NCCL / c10d write their banner and (with NCCL_DEBUG=INFO, which the driver may set to count ranks) their log lines to
+        # stdout — at communicator creation and lazily later (channel setup, the sharded prover's own communicator).  stdout
+        # must carry exactly one JSON line, so fd 1 points at stderr for the whole run and is restored just before that line
+        # is printed (emit_json).
         sys.stdout.flush()
-        saved = os.dup(1)
+        global _SAVED_STDOUT
+        _SAVED_STDOUT = os.dup(1)
         os.dup2(2, 1)
-        try:
-            td_.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
-            td_.barrier(device_ids=[local])
-            torch.cuda.synchronize(local)
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
+        td_.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+        td_.barrier(device_ids=[local])
+        torch.cuda.synchronize(local)
         td = td_
     return world, rank, local, td
+
+
+_SAVED_STDOUT = None
+
+
+def emit_json(obj):
+    """The one JSON line of the run, on the real stdout."""
+    global _SAVED_STDOUT
+    sys.stdout.flush()
+    if _SAVED_STDOUT is not None:
+        os.dup2(_SAVED_STDOUT, 1)
+        os.close(_SAVED_STDOUT)
+        _SAVED_STDOUT = None
+    print(json.dumps(obj), flush=True)
 
 
 def max_over_ranks(td, local, x):
@@ -418,8 +430,9 @@ def bench_ours(args):
     else:
         out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": effective_cores(), "kind": "port",
                                "sample": "not run (rank 0 at N = 1 only, and not with --no-cpu)"}
-    print(json.dumps(out), flush=True)
+    emit_json(out)
     if td is not None:
+        os.dup2(2, 1)  # late NCCL teardown chatter must not follow the JSON line
         td.destroy_process_group()
     return 0
 

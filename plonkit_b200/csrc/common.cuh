@@ -133,12 +133,17 @@ void profile_resolve(pk_ctx* ctx);  // capi.cu
 struct SideStreamScope {
     pk_ctx* ctx;
     cudaStream_t main;
-    explicit SideStreamScope(pk_ctx* c) : ctx(c), main(c->stream) {
+    bool active;
+    // while per-kernel profiling is on everything stays on the main stream: event pairs around a kernel family must not
+    // include the time it spends waiting for SMs the other stream holds
+    explicit SideStreamScope(pk_ctx* c) : ctx(c), main(c->stream), active(!c->prof.enabled) {
+        if (!active) return;
         cudaEventRecord(ctx->ev_fork, main);
         cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0);
         ctx->stream = ctx->side;
     }
     ~SideStreamScope() {
+        if (!active) return;
         cudaEventRecord(ctx->ev_join, ctx->side);
         ctx->stream = main;
         ctx->side_pending = true;

@@ -46,9 +46,9 @@ __global__ void ec_load_bitrev_kernel(const g1_affine_t* bases, g1_xyzz_t* a, in
     size_t r = log_n ? (size_t)(__brev((unsigned)i) >> (32 - log_n)) : 0;
     st_xyzz(a + r, g1_xyzz_t::from_affine(ldg_affine(bases + i)));
 }
-// decimation-in-time stage s with inverse twiddles w^{-e} = -w^{n/2-e}.  MINB = resident blocks per SM the register
-// allocation is bounded for (PK_EC_MINB, default 4: 128 registers; the unbounded kernel takes 168 and runs 3 blocks).
-template <int MINB> __global__ void __launch_bounds__(128, MINB) ec_stage_kernel(g1_xyzz_t* a, const fr_t* tw, int tw_shift, int log_n, int s) {
+// decimation-in-time stage s with inverse twiddles w^{-e} = -w^{n/2-e}.  Bounded to 128 registers (4 resident blocks per
+// SM); 96 and 168 registers were measured within 4 % of it (2^20: 513 / 507 / 526 ms).
+__global__ void __launch_bounds__(128, 4) ec_stage_kernel(g1_xyzz_t* a, const fr_t* tw, int tw_shift, int log_n, int s) {
     size_t u = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const size_t half_n = size_t(1) << (log_n - 1);
     if (u >= half_n) return;
@@ -168,12 +168,8 @@ void ec_intt(pk_ctx* ctx, uint32_t log_n, uint64_t* out_xy) {
     if (log_n) {
         ensure_twiddles(ctx, (int)log_n);
         DomainCache* dc = ctx->domains;
-        static const int minb = [] { const char* e = getenv("PK_EC_MINB"); return e ? atoi(e) : 4; }();
         for (int s = 0; s < (int)log_n; ++s) {
-            const int ts = dc->tw_log - (int)log_n;
-            if (minb <= 3) ec_stage_kernel<3><<<grid1d(n / 2, 128), 128, 0, st>>>(a.p, dc->tw.p, ts, (int)log_n, s);
-            else if (minb == 4) ec_stage_kernel<4><<<grid1d(n / 2, 128), 128, 0, st>>>(a.p, dc->tw.p, ts, (int)log_n, s);
-            else ec_stage_kernel<5><<<grid1d(n / 2, 128), 128, 0, st>>>(a.p, dc->tw.p, ts, (int)log_n, s);
+            ec_stage_kernel<<<grid1d(n / 2, 128), 128, 0, st>>>(a.p, dc->tw.p, dc->tw_log - (int)log_n, (int)log_n, s);
             ctx->prof.kernel_launches++;
         }
     }
