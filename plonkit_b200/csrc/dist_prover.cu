@@ -316,8 +316,12 @@ void dist_prove(pk_ctx* ctx, pk_dist_setup* s, const uint64_t* var_values, uint6
     const int log_n = s->log_n, G = s->G;
     const uint32_t ni = s->num_inputs;
     cudaStream_t st = ctx->stream;
-    cudaEvent_t ev[8];
-    for (auto& e : ev) PK_CUDA(cudaEventCreate(&e));
+    struct PhaseEvents {  // destroyed on every exit path
+        cudaEvent_t e[8];
+        PhaseEvents() { for (auto& x : e) cudaEventCreate(&x); }
+        ~PhaseEvents() { for (auto& x : e) cudaEventDestroy(x); }
+    } phase_events;
+    cudaEvent_t* ev = phase_events.e;
     int evk = 0;
     auto mark = [&] { cudaEventRecord(ev[evk++], st); };
     mark();
@@ -576,7 +580,6 @@ void dist_prove(pk_ctx* ctx, pk_dist_setup* s, const uint64_t* var_values, uint6
         cudaEventElapsedTime(&tot, ev[0], ev[evk - 1]);
         ctx->prof.phase_ms[7] = tot;
     }
-    for (auto& e : ev) cudaEventDestroy(e);
 
     memset(proof, 0, sizeof(*proof));
     proof->n = n - 1;
