@@ -77,6 +77,9 @@ int pk_poly_divide_by_linear(pk_ctx* ctx, const uint64_t* coeffs, uint64_t n, co
 int pk_poly_shifted_grand_product(pk_ctx* ctx, const uint64_t* values, uint64_t n, uint64_t* out);
 /* Polynomial<Fr, Values>::batch_inversion: values[i] <- values[i]^-1 in place, zeros stay zero. */
 int pk_poly_batch_inversion(pk_ctx* ctx, uint64_t* values, uint64_t n);
+/* Pointwise operations of bellman's Polynomial (row a13): op 0 add_assign_scaled (out = a + s b), 1 mul_assign (a .* b),
+ * 2 scale (s a), 3 add_constant (a + s), 4 distribute_powers (out[i] = a[i] s^i).  b / scalar may be NULL where unused. */
+int pk_poly_pointwise(pk_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, const uint64_t scalar[4], uint64_t n, uint64_t* out);
 /* multiexp::dense_multiexp / commit_using_monomials: sum_i scalars[i] * SRS[base_offset + i], normalised to affine. */
 int pk_msm_g1(pk_ctx* ctx, const uint64_t* scalars, uint64_t n, uint64_t base_offset, uint64_t out_xy[8], int* is_infinity,
               int fmt);

@@ -30,7 +30,7 @@ EXPORTS = [
     "pk_prove", "pk_profile_enable", "pk_profile_reset", "pk_profile_get", "pk_bench_ntt", "pk_bench_msm",
     "pk_bench_fieldmul", "pk_bench_msm_pattern", "pk_timer_begin", "pk_timer_end", "pk_g1_sum", "pk_dev_fr_convert", "pk_dev_ntt_rows",
     "pk_dev_twiddle", "pk_poly_evaluate_at", "pk_poly_divide_by_linear", "pk_poly_shifted_grand_product",
-    "pk_poly_batch_inversion", "pk_dev_ec_from_affine", "pk_dev_ec_ntt_rows", "pk_dev_ec_twiddle", "pk_dev_ec_to_affine",
+    "pk_poly_batch_inversion", "pk_poly_pointwise", "pk_dev_ec_from_affine", "pk_dev_ec_ntt_rows", "pk_dev_ec_twiddle", "pk_dev_ec_to_affine",
     "pk_comm_group_create", "pk_comm_group_destroy", "pk_comm_attach_group", "pk_comm_nccl_unique_id", "pk_comm_attach_nccl",
     "pk_dist_setup_create", "pk_dist_setup_destroy", "pk_dist_setup_commitments", "pk_dist_witness_upload", "pk_dist_prove",
 ]
@@ -145,6 +145,7 @@ def load():
     lib.pk_poly_divide_by_linear.argtypes = [vp, vp, u64, vp, vp]
     lib.pk_poly_shifted_grand_product.argtypes = [vp, vp, u64, vp]
     lib.pk_poly_batch_inversion.argtypes = [vp, vp, u64]
+    lib.pk_poly_pointwise.argtypes = [vp, i32, vp, vp, vp, u64, vp]
     lib.pk_comm_group_create.argtypes = [i32, ctypes.POINTER(vp)]
     lib.pk_comm_group_destroy.argtypes = [vp]
     lib.pk_comm_group_destroy.restype = None
@@ -279,6 +280,19 @@ class Context:
         v = np.ascontiguousarray(values, dtype=np.uint64).reshape(-1, 4).copy()
         self._check(self._lib.pk_poly_batch_inversion(self._h, _ptr(v) if v.shape[0] else None, v.shape[0]))
         return v
+
+    POINTWISE_OPS = {"add_assign_scaled": 0, "mul_assign": 1, "scale": 2, "add_constant": 3, "distribute_powers": 4}
+
+    def poly_pointwise(self, op, a, b=None, scalar=None):
+        """bellman's pointwise Polynomial operations (see pk_poly_pointwise); canonical limbs in and out"""
+        a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+        b = None if b is None else np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 4)
+        sc = None if scalar is None else np.ascontiguousarray(scalar, dtype=np.uint64).reshape(4)
+        out = np.zeros_like(a)
+        n = a.shape[0]
+        self._check(self._lib.pk_poly_pointwise(self._h, self.POINTWISE_OPS[op], _ptr(a) if n else None, _ptr(b) if (b is not None and n) else None,
+                                                _ptr(sc), n, _ptr(out) if n else None))
+        return out
 
     def msm_g1(self, scalars, base_offset=0, fmt=FMT_CANONICAL):
         s = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)

@@ -264,6 +264,44 @@ int pk_poly_batch_inversion(pk_ctx* ctx, uint64_t* values, uint64_t n) {
     PK_API_END(ctx)
 }
 
+// Polynomial<Fr, _>::{add_assign_scaled, mul_assign, scale, add_constant, distribute_powers}
+int pk_poly_pointwise(pk_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, const uint64_t scalar[4], uint64_t n, uint64_t* out) {
+    PK_API_BEGIN(ctx)
+    PK_REQUIRE(op >= 0 && op <= 4, PK_ERR_INVALID, "unknown pointwise operation");
+    PK_REQUIRE(n == 0 || (a != nullptr && out != nullptr), PK_ERR_INVALID, "null argument");
+    PK_REQUIRE(op > 1 || n == 0 || b != nullptr, PK_ERR_ASSIGNMENT_MISSING, "second operand missing");
+    PK_REQUIRE(op == 1 || scalar != nullptr, PK_ERR_INVALID, "scalar missing");
+    if (n == 0) return PK_OK;
+    DevBuf<fr_t> da, db, dc(n);
+    upload_fr(ctx, da, a, n);
+    const fr_t s = op == 1 ? fr_t::one() : host_load_canonical<fr_t>(scalar);
+    if (op == 0) {            // a + s * b
+        upload_fr(ctx, db, b, n);
+        const fr_t* in[2] = {da.p, db.p};
+        fr_t coef[2] = {fr_t::one(), s};
+        poly_lincomb(ctx, dc.p, 2, in, coef, n);
+    } else if (op == 1) {     // a * b
+        upload_fr(ctx, db, b, n);
+        fr_mul_pointwise(ctx, da.p, db.p, dc.p, n);
+    } else if (op == 2) {     // s * a
+        const fr_t* in[1] = {da.p};
+        fr_t coef[1] = {s};
+        poly_lincomb(ctx, dc.p, 1, in, coef, n);
+    } else if (op == 3) {     // a + s
+        db.alloc(n);
+        fr_fill(ctx, db.p, s, n);
+        const fr_t* in[2] = {da.p, db.p};
+        fr_t coef[2] = {fr_t::one(), fr_t::one()};
+        poly_lincomb(ctx, dc.p, 2, in, coef, n);
+    } else {                  // a_i * s^i
+        db.alloc(n);
+        poly_powers(ctx, db.p, s, n);
+        fr_mul_pointwise(ctx, da.p, db.p, dc.p, n);
+    }
+    download_fr(ctx, dc.p, out, n);
+    PK_API_END(ctx)
+}
+
 int pk_lde4(pk_ctx* ctx, const uint64_t* coeffs, uint32_t log_n, uint64_t* out_4n, int bitreversed, int fmt) {
     PK_API_BEGIN(ctx)
     PK_REQUIRE(coeffs != nullptr && out_4n != nullptr, PK_ERR_INVALID, "null data");

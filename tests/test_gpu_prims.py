@@ -275,6 +275,35 @@ def test_polynomial_primitives_match_oracle(ctx, orc, n):
         assert all(a * b % R_MOD == 1 for a, b in zip(limbs_to_ints(nz), limbs_to_ints(inv)))
 
 
+@pytest.mark.parametrize("n", [1, 7, 4096, 100003])
+def test_pointwise_polynomial_operations_match_python_integers(ctx, n):
+    """pk_poly_pointwise (bellman Polynomial::add_assign_scaled / mul_assign / scale / add_constant / distribute_powers, SURVEY
+    8 row a13) against Python integers; the same kernels (lincomb, pointwise product, power table) carry the prover's
+    linearisation and opening aggregation."""
+    a = synth.random_field_elements(n, seed=700 + n % 100)
+    b = synth.random_field_elements(n, seed=800 + n % 100)
+    a[n // 2] = 0
+    s = synth.random_field_elements(1, seed=9)[0]
+    ai, bi, si = limbs_to_ints(a), limbs_to_ints(b), limbs_to_ints(s.reshape(1, 4))[0]
+    want = {
+        "add_assign_scaled": [(x + si * y) % R_MOD for x, y in zip(ai, bi)],
+        "mul_assign": [x * y % R_MOD for x, y in zip(ai, bi)],
+        "scale": [si * x % R_MOD for x in ai],
+        "add_constant": [(x + si) % R_MOD for x in ai],
+    }
+    p, dp = 1, []
+    for x in ai:
+        dp.append(x * p % R_MOD)
+        p = p * si % R_MOD
+    want["distribute_powers"] = dp
+    for op, ref in want.items():
+        got = ctx.poly_pointwise(op, a, b if op in ("add_assign_scaled", "mul_assign") else None, None if op == "mul_assign" else s)
+        assert limbs_to_ints(got) == ref, op
+    assert ctx.poly_pointwise("scale", np.zeros((0, 4), dtype=np.uint64), None, s).shape == (0, 4)
+    with pytest.raises(_lib.SynthesisError):
+        ctx.poly_pointwise("add_assign_scaled", a, None, s)          # second operand missing
+
+
 def test_polynomial_primitives_empty_input(ctx):
     e = np.zeros((0, 4), dtype=np.uint64)
     z = ints_to_limbs([3])[0]
