@@ -8,9 +8,9 @@ subcommand names, flags, defaults and overwrite guards:
     prove                    -m  [-l]  -c  -w witness.wtns  -p proof.bin  -j proof.json  -i public.json
                              -t keccak  --overwrite                                          (main.rs:384-424)
     export-verification-key  -m  -c  -v vk.bin  --overwrite                                 (main.rs:484-504)
+    verify                   -p proof.bin  -v vk.bin  -t keccak   (host arithmetic, exit code 400) (main.rs:427-438)
 
-Out of scope: verify / generate-verifier (pairing, Solidity code generation) and the recursive-*
-subcommands.  `proof.json` / `public.json` follow contrib/template.sol:864-951 (33 words); their exact text encoding is
+Out of scope: generate-verifier (Solidity code generation) and the recursive-* subcommands.  `proof.json` / `public.json` follow contrib/template.sol:864-951 (33 words); their exact text encoding is
 not pinned by any in-tree fixture.
 """
 import argparse
@@ -132,6 +132,16 @@ def cmd_export_vk(o):
     print("Verification key saved to %s" % o.vk, file=sys.stderr)
 
 
+def cmd_verify(o):  # main.rs:427-438
+    vk = reader.load_verification_key(o.vk)
+    proof = reader.load_proof(o.proof)
+    if plonk.verify(vk, proof, o.transcript):
+        print("Proof is valid.", file=sys.stderr)
+    else:
+        print("Proof is invalid!", file=sys.stderr)
+        raise SystemExit(400)
+
+
 def build_parser():
     ap = argparse.ArgumentParser(prog="plonkit", description="prove-path subset of the plonkit CLI on the CUDA library")
     sub = ap.add_subparsers(dest="command", required=True)
@@ -167,12 +177,17 @@ def build_parser():
     p.add_argument("-v", "--vk", default="vk.bin")
     p.add_argument("--overwrite", action="store_true")
     p.set_defaults(fn=cmd_export_vk)
+    p = sub.add_parser("verify")
+    p.add_argument("-p", "--proof", default="proof.bin")
+    p.add_argument("-v", "--vk", default="vk.bin")
+    p.add_argument("-t", "--transcript", default="keccak")
+    p.set_defaults(fn=cmd_verify)
     for name in ("analyse", "dump-lagrange", "prove", "export-verification-key"):
         # not a flag of the reference CLI: R1CS shapes whose gate layout no reference fixture pins (linear combinations
         # with more than two terms) are refused unless this is given; the proofs then verify but byte parity with the
         # reference is unpinned (circuit._transpile)
         sub.choices[name].add_argument("--allow-unpinned-transpilation", action="store_true")
-    for name in ("verify", "generate-verifier", "generate-recursive-verifier", "export-recursive-verification-key",
+    for name in ("generate-verifier", "generate-recursive-verifier", "export-recursive-verification-key",
                  "recursive-prove", "recursive-verify", "check-aggregation"):
         q = sub.add_parser(name)
         q.add_argument("rest", nargs=argparse.REMAINDER)

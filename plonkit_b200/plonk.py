@@ -374,7 +374,11 @@ def _proof_from_struct(pr, inputs) -> Proof:
 
 
 def verify(vk: VerificationKey, proof: Proof, transcript: str = "keccak") -> bool:
-    """src/plonk.rs:189-210.  Verification needs the BN254 pairing (G2 / Fq12), which is outside this repo's scope
-    ("G2/pairing OUT OF SCOPE: verify only")."""
-    raise NotImplementedError("pairing-based verification is out of scope; tests/ verify proofs algebraically "
-                              "with the known SRS trapdoor instead")
+    """src/plonk.rs:189-210: bellman's better_cs verifier with the Keccak transcript — host arithmetic with the BN254 pairing
+    (plonkit_b200/verifier.py), as in the reference; the `rescue` transcript's parameters are not in the reference tree."""
+    if transcript == "rescue":
+        raise NotImplementedError("the rescue transcript has no in-tree fixture (SURVEY.md section 0 item 5); use 'keccak'")
+    if transcript != "keccak":
+        raise NotImplementedError("invalid transcript. use 'keccak' or 'rescue'")
+    from . import verifier
+    return verifier.verify(vk, proof)

@@ -92,15 +92,18 @@ def test_poseidon_shaped_golden_fixture(ctx, simple_key):
 def test_proofs_equal_oracle_on_synthetic_circuits(ctx, orc, kind, log_n):
     asm = synth.poseidon_chain_assembly(log_n) if kind == "poseidon" else synth.random_gate_assembly(log_n, seed=log_n)
     srs = orc.srs_gen(asm.n, 42, threads=8)
-    from plonkit_b200.reader import Crs
-    key = Crs(srs, b"", "monomial")
+    from plonkit_b200.reader import CRS_42_G2, Crs
+    key = Crs(srs, CRS_42_G2, "monomial")
     setup = plonk.SetupForProver.prepare_setup_for_prover(asm, key, None, ctx=ctx)
     proof = setup.prove(asm)
     ref = orc.prove(asm.n, asm.num_inputs, asm.wire_idx, asm.var_values, asm.selectors, srs, threads=8)
     assert proof.to_bytes() == ref
     com = orc.setup_commitments(asm.n, asm.num_inputs, asm.wire_idx, asm.selectors, srs, nvars=asm.nvars, threads=8)
-    assert (vk_commitments(setup.make_verification_key()) == com).all()
+    vk = setup.make_verification_key()
+    assert (vk_commitments(vk) == com).all()
     assert orc.verify_trapdoor(proof.to_bytes(), com, 42)
+    if log_n <= 12:
+        assert plonk.verify(vk, proof, "keccak")   # the pairing-based verifier of the API (src/plonk.rs:189-210), no trapdoor
 
 
 def test_prover_pool_keeps_order_and_bytes(orc, simple_key):

@@ -403,3 +403,45 @@ def test_cli_analyse_and_flag_surface(tmp_path):
     with pytest.raises(SystemExit, match="duplicate srs_monomial_form file"):
         cli._guard(str(existing), "srs_monomial_form", False)
     cli._guard(str(existing), "srs_monomial_form", True)
+
+
+def test_verify_accepts_the_reference_proof_with_the_real_pairing(tmp_path):
+    """src/tests.rs:75-81 (test_verify): plonk::verify(vk.bin, proof.bin, "keccak") == true — host arithmetic with the BN254
+    optimal-ate pairing and the two G2 elements of vk.bin, no trapdoor.  Tampered proofs / keys are rejected; the CLI mirrors
+    `plonkit verify` (exit code 400 on an invalid proof, src/bin/main.rs:427-438)."""
+    from plonkit_b200 import __main__ as cli
+    from plonkit_b200 import verifier
+    vk = reader.load_verification_key(os.path.join(SIMPLE, "vk.bin"))
+    proof = reader.load_proof(os.path.join(SIMPLE, "proof.bin"))
+    assert plonk.verify(vk, proof, "keccak") is True
+    # pairing sanity on its own: e(42 G, [1]G2) e(-G, [42]G2) == 1, and not with 43
+    g2 = [verifier.g2_from_bytes(vk.g2_raw[:128]), verifier.g2_from_bytes(vk.g2_raw[128:])]
+    assert verifier.pairing_product_is_one([(verifier.g1_mul((1, 2), 42), g2[0]), (verifier.g1_neg((1, 2)), g2[1])])
+    assert not verifier.pairing_product_is_one([(verifier.g1_mul((1, 2), 43), g2[0]), (verifier.g1_neg((1, 2)), g2[1])])
+    bad = reader.load_proof(os.path.join(SIMPLE, "proof.bin"))
+    bad.quotient_polynomial_at_z = (bad.quotient_polynomial_at_z + 1) % R_MOD
+    assert plonk.verify(vk, bad) is False                      # fails the identity at z
+    bad2 = reader.load_proof(os.path.join(SIMPLE, "proof.bin"))
+    bad2.opening_at_z_proof = bad2.opening_at_z_omega_proof.copy()
+    assert plonk.verify(vk, bad2) is False                     # fails the pairing check only
+    vk2 = reader.load_verification_key(os.path.join(SIMPLE, "vk.bin"))
+    vk2.g2_raw = vk2.g2_raw[:128] + vk2.g2_raw[:128]           # wrong [x]G2
+    assert plonk.verify(vk2, proof) is False
+    with pytest.raises(NotImplementedError):
+        plonk.verify(vk, proof, "rescue")
+    cli.main(["verify", "-p", os.path.join(SIMPLE, "proof.bin"), "-v", os.path.join(SIMPLE, "vk.bin")])
+    pb = tmp_path / "bad.bin"
+    pb.write_bytes(bad.to_bytes())
+    with pytest.raises(SystemExit) as e:
+        cli.main(["verify", "-p", str(pb), "-v", os.path.join(SIMPLE, "vk.bin")])
+    assert e.value.code == 400
+
+
+def test_verify_accepts_a_device_made_proof_fixture():
+    """tests/golden/poseidon9_proof.bin (made by the CUDA prover, == the oracle's bytes) with a verification key assembled from
+    the committed commitments and the constant G2 part of Crs::crs_42: accepted by the pairing-based verifier."""
+    from conftest import GOLDEN
+    com = np.load(os.path.join(GOLDEN, "poseidon9_vk_commitments.npy"))
+    proof = reader.load_proof(os.path.join(GOLDEN, "poseidon9_proof.bin"))
+    vk = reader.VerificationKey(proof.n, proof.num_inputs, com[:6], com[6:7], com[7:11], [5, 7, 10], reader.CRS_42_G2)
+    assert plonk.verify(vk, proof) is True
