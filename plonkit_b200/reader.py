@@ -155,7 +155,7 @@ class Proof:
         return b.getvalue()
 
     @staticmethod
-    def read(f) -> "Proof":
+    def read(f, gated: bool = False) -> "Proof":
         def u64():
             return struct.unpack(">Q", f.read(8))[0]
 
@@ -178,8 +178,12 @@ class Proof:
         gpz, tz, rz = frs(3)
         assert u64() == 3
         pz = frs(3)
+        gsel = None
+        if gated:
+            assert u64() == 2
+            gsel = frs(2)
         o1, o2 = g1s(1)[0], g1s(1)[0]
-        return Proof(n, ni, inputs, wc, gp, qc, wz, wzo, gpz, tz, rz, pz, o1, o2)
+        return Proof(n, ni, inputs, wc, gp, qc, wz, wzo, gpz, tz, rz, pz, o1, o2, gsel)
 
 
 def load_proof(filename: str) -> Proof:  # src/reader.rs:23-25

@@ -30,8 +30,8 @@ class RecursiveVerificationKey:
     s_resc, 4 permutation polynomials (export_vk, src/recursive/mod.rs:196-204, exports bellman's VerificationKey of the
     recursive circuit; its serialisation is unpinned)."""
 
-    def __init__(self, n, num_inputs, commitments):
-        self.n, self.num_inputs, self.commitments = n, num_inputs, commitments
+    def __init__(self, n, num_inputs, commitments, g2_raw=b""):
+        self.n, self.num_inputs, self.commitments, self.g2_raw = n, num_inputs, commitments, g2_raw
 
 
 class RecursiveSetupForProver:
@@ -53,6 +53,7 @@ class RecursiveSetupForProver:
         self._h = h
         self._tag = (big_crs.token, assembly.n)
         self._bases = big_crs.g1_bases[:assembly.n]
+        self._g2_raw = big_crs.g2_raw
         self.ctx._children.add(self)
 
     def close(self):
@@ -75,7 +76,7 @@ class RecursiveSetupForProver:
         self._ensure_srs()
         out = np.zeros((13, 8), dtype=np.uint64)
         self.ctx._check(self.ctx._lib.pk_setup_commitments_gated(self.ctx._h, self._h, out.ctypes.data))
-        return RecursiveVerificationKey(self.n - 1, self.num_inputs, out)
+        return RecursiveVerificationKey(self.n - 1, self.num_inputs, out, self._g2_raw)
 
     def create_proof(self, var_values) -> Proof:
         """better_better_cs create_proof::<_, RollingKeccakTranscript> (src/recursive/mod.rs:127) on the witness."""
@@ -96,3 +97,13 @@ def prove(big_crs, old_proofs, old_vk):
     assembly to `RecursiveSetupForProver(...).create_proof(witness)` instead."""
     raise NotImplementedError("aggregation-circuit synthesis is host Rust outside this repository's scope; the proving call "
                               "behind it is recursive.RecursiveSetupForProver.create_proof")
+
+
+def verify(vk: RecursiveVerificationKey, proof: Proof) -> bool:
+    """The proof check of src/recursive/mod.rs:139-166 (better_better_cs verifier, RollingKeccakTranscript) for proofs of
+    `RecursiveSetupForProver.create_proof`: host arithmetic with the BN254 pairing.  (The aggregation bookkeeping of that
+    function - vks_tree root, the 4 aggregated limbs - belongs to the circuit synthesis and is out of scope.)"""
+    from . import verifier
+    if proof.n != vk.n or proof.num_inputs != vk.num_inputs:
+        return False
+    return verifier.verify_gated(vk.commitments, vk.g2_raw, proof)

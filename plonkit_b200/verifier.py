@@ -423,3 +423,118 @@ def verify(vk, proof) -> bool:
     pair_with_generator = g1_add(g1_add(agg, g1_mul(w1, zeta)), g1_mul(w2, zeta * omega % r_ * u % r_))
     pair_with_x = g1_neg(g1_add(w1, g1_mul(w2, u)))
     return pairing_product_is_one([(pair_with_generator, g2[0]), (pair_with_x, g2[1])])
+
+
+def verify_gated(commitments, g2_raw, proof) -> bool:
+    """Verifier of the two-gate-type prover (plonkit_b200.recursive; protocol of DESIGN.md section 9, byte layout unpinned).
+    `commitments` (13, 8): q_a, q_b, q_c, q_d, q_m, q_const, q_dnext, s_main, s_resc, sigma_0..3.  Gate terms: the main gate
+    enters the linearisation scaled by s_main(z); the Rescue x^5 gate (a^2 = b, b^2 = c, c a = d) enters the identity at z as
+    s_resc(z) (alpha (a^2 - b) + alpha^2 (b^2 - c) + alpha^3 (c a - d)); the permutation argument uses alpha^4 and L_0 alpha^5."""
+    n = proof.n + 1
+    if n & (n - 1) or proof.gate_selectors_at_z is None or len(proof.input_values) != proof.num_inputs:
+        return False
+    log_n = n.bit_length() - 1
+    vk = [_pt(c) for c in commitments]
+    cw = [_pt(c) for c in proof.wire_commitments]
+    cz = _pt(proof.grand_product_commitment)
+    ct = [_pt(c) for c in proof.quotient_poly_commitments]
+    w1, w2 = _pt(proof.opening_at_z_proof), _pt(proof.opening_at_z_omega_proof)
+    if len(vk) != 13 or not all(g1_on_curve(p) for p in vk + cw + [cz] + ct + [w1, w2]):
+        return False
+    if len(g2_raw) != 256:
+        return False
+    g2 = [g2_from_bytes(g2_raw[:128]), g2_from_bytes(g2_raw[128:256])]
+    if not all(g2_on_curve(q) for q in g2):
+        return False
+    wz, dzw = proof.wire_values_at_z, proof.wire_values_at_z_omega[0]
+    zzw, tz, rz, sz = proof.grand_product_at_z_omega, proof.quotient_polynomial_at_z, proof.linearization_polynomial_at_z, proof.permutation_polynomials_at_z
+    smz, srz = proof.gate_selectors_at_z
+    if any(x >= R_MOD for x in list(proof.input_values) + list(wz) + [dzw, zzw, tz, rz, smz, srz] + list(sz)):
+        return False
+
+    tr = RollingKeccakTranscript()
+    for x in proof.input_values:
+        tr.update_u256(x)
+    for p in cw:
+        tr.update_g1(p)
+    beta, gamma = tr.challenge(), tr.challenge()
+    tr.update_g1(cz)
+    alpha = tr.challenge()
+    for p in ct:
+        tr.update_g1(p)
+    zeta = tr.challenge()
+    for x in list(wz) + [dzw, smz, srz] + list(sz) + [tz, rz, zzw]:
+        tr.update_u256(x)
+    v = tr.challenge()
+    tr.update_g1(w1)
+    tr.update_g1(w2)
+    u = tr.challenge()
+
+    r_ = R_MOD
+    al = [pow(alpha, i, r_) for i in range(6)]
+    omega = root_of_unity(log_n)
+    zeta_n = pow(zeta, n, r_)
+    zh = (zeta_n - 1) % r_
+    if zh == 0:
+        return False
+    n_inv = pow(n, -1, r_)
+
+    def lagrange(i):
+        wi = pow(omega, i, r_)
+        return wi * zh % r_ * n_inv % r_ * pow(zeta - wi, -1, r_) % r_
+    l0 = lagrange(0)
+    k = NON_RESIDUES
+    # the quotient identity at z
+    rhs = rz
+    for i, inp in enumerate(proof.input_values):
+        rhs = (rhs + lagrange(i) * inp) % r_
+    rhs = (rhs + srz * (al[1] * (wz[0] * wz[0] - wz[1]) + al[2] * (wz[1] * wz[1] - wz[2]) + al[3] * (wz[2] * wz[0] - wz[3]))) % r_
+    zpart = zzw * al[4] % r_
+    for i in range(3):
+        zpart = zpart * ((sz[i] * beta + gamma + wz[i]) % r_) % r_
+    zpart = zpart * ((gamma + wz[3]) % r_) % r_
+    rhs = (rhs - zpart - l0 * al[5]) % r_
+    if zh * tz % r_ != rhs:
+        return False
+    # the commitment of the linearisation polynomial
+    main = vk[5]
+    for i in range(4):
+        main = g1_add(main, g1_mul(vk[i], wz[i]))
+    main = g1_add(main, g1_mul(vk[4], wz[0] * wz[1] % r_))
+    main = g1_add(main, g1_mul(vk[6], dzw))
+    r_com = g1_mul(main, smz)
+    gpz = al[4]
+    for i in range(4):
+        gpz = gpz * ((zeta * k[i] * beta + gamma + wz[i]) % r_) % r_
+    gpz = (gpz + l0 * al[5]) % r_
+    lastp = beta * zzw % r_ * al[4] % r_
+    for i in range(3):
+        lastp = lastp * ((beta * sz[i] + gamma + wz[i]) % r_) % r_
+    r_com = g1_add(g1_add(r_com, g1_mul(cz, gpz)), g1_neg(g1_mul(vk[12], lastp)))
+    # the two batched openings, at z (powers of v: t, r, a..d, s_main, s_resc, sigma_0..2) and at z omega (Z, d)
+    vp = [pow(v, i, r_) for i in range(13)]
+    f = ct[0]
+    zp = 1
+    for i in range(1, 4):
+        zp = zp * zeta_n % r_
+        f = g1_add(f, g1_mul(ct[i], zp))
+    f = g1_add(f, g1_mul(r_com, v))
+    for i in range(4):
+        f = g1_add(f, g1_mul(cw[i], vp[2 + i]))
+    f = g1_add(g1_add(f, g1_mul(vk[7], vp[6])), g1_mul(vk[8], vp[7]))
+    for i in range(3):
+        f = g1_add(f, g1_mul(vk[9 + i], vp[8 + i]))
+    e = (tz + v * rz) % r_
+    for i in range(4):
+        e = (e + wz[i] * vp[2 + i]) % r_
+    e = (e + smz * vp[6] + srz * vp[7]) % r_
+    for i in range(3):
+        e = (e + sz[i] * vp[8 + i]) % r_
+    f2 = g1_add(g1_mul(cz, vp[11]), g1_mul(cw[3], vp[12]))
+    e2 = (zzw * vp[11] + dzw * vp[12]) % r_
+    # e(F - E G + z W1 + u (F2 - E2 G + z omega W2), G2) == e(W1 + u W2, [tau] G2)
+    lhs = g1_add(g1_add(f, g1_neg(g1_mul((1, 2), e))), g1_mul(w1, zeta))
+    lhs2 = g1_add(g1_add(f2, g1_neg(g1_mul((1, 2), e2))), g1_mul(w2, zeta * omega % r_))
+    lhs = g1_add(lhs, g1_mul(lhs2, u))
+    pair_with_x = g1_neg(g1_add(w1, g1_mul(w2, u)))
+    return pairing_product_is_one([(lhs, g2[0]), (pair_with_x, g2[1])])

@@ -272,17 +272,20 @@ def test_two_gate_type_prover_matches_its_oracle_and_verifies(ctx, orc, log_n):
     verifier (known trapdoor) must accept it against the exported 13-commitment key, and reject a tampered proof; a witness
     that breaks a custom-gate row is refused like an unsatisfied main-gate row."""
     from plonkit_b200 import recursive
-    from plonkit_b200.reader import Crs
+    from plonkit_b200.reader import CRS_42_G2, Crs
     asm, gate_type = synth.rescue_chain_assembly(log_n)
     assert gate_type.sum() > 0 and asm.n == 1 << log_n
     srs = orc.srs_gen(asm.n, 42, threads=8)
-    setup = recursive.RecursiveSetupForProver(asm, gate_type, Crs(srs), ctx=ctx)
-    proof = setup.create_proof(asm.var_values).to_bytes()
+    setup = recursive.RecursiveSetupForProver(asm, gate_type, Crs(srs, CRS_42_G2), ctx=ctx)
+    proof_obj = setup.create_proof(asm.var_values)
+    proof = proof_obj.to_bytes()
     assert proof == orc.prove2(asm.n, asm.num_inputs, asm.wire_idx, asm.var_values, asm.selectors, gate_type, srs, threads=8)
     vk = setup.export_vk()
     assert (vk.commitments == orc.setup_commitments2(asm.n, asm.num_inputs, asm.wire_idx, asm.selectors, gate_type, srs,
                                                       nvars=asm.nvars, threads=8)).all()
     assert orc.verify_trapdoor2(proof, vk.commitments, 42)
+    if log_n <= 10:
+        assert recursive.verify(vk, proof_obj)          # the pairing check, no trapdoor
     bad = bytearray(proof)
     bad[-150] ^= 1          # inside s_resc(z)
     assert not orc.verify_trapdoor2(bytes(bad), vk.commitments, 42)

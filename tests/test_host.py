@@ -445,3 +445,26 @@ def test_verify_accepts_a_device_made_proof_fixture():
     proof = reader.load_proof(os.path.join(GOLDEN, "poseidon9_proof.bin"))
     vk = reader.VerificationKey(proof.n, proof.num_inputs, com[:6], com[6:7], com[7:11], [5, 7, 10], reader.CRS_42_G2)
     assert plonk.verify(vk, proof) is True
+
+
+def test_two_gate_type_verifier_accepts_the_oracle_proof_with_the_real_pairing(orc):
+    """The pairing-based verifier of the two-gate-type prover (recursive.verify, the proof check of src/recursive/mod.rs:139-166;
+    parity unpinned) accepts the oracle's proof of a 2^6 rescue-shaped circuit against the 13 setup commitments and the G2 part
+    of Crs::crs_42, agrees with the oracle's trapdoor check, and rejects a tampered evaluation and a swapped opening."""
+    from plonkit_b200 import recursive
+    asm, gate_type = synth.rescue_chain_assembly(6)
+    srs = orc.srs_gen(asm.n, 42, threads=2)
+    raw = orc.prove2(asm.n, asm.num_inputs, asm.wire_idx, asm.var_values, asm.selectors, gate_type, srs, threads=2)
+    com = orc.setup_commitments2(asm.n, asm.num_inputs, asm.wire_idx, asm.selectors, gate_type, srs, nvars=asm.nvars, threads=2)
+    proof = reader.Proof.read(io.BytesIO(raw), gated=True)
+    assert proof.to_bytes() == raw
+    vk = recursive.RecursiveVerificationKey(asm.n - 1, asm.num_inputs, com, reader.CRS_42_G2)
+    assert orc.verify_trapdoor2(raw, com, 42)
+    assert recursive.verify(vk, proof) is True
+    bad = reader.Proof.read(io.BytesIO(raw), gated=True)
+    bad.gate_selectors_at_z = [proof.gate_selectors_at_z[0], (proof.gate_selectors_at_z[1] + 1) % R_MOD]
+    assert recursive.verify(vk, bad) is False
+    bad = reader.Proof.read(io.BytesIO(raw), gated=True)
+    bad.opening_at_z_proof = proof.opening_at_z_omega_proof
+    assert recursive.verify(vk, bad) is False
+    assert recursive.verify(recursive.RecursiveVerificationKey(asm.n - 1, asm.num_inputs, com, b""), proof) is False
