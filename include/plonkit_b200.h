@@ -103,7 +103,9 @@ int pk_dev_ntt_rows(pk_ctx* ctx, void* dev, uint32_t log_len, uint64_t rows, int
 int pk_dev_twiddle(pk_ctx* ctx, void* dev, uint64_t rows, uint64_t cols, uint32_t log_total, uint64_t row0, int inverse);
 /* The same local steps over G1 POINTS, for Crs::from_powers (src/plonk.rs:179-185) of a key too large / too slow for one
  * GPU: device arrays of 64-byte affine points (canonical limbs, (0,0) = infinity) and of 128-byte XYZZ accumulators.
- * ntt_rows is UNSCALED (no 1/len); pk_dev_ec_to_affine multiplies by 2^-log_scale while normalising. */
+ * ntt_rows is UNSCALED (no 1/len).  pk_dev_ec_twiddle: inverse = 0 forward twiddles, 1 inverse twiddles, 2 inverse twiddles
+ * times 2^-log_total (the scale of the whole inverse transform, free on a step that multiplies every point anyway);
+ * pk_dev_ec_to_affine multiplies by 2^-log_scale while normalising (log_scale = 0: normalise only). */
 int pk_dev_ec_from_affine(pk_ctx* ctx, const void* dev_affine, void* dev_xyzz, uint64_t n);
 int pk_dev_ec_ntt_rows(pk_ctx* ctx, void* dev_xyzz, uint32_t log_len, uint64_t rows, int inverse);
 int pk_dev_ec_twiddle(pk_ctx* ctx, void* dev_xyzz, uint64_t rows, uint64_t cols, uint32_t log_total, uint64_t row0, int inverse);

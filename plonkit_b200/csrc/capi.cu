@@ -23,7 +23,7 @@ void setup_use_lagrange(pk_ctx* ctx, pk_setup* s, bool on);
 void ec_intt(pk_ctx* ctx, uint32_t log_n, uint64_t* out_xy);
 void ec_dev_from_affine(pk_ctx* ctx, const g1_affine_t* in_canonical, g1_xyzz_t* out, size_t n);
 void ec_dev_ntt_rows(pk_ctx* ctx, g1_xyzz_t* data, int log_len, size_t rows, bool inverse);
-void ec_dev_twiddle_rows(pk_ctx* ctx, g1_xyzz_t* a, size_t rows, size_t cols, int log_total, size_t row0, bool inverse);
+void ec_dev_twiddle_rows(pk_ctx* ctx, g1_xyzz_t* a, size_t rows, size_t cols, int log_total, size_t row0, int mode);
 void ec_dev_to_affine(pk_ctx* ctx, const g1_xyzz_t* in, g1_affine_t* out_canonical, size_t n, int log_scale);
 void srs_gen(pk_ctx* ctx, uint64_t n, uint64_t tau, uint64_t* out_xy);
 void dist_setup_create(pk_ctx* ctx, const pk_assembly* as, pk_dist_setup** out);
@@ -404,7 +404,7 @@ int pk_dev_ec_twiddle(pk_ctx* ctx, void* dev_xyzz, uint64_t rows, uint64_t cols,
     PK_API_BEGIN(ctx)
     PK_REQUIRE(dev_xyzz != nullptr && rows >= 1 && cols >= 1, PK_ERR_INVALID, "bad argument");
     PK_REQUIRE(log_total <= 28, PK_ERR_DEGREE_TOO_LARGE, "domain larger than 2^28");
-    ec_dev_twiddle_rows(ctx, static_cast<g1_xyzz_t*>(dev_xyzz), rows, cols, (int)log_total, row0, inverse != 0);
+    ec_dev_twiddle_rows(ctx, static_cast<g1_xyzz_t*>(dev_xyzz), rows, cols, (int)log_total, row0, inverse);
     PK_CUDA(cudaStreamSynchronize(ctx->stream));
     PK_API_END(ctx)
 }

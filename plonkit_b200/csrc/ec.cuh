@@ -162,6 +162,90 @@ struct alignas(16) g1_xyzz_t {
     }
 };
 
+// Plain Jacobian coordinates (x = X/Z^2, y = Y/Z^3; infinity: Z = 0) for the window loop of the scalar multiplication
+// (ecmul.cuh): with a = 0 a doubling is 7 field products against the 9 of XYZZ, and a window there is two doublings per
+// addition.  g1_jacc_t is a table entry: a Jacobian point with Z^2 and Z^3 kept beside it, so that adding it costs 14.
+// All coordinates of both types are in LAZY form ([0, 2p), fp.cuh): no conditional subtraction after any product; only
+// to_xyzz() normalises.
+struct g1_jacc_t {
+    fq_t X, Y, Z, ZZ, ZZZ;
+    PK_HD bool is_inf() const { return Z.lis_zero(); }
+    PK_HD g1_jacc_t neg() const { g1_jacc_t r = *this; r.Y = fq_t::zero().lsub(Y); return r; }
+};
+struct g1_jac_t {
+    fq_t X, Y, Z;
+
+    static PK_HD g1_jac_t infinity() {
+        g1_jac_t p;
+        p.X = fq_t::zero(); p.Y = fq_t::zero(); p.Z = fq_t::zero();
+        return p;
+    }
+    PK_HD bool is_inf() const { return Z.lis_zero(); }
+    // an XYZZ point (canonical coordinates) as Jacobian with Z := ZZ: Z^2 = ZZ^2 and Z^3 = ZZ^3 = ZZZ^2, so X' = X ZZ, Y' = Y ZZZ
+    static PK_HD g1_jac_t from_xyzz(const g1_xyzz_t& p) {
+        if (p.is_inf()) return infinity();
+        g1_jac_t r;
+        r.X = p.X.lmul(p.ZZ); r.Y = p.Y.lmul(p.ZZZ); r.Z = p.ZZ;
+        return r;
+    }
+    PK_HD g1_xyzz_t to_xyzz() const {
+        if (is_inf()) return g1_xyzz_t::infinity();
+        g1_xyzz_t r;
+        const fq_t zz = Z.lmul(Z);
+        r.X = X.lnormalize(); r.Y = Y.lnormalize(); r.ZZ = zz.lnormalize(); r.ZZZ = zz.lmul(Z).lnormalize();
+        return r;
+    }
+    PK_HD g1_jacc_t cached() const {
+        g1_jacc_t r;
+        r.X = X; r.Y = Y; r.Z = Z; r.ZZ = Z.lmul(Z); r.ZZZ = r.ZZ.lmul(Z);
+        return r;
+    }
+    static PK_HD g1_jac_t from_cached(const g1_jacc_t& c) { g1_jac_t r; r.X = c.X; r.Y = c.Y; r.Z = c.Z; return r; }
+    // a = 0 doubling, 3M + 4S: A = X^2, B2 = 2 Y^2, C2 = B2^2 = 4 Y^4, D = 2 X B2 = 4 X Y^2, E = 3 A;
+    // X3 = E^2 - 2 D, Y3 = E (D - X3) - 2 C2, Z3 = 2 Y Z
+    PK_HD g1_jac_t dbl() const {
+        if (is_inf()) return *this;
+        g1_jac_t r;
+        r.Z = Y.lmul(Z);
+        r.Z = r.Z.ladd(r.Z);
+        fq_t B2 = Y.lmul(Y);
+        B2 = B2.ladd(B2);
+        fq_t D = X.lmul(B2);
+        D = D.ladd(D);
+        fq_t C2 = B2.lmul(B2);
+        C2 = C2.ladd(C2);
+        fq_t E = X.lmul(X);
+        E = E.ladd(E).ladd(E);
+        r.X = E.lmul(E).lsub(D.ladd(D));
+        r.Y = E.lmul(D.lsub(r.X)).lsub(C2);
+        return r;
+    }
+    // add-2007-bl with the second operand's Z^2, Z^3 given: 11M + 3S, all special cases handled
+    PK_HD g1_jac_t add(const g1_jacc_t& b) const {
+        if (b.is_inf()) return *this;
+        if (is_inf()) return from_cached(b);
+        const fq_t Z1Z1 = Z.lmul(Z);
+        const fq_t U1 = X.lmul(b.ZZ);
+        const fq_t U2 = b.X.lmul(Z1Z1);
+        const fq_t S1 = Y.lmul(b.ZZZ);
+        const fq_t S2 = b.Y.lmul(Z.lmul(Z1Z1));
+        const fq_t H = U2.lsub(U1);
+        const fq_t R = S2.lsub(S1);
+        if (H.lis_zero()) {
+            if (R.lis_zero()) return dbl();
+            return infinity();
+        }
+        const fq_t HH = H.lmul(H);
+        const fq_t HHH = H.lmul(HH);
+        const fq_t V = U1.lmul(HH);
+        g1_jac_t r;
+        r.X = R.lmul(R).lsub(HHH).lsub(V.ladd(V));
+        r.Y = R.lmul(V.lsub(r.X)).lsub(S1.lmul(HHH));
+        r.Z = Z.lmul(b.Z).lmul(H);
+        return r;
+    }
+};
+
 #ifdef __CUDACC__
 __device__ __forceinline__ g1_affine_t ldg_affine(const g1_affine_t* p) {
     g1_affine_t a;

@@ -5,6 +5,7 @@
 //                Every butterfly is a 254-bit scalar multiplication plus a point add/sub.
 // Both are setup-time tools, not part of the per-proof path.  First version: one kernel per radix-2 stage over an
 // XYZZ array in global memory; the twiddle multiplication is the GLV double-and-add of ecmul.cuh.
+#include <cstdlib>
 #include "ecmul.cuh"
 #include "msm.cuh"
 #include "ntt.cuh"
@@ -46,27 +47,44 @@ __global__ void ec_load_bitrev_kernel(const g1_affine_t* bases, g1_xyzz_t* a, in
     size_t r = log_n ? (size_t)(__brev((unsigned)i) >> (32 - log_n)) : 0;
     st_xyzz(a + r, g1_xyzz_t::from_affine(ldg_affine(bases + i)));
 }
-// decimation-in-time stage s with inverse twiddles w^{-e} = -w^{n/2-e}.  Bounded to 128 registers (4 resident blocks per
-// SM); 96 and 168 registers were measured within 4 % of it (2^20: 513 / 507 / 526 ms).
-__global__ void __launch_bounds__(128, 4) ec_stage_kernel(g1_xyzz_t* a, const fr_t* tw, int tw_shift, int log_n, int s) {
+// decimation-in-time stage s with inverse twiddles w^{-e} = -w^{n/2-e}.
+//
+// The 1/n of the inverse transform rides on the twiddles instead of costing one more multiplication per point at the end:
+// c F = c F_even + (c w^i) F_odd, so at every stage only the FIRST block (the all-even chain) uses twiddles scaled by
+// c = 1/n, and the single leaf under it (a[0]) is scaled before stage 0: log n + 1 extra multiplications instead of n.
+//
+// Stages with fewer than 32 distinct twiddles run in twiddle-major thread order: a warp then holds ONE twiddle, and the
+// e == 0 warps skip the multiplication instead of idling through their neighbours' (a point is 128 B, so the order of the
+// butterflies within a stage does not change the memory transactions).
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) ec_stage_kernel(g1_xyzz_t* a, const fr_t* tw, int tw_shift, int log_n, int s, fr_t scale) {
     size_t u = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const size_t half_n = size_t(1) << (log_n - 1);
     if (u >= half_n) return;
     const size_t m = size_t(1) << s;
-    const size_t lo = u & (m - 1);
-    const size_t i0 = ((u >> s) << (s + 1)) | lo, i1 = i0 + m;
+    size_t lo, blk;
+    if (s < 5) { lo = u >> (log_n - 1 - s); blk = u & ((size_t(1) << (log_n - 1 - s)) - 1); }
+    else { lo = u & (m - 1); blk = u >> s; }
+    const size_t i0 = (blk << (s + 1)) | lo, i1 = i0 + m;
     const size_t e = lo << (log_n - 1 - s);
     g1_xyzz_t x = ld_xyzz(a + i0), y = ld_xyzz(a + i1);
-    g1_xyzz_t t;
-    if (e == 0) t = y;
-    else t = scalar_mul(y, ldg_fp(tw + ((half_n - e) << tw_shift)).from_mont()).neg();
+    fr_t k = scale;
+    if (e) {
+        k = ldg_fp(tw + ((half_n - e) << tw_shift));
+        if (blk == 0) k = k * scale;
+    }
+    g1_xyzz_t t = (e || blk == 0) ? scalar_mul(y, k.from_mont()) : y;
+    if (e) t = t.neg();
     st_xyzz(a + i0, x.add(t));
     st_xyzz(a + i1, x.add(t.neg()));
 }
-__global__ void __launch_bounds__(128) ec_finish_kernel(const g1_xyzz_t* a, g1_affine_t* out, fr_t ninv_canonical, size_t n) {
+// out[i] = affine(scale * a[i]) (has_scale) or affine(a[i]), canonical limbs
+__global__ void __launch_bounds__(128) ec_finish_kernel(const g1_xyzz_t* a, g1_affine_t* out, fr_t scale_canonical, int has_scale, size_t n) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    g1_affine_t p = scalar_mul(ld_xyzz(a + i), ninv_canonical).to_affine();
+    g1_xyzz_t v = ld_xyzz(a + i);
+    if (has_scale) v = scalar_mul(v, scale_canonical);
+    g1_affine_t p = v.to_affine();
     if (!p.is_inf()) { p.x = p.x.from_mont(); p.y = p.y.from_mont(); }
     st_affine(out + i, p);
 }
@@ -96,26 +114,33 @@ __global__ void __launch_bounds__(128) ec_rows_stage_kernel(g1_xyzz_t* a, const 
     if (u >= half) return;
     a += (size_t)blockIdx.y << log_len;
     const size_t m = size_t(1) << s;
-    const size_t lo = u & (m - 1);
-    const size_t i0 = ((u >> s) << (s + 1)) | lo, i1 = i0 + m;
+    size_t lo, blk;                                  // twiddle-major order in the first stages, as in ec_stage_kernel
+    if (s < 5) { lo = u >> (log_len - 1 - s); blk = u & ((size_t(1) << (log_len - 1 - s)) - 1); }
+    else { lo = u & (m - 1); blk = u >> s; }
+    const size_t i0 = (blk << (s + 1)) | lo, i1 = i0 + m;
     const size_t e = lo << (log_len - 1 - s);
     g1_xyzz_t x = ld_xyzz(a + i0), y = ld_xyzz(a + i1);
-    g1_xyzz_t t;
-    if (e == 0) t = y;
-    else if (inverse) t = scalar_mul(y, ldg_fp(tw + ((half - e) << tw_shift)).from_mont()).neg();
-    else t = scalar_mul(y, ldg_fp(tw + (e << tw_shift)).from_mont());
+    g1_xyzz_t t = y;
+    if (e) {
+        t = scalar_mul(y, ldg_fp(tw + ((inverse ? half - e : e) << tw_shift)).from_mont());
+        if (inverse) t = t.neg();
+    }
     st_xyzz(a + i0, x.add(t));
     st_xyzz(a + i1, x.add(t.neg()));
 }
-// a[r][c] <- w^{+-(row0 + r) * c} * a[r][c]   (w: primitive 2^log_total-th root of unity)
-__global__ void __launch_bounds__(128) ec_twiddle_rows_kernel(g1_xyzz_t* a, size_t rows, size_t cols, fr_t w, size_t row0, int log_total) {
+// a[r][c] <- scale * w^{+-(row0 + r) * c} * a[r][c]   (w: primitive 2^log_total-th root of unity; scale in Montgomery
+// form, has_scale == 0 means 1: the 1/N of a four-step inverse transform costs nothing extra when it rides on this step)
+__global__ void __launch_bounds__(128) ec_twiddle_rows_kernel(g1_xyzz_t* a, size_t rows, size_t cols, fr_t w, size_t row0, int log_total,
+                                                              fr_t scale, int has_scale) {
     size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     size_t r = blockIdx.y;
     if (c >= cols || r >= rows) return;
     const uint64_t mask = (uint64_t(1) << log_total) - 1;
     const uint64_t e = ((uint64_t)(row0 + r) * (uint64_t)c) & mask;
-    if (e == 0) return;
-    st_xyzz(a + r * cols + c, scalar_mul(ld_xyzz(a + r * cols + c), w.pow_u64(e).from_mont()));
+    if (e == 0 && !has_scale) return;
+    fr_t k = w.pow_u64(e);
+    if (has_scale) k = k * scale;
+    st_xyzz(a + r * cols + c, scalar_mul(ld_xyzz(a + r * cols + c), k.from_mont()));
 }
 
 void ec_dev_from_affine(pk_ctx* ctx, const g1_affine_t* in_canonical, g1_xyzz_t* out, size_t n) {
@@ -139,18 +164,22 @@ void ec_dev_ntt_rows(pk_ctx* ctx, g1_xyzz_t* data, int log_len, size_t rows, boo
     PK_CUDA(cudaStreamSynchronize(ctx->stream));
     PK_CUDA(cudaGetLastError());
 }
-void ec_dev_twiddle_rows(pk_ctx* ctx, g1_xyzz_t* a, size_t rows, size_t cols, int log_total, size_t row0, bool inverse) {
+// mode 0: forward twiddles; 1: inverse twiddles; 2: inverse twiddles times 2^-log_total (the scale of the whole transform)
+void ec_dev_twiddle_rows(pk_ctx* ctx, g1_xyzz_t* a, size_t rows, size_t cols, int log_total, size_t row0, int mode) {
     PK_REQUIRE(rows >= 1 && rows <= 65535, PK_ERR_INVALID, "row batch too large");
+    PK_REQUIRE(mode >= 0 && mode <= 2, PK_ERR_INVALID, "twiddle mode must be 0 (forward), 1 (inverse) or 2 (inverse, scaled)");
     fr_t w = host_root_of_unity(log_total);
-    if (inverse) w = w.inverse();
-    ec_twiddle_rows_kernel<<<dim3((unsigned)((cols + 127) / 128), (unsigned)rows), 128, 0, ctx->stream>>>(a, rows, cols, w, row0, log_total);
+    if (mode) w = w.inverse();
+    const fr_t scale = mode == 2 ? fr_t::from_u32(2).inverse().pow_u64(log_total) : fr_t::one();
+    ec_twiddle_rows_kernel<<<dim3((unsigned)((cols + 127) / 128), (unsigned)rows), 128, 0, ctx->stream>>>(a, rows, cols, w, row0, log_total,
+                                                                                                       scale, mode == 2 ? 1 : 0);
     ctx->prof.kernel_launches++;
     PK_CUDA(cudaGetLastError());
 }
 // out[i] = affine(2^-log_scale * in[i]), canonical limbs
 void ec_dev_to_affine(pk_ctx* ctx, const g1_xyzz_t* in, g1_affine_t* out_canonical, size_t n, int log_scale) {
     fr_t scale = fr_t::from_u32(2).inverse().pow_u64(log_scale).from_mont();
-    ec_finish_kernel<<<grid1d(n, 128), 128, 0, ctx->stream>>>(in, out_canonical, scale, n);
+    ec_finish_kernel<<<grid1d(n, 128), 128, 0, ctx->stream>>>(in, out_canonical, scale, log_scale ? 1 : 0, n);
     ctx->prof.kernel_launches++;
     PK_CUDA(cudaGetLastError());
 }
@@ -168,13 +197,20 @@ void ec_intt(pk_ctx* ctx, uint32_t log_n, uint64_t* out_xy) {
     if (log_n) {
         ensure_twiddles(ctx, (int)log_n);
         DomainCache* dc = ctx->domains;
+        const fr_t ninv = fr_t::from_u32(2).inverse().pow_u64(log_n);      // rides on the twiddles of the all-even chain
+        ec_twiddle_rows_kernel<<<1, 128, 0, st>>>(a.p, 1, 1, fr_t::one(), 0, (int)log_n, ninv, 1);   // the leaf a[0] *= 1/n
+        ctx->prof.kernel_launches++;
+        // resident blocks per SM the stage kernel is compiled for: 2 (242 registers, nothing spilled) measured 380 ms at 2^20,
+        // 4 (128 registers, 1.9 KB spilled) 397 ms, 3 (168 registers) 415 ms; PK_EC_MINB selects the others for re-measurement
+        static const int minb = getenv("PK_EC_MINB") ? atoi(getenv("PK_EC_MINB")) : 2;
         for (int s = 0; s < (int)log_n; ++s) {
-            ec_stage_kernel<<<grid1d(n / 2, 128), 128, 0, st>>>(a.p, dc->tw.p, dc->tw_log - (int)log_n, (int)log_n, s);
+            if (minb == 3) ec_stage_kernel<3><<<grid1d(n / 2, 128), 128, 0, st>>>(a.p, dc->tw.p, dc->tw_log - (int)log_n, (int)log_n, s, ninv);
+            else if (minb == 2) ec_stage_kernel<2><<<grid1d(n / 2, 128), 128, 0, st>>>(a.p, dc->tw.p, dc->tw_log - (int)log_n, (int)log_n, s, ninv);
+            else ec_stage_kernel<4><<<grid1d(n / 2, 128), 128, 0, st>>>(a.p, dc->tw.p, dc->tw_log - (int)log_n, (int)log_n, s, ninv);
             ctx->prof.kernel_launches++;
         }
     }
-    fr_t ninv = fr_t::from_u32(2).inverse().pow_u64(log_n).from_mont();
-    ec_finish_kernel<<<grid1d(n, 128), 128, 0, st>>>(a.p, out.p, ninv, n);
+    ec_finish_kernel<<<grid1d(n, 128), 128, 0, st>>>(a.p, out.p, fr_t::one(), 0, n);
     ctx->prof.kernel_launches++;
     PK_CUDA(cudaGetLastError());
     PK_CUDA(cudaMemcpyAsync(out_xy, out.p, n * sizeof(g1_affine_t), cudaMemcpyDeviceToHost, st));

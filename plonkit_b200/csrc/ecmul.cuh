@@ -80,10 +80,44 @@ PK_HD void decompose(const uint32_t* k, uint32_t* k1, bool& neg1, uint32_t* k2, 
 // k * P for a canonical scalar k < r (any XYZZ point P, infinity included).
 // GLV split, then a JOINT FIXED 2-BIT WINDOW over the two ~128-bit halves: the table holds a P1 + b P2 for a, b in 0..3
 // (P1 = +-P, P2 = +-phi(P); 15 points, built with 2 doublings and 11 additions) and every window costs two doublings and
-// ONE addition.  65 windows: 130 doublings + 65 additions + the table = ~2.25 K field products, and — what matters on a
-// SIMT machine — the schedule is the same for every lane: the bit-by-bit version below executes its addition in almost
-// every iteration of a warp (any lane with a set bit pays for all), ~3.0 K products of warp time per multiplication.
+// ONE addition.  The schedule is the same for every lane, which is what matters on a SIMT machine: the bit-by-bit
+// version below executes its addition in almost every iteration of a warp (any lane with a set bit pays for all).
+// The window loop runs in plain Jacobian coordinates in lazy form (ec.cuh): 2 * 7 + 14 = 28 field products per window,
+// none followed by a conditional subtraction, against the 2 * 9 + 14 = 32 of XYZZ (scalar_mul_xyzz below); 65 windows +
+// the table + the conversions = ~2.0 K products.
 PK_HD g1_xyzz_t scalar_mul(const g1_xyzz_t& P, const fr_t& k_canonical) {
+    if (P.is_inf() || k_canonical.is_zero()) return g1_xyzz_t::infinity();
+    uint32_t k1[5], k2[5];
+    bool n1, n2;
+    glv::decompose(k_canonical.v, k1, n1, k2, n2);
+    g1_jacc_t T[16];                     // T[0] is never read: a window with both digits zero adds nothing
+    fq_t beta;
+    for (int i = 0; i < 8; ++i) beta.v[i] = glvc::BETA_MONT(i);
+    const g1_jac_t J = g1_jac_t::from_xyzz(P);
+    T[1] = J.cached();
+    T[4] = T[1];
+    T[4].X = T[1].X.lmul(beta);          // phi(P): x = X / Z^2 is scaled by beta
+    if (n1) T[1] = T[1].neg();
+    if (n2) T[4] = T[4].neg();
+    T[2] = g1_jac_t::from_cached(T[1]).dbl().cached();
+    T[3] = g1_jac_t::from_cached(T[2]).add(T[1]).cached();
+    T[8] = g1_jac_t::from_cached(T[4]).dbl().cached();
+    T[12] = g1_jac_t::from_cached(T[8]).add(T[4]).cached();
+    for (int b = 1; b < 4; ++b)
+        for (int a = 1; a < 4; ++a) T[a + 4 * b] = g1_jac_t::from_cached(T[a]).add(T[4 * b]).cached();
+    g1_jac_t r = g1_jac_t::infinity();
+    for (int w = 64; w >= 0; --w) {
+        r = r.dbl().dbl();
+        const int bit = 2 * w;
+        const uint32_t a = (k1[bit >> 5] >> (bit & 31)) & 3u, b = (k2[bit >> 5] >> (bit & 31)) & 3u;
+        const uint32_t idx = a | (b << 2);
+        if (idx) r = r.add(T[idx]);
+    }
+    return r.to_xyzz();
+}
+
+// the same joint 2-bit window entirely in XYZZ coordinates (the first version; ~2.25 K products): kept as a cross-check
+PK_HD g1_xyzz_t scalar_mul_xyzz(const g1_xyzz_t& P, const fr_t& k_canonical) {
     if (P.is_inf() || k_canonical.is_zero()) return g1_xyzz_t::infinity();
     uint32_t k1[5], k2[5];
     bool n1, n2;

@@ -147,8 +147,8 @@ class DistributedNtt:
 
 class CudaEcNttOps:
     """Local steps of the distributed EC inverse NTT on caller-owned CUDA tensors (pk_dev_ec_*).  Points travel as
-    128-byte XYZZ accumulators ((..., 16) int64 views) between `enter` (affine -> XYZZ) and `leave` (scale by 1/N,
-    normalise to affine)."""
+    128-byte XYZZ accumulators ((..., 16) int64 views) between `enter` (affine -> XYZZ) and `leave` (normalise to affine);
+    the 1/N of the inverse transform rides on the twiddle step, which multiplies every point anyway."""
 
     def __init__(self, ctx, device):
         self.ctx, self.device = ctx, device
@@ -171,13 +171,13 @@ class CudaEcNttOps:
 
     def twiddle(self, t, log_total, row0):
         self._sync()
-        self.ctx.dev_ec_twiddle(t.data_ptr(), t.shape[0], t.shape[1], log_total, row0, True)
+        self.ctx.dev_ec_twiddle(t.data_ptr(), t.shape[0], t.shape[1], log_total, row0, 2)      # inverse twiddles times 1/N
 
     def leave(self, t, log_total):
         import torch
         self._sync()
         out = torch.empty(t.shape[:-1] + (8,), dtype=torch.int64, device=t.device)
-        self.ctx.dev_ec_to_affine(t.data_ptr(), out.data_ptr(), t.numel() // 16, log_total)
+        self.ctx.dev_ec_to_affine(t.data_ptr(), out.data_ptr(), t.numel() // 16, 0)
         return out
 
 
@@ -212,7 +212,7 @@ class DistributedEcIntt:
         pts = self.ops.enter(t.transpose(0, 1).contiguous())               # (C, N1, E): this rank's columns as rows
         e = pts.shape[-1]
         self.ops.ntt_rows(pts)                                             # over n1 -> k1 (inverse, unscaled)
-        self.ops.twiddle(pts, self.log_n, self.rank * c)                   # * w_N^-(n2 * k1)
+        self.ops.twiddle(pts, self.log_n, self.rank * c)                   # * w_N^-(n2 * k1) / N
         send = pts.view(c, w, k, e).permute(1, 0, 2, 3).contiguous()       # (world, C, K): block q goes to rank q
         recv = torch.empty_like(send)
         if w == 1:
@@ -221,7 +221,7 @@ class DistributedEcIntt:
             td.all_to_all_single(recv, send, group=self.group)
         rows = recv.view(n2, k, e).transpose(0, 1).contiguous()            # (K, N2): my k1 rows, all n2
         self.ops.ntt_rows(rows)                                            # over n2 -> k2
-        return self.ops.leave(rows, self.log_n)                            # * 1/N, affine
+        return self.ops.leave(rows, self.log_n)                            # affine
 
     def gather_natural(self, rows):
         """All ranks' outputs reassembled into the natural-order Lagrange key (test helper; O(N) traffic)."""

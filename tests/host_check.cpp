@@ -61,6 +61,18 @@ void hc_g1_ops(const uint64_t* p, const uint64_t* q, uint32_t k, uint64_t* out) 
     g1_xyzz_t L = Xn.add_mixed_lazy(Q).add_mixed_lazy(Q).add_mixed_lazy(P).lnorm();
     store_pt(L.to_affine(), out + 32);
 }
+// Jacobian window-loop arithmetic (ec.cuh g1_jac_t / g1_jacc_t) on accumulators with non-trivial Z:
+// out[0] = p + q, out[1] = 2p, out[2] = (p + q) + q, each through XYZZ -> Jacobian -> XYZZ
+void hc_jac_ops(const uint64_t* p, const uint64_t* q, uint64_t* out) {
+    g1_xyzz_t X = g1_xyzz_t::from_affine(load_pt(p)), Y = g1_xyzz_t::from_affine(load_pt(q));
+    g1_xyzz_t Xn = X.dbl().add(X).add(X.dbl().neg());   // == p with ZZ != 1 (infinity stays infinity)
+    g1_xyzz_t Yn = Y.dbl().add(Y).add(Y.dbl().neg());
+    g1_jac_t J = g1_jac_t::from_xyzz(Xn);
+    g1_jacc_t C = g1_jac_t::from_xyzz(Yn).cached();
+    store_pt(J.add(C).to_xyzz().to_affine(), out);
+    store_pt(J.dbl().to_xyzz().to_affine(), out + 8);
+    store_pt(J.add(C).add(C).to_xyzz().to_affine(), out + 16);
+}
 void hc_lazy_field(const uint32_t* a, const uint32_t* b, uint32_t* o, int n) {
     // o = normalise( lsub( lmul(lmul(a,b), ladd(a,b)), lmul(b,b) ) )  vs the same with canonical ops computed by the caller
     for (int i = 0; i < n; ++i) {
@@ -70,7 +82,7 @@ void hc_lazy_field(const uint32_t* a, const uint32_t* b, uint32_t* o, int n) {
     }
 }
 // GLV: out_k = (|k1| (5 limbs), sign1, |k2| (5 limbs), sign2); out_pt[0] = k * p (GLV, joint 2-bit window), out_pt[1] = k * p
-// (plain 254-bit walk), out_pt[2] = k * p (GLV, bit by bit)
+// (plain 254-bit walk), out_pt[2] = k * p (GLV, bit by bit), out_pt[3] = k * p (GLV, joint window, all in XYZZ)
 void hc_glv(const uint64_t* p, const uint32_t* k_canonical, uint32_t* out_k, uint64_t* out_pt) {
     bool n1, n2;
     glv::decompose(k_canonical, out_k, n1, out_k + 6, n2);
@@ -82,6 +94,7 @@ void hc_glv(const uint64_t* p, const uint32_t* k_canonical, uint32_t* out_k, uin
     store_pt(scalar_mul(Q, k).to_affine(), out_pt);
     store_pt(scalar_mul_plain(Q, k).to_affine(), out_pt + 8);
     store_pt(scalar_mul_bitwise(Q, k).to_affine(), out_pt + 16);
+    store_pt(scalar_mul_xyzz(Q, k).to_affine(), out_pt + 24);
 }
 void hc_keccak(const uint8_t* d, uint64_t n, uint8_t* out) { Keccak256 h; h.update(d, n); h.finish(out); }
 // transcript: commit `n` 32-byte big-endian values, then draw `m` challenges (canonical LE limbs out)

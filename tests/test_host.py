@@ -326,6 +326,21 @@ def test_xyzz_formulas_against_oracle_group_law(hc, orc, simple_key):
         assert (out[3] == orc.g1_mul(p, 11)).all()
 
 
+def test_jacobian_window_arithmetic_against_oracle_group_law(hc, orc, simple_key):
+    """ec.cuh g1_jac_t (the window loop of ecmul.cuh's scalar multiplication): XYZZ -> Jacobian -> XYZZ conversions, the
+    a = 0 doubling and the addition of a table entry, with the special cases (equal, opposite, either operand infinity)."""
+    g = simple_key.g1_bases
+    inf = np.zeros(8, dtype=np.uint64)
+    neg5 = g[5].copy()
+    neg5[4:] = ints_to_limbs([Q_MOD - limbs_to_ints(g[5][4:])[0]])[0]
+    for p, q in [(g[3], g[7]), (g[5], g[5]), (g[5], neg5), (g[5], inf), (inf, g[9]), (inf, inf), (g[40], g[2])]:
+        out = np.zeros((3, 8), dtype=np.uint64)
+        hc.hc_jac_ops(_p(np.ascontiguousarray(p)), _p(np.ascontiguousarray(q)), _p(out))
+        assert (out[0] == orc.g1_add(p, q)).all()
+        assert (out[1] == orc.g1_add(p, p)).all()
+        assert (out[2] == orc.g1_add(orc.g1_add(p, q), q)).all()
+
+
 def test_lazy_form_field_chain(hc):
     """fp.cuh lazy form ([0, 2p)): products without the final conditional subtraction, add/sub modulo 2p; a chain of
     them normalised once must equal the canonical computation (Montgomery factors included)."""
@@ -355,13 +370,13 @@ def test_glv_decomposition_and_scalar_multiplication(hc, orc, simple_key):
         p = simple_key.g1_bases[3 + n % 50] if n != 5 else inf
         kk = ints_to_limbs([k]).view(np.uint32)
         out_k = np.zeros(12, dtype=np.uint32)
-        out_pt = np.zeros((3, 8), dtype=np.uint64)
+        out_pt = np.zeros((4, 8), dtype=np.uint64)
         hc.hc_glv(_p(np.ascontiguousarray(p)), _p(kk), _p(out_k), _p(out_pt))
         k1 = sum(int(out_k[i]) << (32 * i) for i in range(5)) * (-1 if out_k[5] else 1)
         k2 = sum(int(out_k[6 + i]) << (32 * i) for i in range(5)) * (-1 if out_k[11] else 1)
         assert (k1 + k2 * lam - k) % R_MOD == 0 and abs(k1) < (1 << 129) and abs(k2) < (1 << 129)
         want = orc.g1_mul(p, k)
-        assert (out_pt[0] == want).all() and (out_pt[1] == want).all() and (out_pt[2] == want).all(), hex(k)
+        assert all((out_pt[j] == want).all() for j in range(4)), hex(k)
 
 
 def test_host_keccak_and_transcript_match_oracle(hc, orc):
