@@ -483,3 +483,24 @@ def test_two_gate_type_verifier_accepts_the_oracle_proof_with_the_real_pairing(o
     bad.opening_at_z_proof = proof.opening_at_z_omega_proof
     assert recursive.verify(vk, bad) is False
     assert recursive.verify(recursive.RecursiveVerificationKey(asm.n - 1, asm.num_inputs, com, b""), proof) is False
+
+
+def test_verifier_handles_a_selector_commitment_at_infinity(orc):
+    """An addition-only circuit has q_m = 0, so its commitment in the verification key is the point at infinity ((0, 0) in
+    vk.bin): the oracle's proof of it must be accepted by the pairing-based verifier, which skips that term, absorbs nothing
+    for it in the transcript (vk commitments are not absorbed) and still rejects a wrong public input."""
+    m1 = R_MOD - 1
+    rows = [(1, 0, 0, 0, [m1, 0, 0, 0, 0, 0, 0]),            # public input x
+            (1, 2, 3, 0, [1, 1, m1, 0, 0, 0, 0]),            # x + y - z = 0
+            (3, 2, 4, 0, [1, 1, m1, 0, 0, 0, 0])]            # z + y - w = 0
+    asm = circuit.assembly_from_rows(rows, [0, 3, 4, 7, 11], 1)
+    assert asm.n == 4 and circuit.is_satisfied(asm)
+    srs = orc.srs_gen(asm.n, 42, threads=1)
+    raw = orc.prove(asm.n, asm.num_inputs, asm.wire_idx, asm.var_values, asm.selectors, srs, threads=1)
+    com = orc.setup_commitments(asm.n, asm.num_inputs, asm.wire_idx, asm.selectors, srs, nvars=asm.nvars, threads=1)
+    assert not com[4].any()                                   # [q_m] = infinity
+    proof = reader.Proof.read(io.BytesIO(raw))
+    vk = reader.VerificationKey(asm.n - 1, 1, com[:6], com[6:7], com[7:11], [5, 7, 10], reader.CRS_42_G2)
+    assert plonk.verify(vk, proof) is True
+    proof.input_values = [4]
+    assert plonk.verify(vk, proof) is False
