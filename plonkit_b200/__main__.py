@@ -103,9 +103,11 @@ def cmd_dump_lagrange(o):
 
 
 def cmd_prove(o):
-    c = CircomCircuit(reader.load_r1cs(resolve_circuit_file(o.circuit)), reader.load_witness_from_file(o.witness), None, AUX_OFFSET,
+    c = CircomCircuit(reader.load_r1cs(resolve_circuit_file(o.circuit)), reader.load_witness_limbs(o.witness), None, AUX_OFFSET,
                       not o.allow_unpinned_transpilation)
-    setup = plonk.SetupForProver.prepare_setup_for_prover(c, reader.load_key_monomial_form(o.srs_monomial_form),
+    # the gate tables do not depend on the witness: transpile without it, then assign the witness through the circuit's plan
+    shape = CircomCircuit(c.r1cs, None, None, AUX_OFFSET, c.strict)
+    setup = plonk.SetupForProver.prepare_setup_for_prover(shape, reader.load_key_monomial_form(o.srs_monomial_form),
                                                           reader.maybe_load_key_lagrange_form(o.srs_lagrange_form))
     print("Proving...", file=sys.stderr)
     proof = setup.prove(c, o.transcript)

@@ -17,7 +17,7 @@ from typing import List, Optional, Tuple
 
 import numpy as np
 
-from .bn254 import R_MOD, ints_to_limbs
+from .bn254 import R_MOD, ints_to_limbs, limbs_to_ints
 
 AUX_OFFSET = 1  # src/plonk.rs:24
 SELECTOR_NAMES = ("q_a", "q_b", "q_c", "q_d", "q_m", "q_const", "q_dnext")
@@ -42,9 +42,16 @@ class CircomCircuit:  # src/circom_circuit.rs:40-47
     strict: bool = True   # False: also transpile constraint shapes no reference fixture pins (see _transpile)
 
     def _w(self, i):
-        if self.wire_mapping is None:
-            return self.witness[i]
-        return self.witness[self.wire_mapping[i]]
+        j = i if self.wire_mapping is None else self.wire_mapping[i]
+        if isinstance(self.witness, np.ndarray):      # (len, 4) uint64 canonical limbs (reader.load_witness_limbs)
+            return limbs_to_ints(self.witness[j:j + 1])[0]
+        return self.witness[j]
+
+    def witness_ints(self):
+        """the witness as Python integers whatever form it is held in"""
+        if isinstance(self.witness, np.ndarray):
+            return limbs_to_ints(self.witness)
+        return self.witness
 
     def get_public_inputs(self):  # src/circom_circuit.rs:50-59
         if self.witness is None:
@@ -79,6 +86,7 @@ class Assembly:
     var_values: Optional[np.ndarray]     # (nvars, 4) uint64 canonical LE limbs, or None (setup only)
     nvars: int
     num_gates: int = 0                   # gates before padding (incl. input gates)
+    plan: Optional["WitnessPlan"] = None  # how var_values follow from a circom witness (set by synthesize)
 
     def public_inputs(self):
         from .bn254 import limbs_to_ints
@@ -109,6 +117,7 @@ def _norm_lc(lc: LC):
 class _Gates:
     rows: list = field(default_factory=list)   # (a, b, c, d, [7 selector ints])
     values: list = field(default_factory=list)  # variable values (None when no witness)
+    program: list = field(default_factory=list)  # per new variable, in order: (const, [(var, coeff)]) — its value as a combination of earlier ones
     hints: int = 0
     stats: list = field(default_factory=list)
 
@@ -128,7 +137,9 @@ def _transpile(circuit: CircomCircuit, strict: bool = True) -> _Gates:
     g = _Gates()
     # variable id == witness index: Input(i) -> i ; Aux(j + aux_offset) -> num_inputs + j  (circom_circuit.rs:75-105)
     if have_w:
-        g.values = [0] + [circuit._w(i) % R_MOD for i in range(1, r.num_variables)]
+        wit = circuit.witness_ints()
+        wm = circuit.wire_mapping
+        g.values = [0] + [(wit[i] if wm is None else wit[wm[i]]) % R_MOD for i in range(1, r.num_variables)]
     else:
         g.values = [None] * r.num_variables
     # public-input gates first
@@ -136,14 +147,12 @@ def _transpile(circuit: CircomCircuit, strict: bool = True) -> _Gates:
         g.rows.append((i, 0, 0, 0, [R_MOD - 1, 0, 0, 0, 0, 0, 0]))
     M1 = R_MOD - 1
 
-    def new_var(val):
-        g.values.append(val)
+    def new_var(terms, const):
+        """a fresh variable whose value is sum(terms) + const: recorded in g.program (the per-proof witness assignment replays
+        it, WitnessPlan) and evaluated right away when a witness is at hand"""
+        g.program.append((const, list(terms)))
+        g.values.append((sum(c * g.values[v] for v, c in terms) + const) % R_MOD if have_w else None)
         return len(g.values) - 1
-
-    def lc_value(terms, const):
-        if not have_w:
-            return None
-        return (sum(c * g.values[v] for v, c in terms) + const) % R_MOD
 
     def chain(terms, const, out):
         """Gates enforcing sum(terms) + const - out = 0 (out = None: the sum itself is zero).  More than four summands
@@ -155,8 +164,7 @@ def _transpile(circuit: CircomCircuit, strict: bool = True) -> _Gates:
             g.rows.append((wires[0], wires[1], wires[2], wires[3], [coefs[0], coefs[1], coefs[2], coefs[3], 0, const, 0]))
             return
         first, rest = items[:4], items[4:]
-        acc_val = lc_value(first, const)
-        acc = new_var(acc_val)
+        acc = new_var(first, const)
         g.rows.append((first[0][0], first[1][0], first[2][0], first[3][0],
                        [first[0][1], first[1][1], first[2][1], first[3][1], 0, const, M1]))
         while rest:
@@ -164,10 +172,9 @@ def _transpile(circuit: CircomCircuit, strict: bool = True) -> _Gates:
             wires = [v for v, _ in take] + [0] * (3 - len(take))
             coefs = [c for _, c in take] + [0] * (3 - len(take))
             if rest:
-                nxt_val = None if not have_w else (acc_val + sum(c * g.values[v] for v, c in take)) % R_MOD
-                nxt = new_var(nxt_val)
+                nxt = new_var([(acc, 1)] + list(take), 0)
                 g.rows.append((wires[0], wires[1], wires[2], acc, [coefs[0], coefs[1], coefs[2], 1, 0, 0, M1]))
-                acc, acc_val = nxt, nxt_val
+                acc = nxt
             else:
                 g.rows.append((wires[0], wires[1], wires[2], acc, [coefs[0], coefs[1], coefs[2], 1, 0, 0, 0]))
 
@@ -176,7 +183,7 @@ def _transpile(circuit: CircomCircuit, strict: bool = True) -> _Gates:
         combination already is a single variable"""
         if len(terms) == 1 and const == 0:
             return terms[0]
-        t = new_var(lc_value(terms, const))
+        t = new_var(terms, const)
         if len(terms) == 2:   # the pinned layout: (a = v1, b = v2, c = t), q_c = -1
             (v1, c1), (v2, c2) = terms
             g.rows.append((v1, v2, t, 0, [c1, c2, M1, 0, 0, const, 0]))
@@ -222,6 +229,98 @@ def _transpile(circuit: CircomCircuit, strict: bool = True) -> _Gates:
     return g
 
 
+class WitnessPlan:
+    """The per-proof half of synthesis: var_values of an `Assembly` from a circom witness, without transpiling again.
+
+    bellman re-synthesises the transpiled circuit inside every `prove` (src/plonk.rs:132-176) and evaluates each variable's
+    value there; the gate tables do not depend on the witness, so here `_transpile` runs once (prepare_setup_for_prover) and
+    leaves (i) the direct variables — variable i is witness[wire_mapping[i]], variable 0 the dummy 0 — and (ii) a
+    straight-line program for the variables it introduced: value = const + sum coeff * earlier value.  `assign` replays
+    it in the native host library (csrc/host/witness.cpp) or, if that is not built, with Python integers — same values."""
+
+    def __init__(self, num_direct: int, program):
+        self.num_direct = num_direct
+        self.num_new = len(program)
+        off = np.zeros(self.num_new + 1, dtype=np.uint64)
+        tv, tc, consts = [], [], []
+        for k, (const, terms) in enumerate(program):
+            for v, c in terms:
+                if not 0 <= v < num_direct + k:
+                    raise ValueError("witness program entry %d reads variable %d before it is assigned" % (k, v))
+                tv.append(v)
+                tc.append(c % R_MOD)
+            consts.append(const % R_MOD)
+            off[k + 1] = len(tv)
+        self.off = off
+        self.term_var = np.asarray(tv, dtype=np.uint32)
+        self.term_coef = ints_to_limbs(tc) if tc else np.zeros((0, 4), dtype=np.uint64)
+        self.consts = ints_to_limbs(consts) if consts else np.zeros((0, 4), dtype=np.uint64)
+        self._coef_mont = None      # the coefficients in Montgomery form, made once by the host library
+
+    @property
+    def nvars(self):
+        return self.num_direct + self.num_new
+
+    def assign(self, witness, wire_mapping=None, native: Optional[bool] = None, threads: Optional[int] = None) -> np.ndarray:
+        """witness: list of integers or (len, 4) uint64 canonical limbs -> (nvars, 4) uint64 canonical limbs.
+        native: None = the host library when it is built, True = require it, False = Python integers."""
+        if isinstance(witness, np.ndarray):
+            w = np.ascontiguousarray(witness, dtype=np.uint64).reshape(-1, 4)
+        else:
+            w = ints_to_limbs([x % R_MOD for x in witness])
+        idx = np.arange(self.num_direct) if wire_mapping is None else np.asarray(wire_mapping[:self.num_direct], dtype=np.int64)
+        if self.num_direct > len(idx) or (len(idx) and int(idx.max()) >= w.shape[0]):
+            raise ValueError("witness holds %d values, the circuit has %d variables" % (w.shape[0], self.num_direct))
+        values = np.zeros((self.nvars, 4), dtype=np.uint64)
+        values[:self.num_direct] = w[idx]
+        values[0] = 0                                   # variable 0 is bellman's dummy variable, not the constant ONE
+        lib = host_library() if native in (None, True) else None
+        if lib is None and native:
+            raise RuntimeError("libplonkit_host.so is not built (python __graft_entry__.py)")
+        if lib is not None:
+            import ctypes
+            import os
+            vp = ctypes.c_void_p
+            if self._coef_mont is None:
+                self._coef_mont = np.zeros_like(self.term_coef)
+                lib.ph_fr_to_mont(self.term_coef.ctypes.data_as(vp), self._coef_mont.ctypes.data_as(vp), ctypes.c_uint64(len(self.term_coef)))
+            if threads is None:
+                threads = min(16, os.cpu_count() or 1)
+            rc = lib.ph_assign_witness(ctypes.c_uint64(self.num_direct), ctypes.c_uint64(self.num_new), self.off.ctypes.data_as(vp),
+                                       self.term_var.ctypes.data_as(vp), self._coef_mont.ctypes.data_as(vp), 1,
+                                       self.consts.ctypes.data_as(vp), values.ctypes.data_as(vp), int(threads))
+            if rc:
+                raise ValueError("witness assignment failed at variable %d (value not in the field, or a malformed program)" % (rc - 1))
+            return values
+        vals = limbs_to_ints(values[:self.num_direct])
+        if any(v >= R_MOD for v in vals):
+            raise ValueError("witness value not in the field")
+        coef, consts = limbs_to_ints(self.term_coef), limbs_to_ints(self.consts)
+        for k in range(self.num_new):
+            lo, hi = int(self.off[k]), int(self.off[k + 1])
+            vals.append((consts[k] + sum(coef[j] * vals[self.term_var[j]] for j in range(lo, hi))) % R_MOD)
+        if self.num_new:
+            values[self.num_direct:] = ints_to_limbs(vals[self.num_direct:])
+        return values
+
+
+_HOST_LIB = [False]
+
+
+def host_library():
+    """plonkit_b200/libplonkit_host.so (plain C++ host helpers, built by __graft_entry__.build()), or None if not built"""
+    if _HOST_LIB[0] is False:
+        import ctypes
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libplonkit_host.so")
+        lib = None
+        if os.path.exists(path):
+            lib = ctypes.CDLL(path)
+            lib.ph_assign_witness.restype = ctypes.c_int64
+        _HOST_LIB[0] = lib
+    return _HOST_LIB[0]
+
+
 def transpile_with_gates_count(circuit: CircomCircuit, strict: Optional[bool] = None):
     """src/transpile.rs:127-139 -> (gates_count, hints_count).  Counts exclude the public-input gates."""
     g = _transpile(circuit, circuit.strict if strict is None else strict)
@@ -231,7 +330,9 @@ def transpile_with_gates_count(circuit: CircomCircuit, strict: Optional[bool] = 
 
 def synthesize(circuit: CircomCircuit, strict: Optional[bool] = None) -> Assembly:
     g = _transpile(circuit, circuit.strict if strict is None else strict)
-    return assembly_from_rows(g.rows, g.values, circuit.r1cs.num_inputs - 1)
+    asm = assembly_from_rows(g.rows, g.values, circuit.r1cs.num_inputs - 1)
+    asm.plan = WitnessPlan(circuit.r1cs.num_variables, g.program)
+    return asm
 
 
 def assembly_from_rows(rows, values, num_inputs) -> Assembly:

@@ -52,6 +52,28 @@ def _as_assembly(circuit) -> Assembly:
     raise TypeError("circuit must be a CircomCircuit or an Assembly")
 
 
+class _WitnessSource:
+    """What a setup remembers of the circuit it was prepared from, so that `prove(circuit)` with another witness of the SAME
+    R1CS assigns the variables through the circuit's WitnessPlan (native host code, milliseconds) instead of transpiling
+    the R1CS again the way bellman's `prove` re-synthesises it (src/plonk.rs:132-176) — same values, same proof."""
+
+    def __init__(self, circuit, asm):
+        self.plan = getattr(asm, "plan", None) if isinstance(circuit, CircomCircuit) else None
+        self.r1cs = circuit.r1cs if isinstance(circuit, CircomCircuit) else None
+        self.strict = getattr(circuit, "strict", None)
+
+    def values(self, circuit):
+        """var_values ((nvars, 4) uint64) of `circuit`: an array as is, an Assembly's own, a CircomCircuit's via the plan"""
+        if isinstance(circuit, np.ndarray):
+            return circuit
+        if (self.plan is not None and isinstance(circuit, CircomCircuit) and circuit.r1cs is self.r1cs
+                and circuit.strict == self.strict):
+            if circuit.witness is None:
+                return None
+            return self.plan.assign(circuit.witness, circuit.wire_mapping)
+        return _as_assembly(circuit).var_values
+
+
 def domain_log2(circuit) -> int:
     """log2 of the evaluation domain of a circuit (setup_polynomials.n.next_power_of_two(), src/plonk.rs:180)."""
     return _as_assembly(circuit).n.bit_length() - 1
@@ -83,6 +105,7 @@ class SetupForProver:
         self.n = asm.n
         self.num_inputs = asm.num_inputs
         self.nvars = asm.nvars
+        self._source = _WitnessSource(circuit, asm)
         self._loaded_key_id = None
         self._ensure_srs()
         wire_idx = np.ascontiguousarray(asm.wire_idx, dtype=np.uint32)
@@ -130,9 +153,7 @@ class SetupForProver:
             raise SynthesisError(4, "witness does not satisfy the circuit")
 
     def upload_witness(self, circuit_or_values):
-        vals = circuit_or_values
-        if not isinstance(vals, np.ndarray):
-            vals = _as_assembly(vals).var_values
+        vals = self._source.values(circuit_or_values)
         if vals is None:
             raise SynthesisError(1, "circuit has no witness")
         vals = np.ascontiguousarray(vals, dtype=np.uint64).reshape(-1, 4)
@@ -151,8 +172,7 @@ class SetupForProver:
         self._ensure_srs()
         vals, nvars = None, 0
         if circuit is not None:
-            asm = circuit if isinstance(circuit, np.ndarray) else _as_assembly(circuit)
-            arr = asm if isinstance(asm, np.ndarray) else asm.var_values
+            arr = self._source.values(circuit)
             if arr is None:
                 raise SynthesisError(1, "circuit has no witness")
             vals = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 4)
@@ -188,6 +208,7 @@ class ShardedSetupForProver:
             raise SynthesisError(2, "monomial SRS holds %d bases, the circuit needs %d" % (key_monomial_form.size, asm.n))
         self.ctx, self.key_monomial_form = ctx, key_monomial_form
         self.n, self.num_inputs, self.nvars = asm.n, asm.num_inputs, asm.nvars
+        self._source = _WitnessSource(circuit, asm)
         world, rank = ctx.world, ctx.rank
         if asm.n % world:
             raise SynthesisError(6, "domain size is not divisible by the number of ranks")
@@ -221,7 +242,10 @@ class ShardedSetupForProver:
                                self.key_monomial_form.g2_raw)
 
     def upload_witness(self, values):
-        vals = np.ascontiguousarray(values, dtype=np.uint64).reshape(-1, 4)
+        vals = self._source.values(values)
+        if vals is None:
+            raise SynthesisError(1, "circuit has no witness")
+        vals = np.ascontiguousarray(vals, dtype=np.uint64).reshape(-1, 4)
         self.ctx._check(self.ctx._lib.pk_dist_witness_upload(self.ctx._h, self._h, vals.ctypes.data, vals.shape[0]))
 
     def prove(self, circuit=None, transcript: str = "keccak") -> Proof:
@@ -229,7 +253,7 @@ class ShardedSetupForProver:
             raise NotImplementedError("the sharded prover implements the 'keccak' transcript")
         vals, nvars = None, 0
         if circuit is not None:
-            arr = circuit if isinstance(circuit, np.ndarray) else _as_assembly(circuit).var_values
+            arr = self._source.values(circuit)
             if arr is None:
                 raise SynthesisError(1, "circuit has no witness")
             vals = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 4)

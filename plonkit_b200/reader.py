@@ -247,7 +247,37 @@ def load_witness_from_file(filename: str) -> List[int]:  # src/reader.rs:92-98
         return load_witness_from_array(f.read())
 
 
+def load_witness_limbs(filename: str) -> np.ndarray:
+    """load_witness_from_file as a (len, 4) uint64 array of canonical little-endian limbs: for a `.wtns` file the 32-byte
+    elements are taken as they lie in the file, no Python integer per value (what `WitnessPlan.assign` and the device consume)"""
+    if filename.endswith("json"):
+        return ints_to_limbs(load_witness_from_file(filename))
+    with open(filename, "rb") as f:
+        buffer = f.read()
+    off, witness_len = _wtns_body(buffer)
+    limbs = np.frombuffer(buffer, dtype="<u8", count=witness_len * 4, offset=off).reshape(witness_len, 4).astype(np.uint64)
+    # value < r, limb by limb from the top
+    r = ints_to_limbs([R_MOD])[0]
+    less = np.zeros(witness_len, dtype=bool)
+    equal = np.ones(witness_len, dtype=bool)
+    for i in (3, 2, 1, 0):
+        less |= equal & (limbs[:, i] < r[i])
+        equal &= limbs[:, i] == r[i]
+    if not less.all():
+        raise ValueError("witness element is not in the field")
+    return limbs
+
+
 def load_witness_from_array(buffer: bytes) -> List[int]:  # src/reader.rs:119-175
+    off, witness_len = _wtns_body(buffer)
+    vals = [int.from_bytes(buffer[off + 32 * i:off + 32 * i + 32], "little") for i in range(witness_len)]
+    if any(v >= R_MOD for v in vals):
+        raise ValueError("witness element is not in the field")
+    return vals
+
+
+def _wtns_body(buffer: bytes):
+    """header checks of src/reader.rs:119-175 -> (offset of the first element, number of elements)"""
     if buffer[:4] != b"wtns":
         raise ValueError("invalid file header")
     version, num_sections = struct.unpack_from("<II", buffer, 4)
@@ -277,10 +307,9 @@ def load_witness_from_array(buffer: bytes) -> List[int]:  # src/reader.rs:119-17
         raise ValueError("invalid section type")
     if sec_size != witness_len * field_size:
         raise ValueError("invalid witness section size %d" % sec_size)
-    vals = [int.from_bytes(buffer[off + 32 * i:off + 32 * i + 32], "little") for i in range(witness_len)]
-    if any(v >= R_MOD for v in vals):
-        raise ValueError("witness element is not in the field")
-    return vals
+    if len(buffer) < off + sec_size:
+        raise ValueError("witness file is truncated")
+    return off, witness_len
 
 
 # ---------------------------------------------------------------- R1CS (App. B.5 / B.6)

@@ -26,6 +26,27 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert getattr(lib, name) is not None
 
 
+def test_host_library_loads_and_exports_every_declared_symbol():
+    """include/plonkit_host.h (plain C++ host helpers, no CUDA) against plonkit_b200/libplonkit_host.so, and its field product
+    against Python integers"""
+    lib = circuit.host_library()
+    assert lib is not None, "libplonkit_host.so is not built (python __graft_entry__.py)"
+    hdr = open(os.path.join(ROOT, "include", "plonkit_host.h")).read()
+    declared = set(re.findall(r"\b(ph_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == {"ph_assign_witness", "ph_fr_to_mont", "ph_fr_mul"}
+    for name in declared:
+        assert getattr(lib, name) is not None
+    rng = np.random.default_rng(3)
+    a = [0, 1, R_MOD - 1, R_MOD - 2, 1 << 253] + [int.from_bytes(rng.bytes(32), "little") % R_MOD for _ in range(500)]
+    b = [R_MOD - 1] * 3 + [5, 1 << 253] + [int.from_bytes(rng.bytes(32), "little") % R_MOD for _ in range(500)]
+    A, B = ints_to_limbs(a), ints_to_limbs(b)
+    out = np.zeros_like(A)
+    lib.ph_fr_mul(_p(A), _p(B), _p(out), ctypes.c_uint64(len(a)))
+    assert limbs_to_ints(out) == [x * y % R_MOD for x, y in zip(a, b)]
+    lib.ph_fr_to_mont(_p(A), _p(out), ctypes.c_uint64(len(a)))
+    assert limbs_to_ints(out) == [x * (1 << 256) % R_MOD for x in a]
+
+
 def test_constants_in_library_match_appendix_c():
     c = _lib.constants()
     vals = limbs_to_ints(c.reshape(6, 4))
@@ -96,6 +117,31 @@ def test_wtns_parser_and_its_error_paths():
             reader.load_witness_from_array(bad)
     with pytest.raises(ValueError):
         reader.load_witness_from_array(_wtns([R_MOD]))
+
+
+def test_witness_as_limbs_equals_witness_as_integers(tmp_path):
+    """reader.load_witness_limbs: the same values as load_witness_from_file, as the (len, 4) limb array the prover consumes
+    (.wtns elements taken as they lie in the file), same field check; a CircomCircuit holding it behaves the same."""
+    vals = [1, 35, 3, 9, R_MOD - 1, 1 << 200, (1 << 64) - 1, 1 << 64]
+    path = tmp_path / "w.wtns"
+    path.write_bytes(_wtns(vals))
+    limbs = reader.load_witness_limbs(str(path))
+    assert limbs.shape == (len(vals), 4) and limbs_to_ints(limbs) == vals == reader.load_witness_from_file(str(path))
+    assert limbs_to_ints(reader.load_witness_limbs(os.path.join(SIMPLE, "witness.json"))) == \
+        reader.load_witness_from_file(os.path.join(SIMPLE, "witness.json"))
+    for bad in (R_MOD, R_MOD + 1, (1 << 256) - 1):
+        path.write_bytes(_wtns([1, bad % (1 << 256)]))
+        with pytest.raises(ValueError, match="not in the field"):
+            reader.load_witness_limbs(str(path))
+    path.write_bytes(_wtns([1, 2, 3])[:-5])
+    with pytest.raises(ValueError, match="truncated"):
+        reader.load_witness_limbs(str(path))
+    r1cs = reader.load_r1cs(os.path.join(SIMPLE, "circuit.r1cs.json"))
+    wj = reader.load_witness_from_file(os.path.join(SIMPLE, "witness.json"))
+    a = circuit.CircomCircuit(r1cs, wj)
+    b = circuit.CircomCircuit(r1cs, ints_to_limbs(wj))
+    assert a.get_public_inputs() == b.get_public_inputs() and a.get_public_inputs_json() == b.get_public_inputs_json()
+    assert (circuit.synthesize(a).var_values == circuit.synthesize(b).var_values).all()
 
 
 def _r1cs_bin(n_wires, n_pub_out, n_pub_in, n_prv_in, constraints, field_size=32):
@@ -504,3 +550,55 @@ def test_verifier_handles_a_selector_commitment_at_infinity(orc):
     assert plonk.verify(vk, proof) is True
     proof.input_values = [4]
     assert plonk.verify(vk, proof) is False
+
+
+def test_witness_plan_replays_synthesis_natively_and_in_python():
+    """circuit.WitnessPlan (the per-proof half of synthesis; bellman redoes all of it inside every prove, src/plonk.rs:132-176):
+    var_values from a witness through the native host library (csrc/host/witness.cpp, 1 and 8 threads) and through Python
+    integers == synthesize(circuit).var_values — for the reference's simple circuit (strict layout), for a Poseidon-shaped
+    R1CS with ~60-term combinations (running sums), with a wire mapping, with the witness given as limbs, and for ANOTHER
+    witness of the same R1CS assigned through the plan of the first."""
+    assert circuit.host_library() is not None, "libplonkit_host.so is not built (python __graft_entry__.py)"
+    simple = circuit.CircomCircuit(reader.load_r1cs(os.path.join(SIMPLE, "circuit.r1cs.json")),
+                                   reader.load_witness_from_file(os.path.join(SIMPLE, "witness.json")))
+    r1cs, wit = synth.poseidon_r1cs(20)
+    pos = circuit.CircomCircuit(r1cs, wit, None, circuit.AUX_OFFSET, False)
+    rng = np.random.default_rng(5)
+    perm = [0] + [int(x) + 1 for x in rng.permutation(r1cs.num_variables - 1)]      # variable i reads witness[perm[i]]
+    shuffled = [0] * len(wit)
+    for i, j in enumerate(perm):
+        shuffled[j] = wit[i]
+    mapped = circuit.CircomCircuit(r1cs, shuffled, perm, circuit.AUX_OFFSET, False)
+    for c in (simple, pos, mapped):
+        asm = circuit.synthesize(c)
+        assert asm.plan.nvars == asm.nvars
+        for kw in ({"native": True, "threads": 1}, {"native": True, "threads": 8}, {"native": False}):
+            assert (asm.plan.assign(c.witness, c.wire_mapping, **kw) == asm.var_values).all(), kw
+        assert (asm.plan.assign(ints_to_limbs(c.witness), c.wire_mapping) == asm.var_values).all()
+    # another witness of the same R1CS: the plan of the first circuit, no second transpilation
+    plan = circuit.synthesize(pos).plan
+    r2, wit2 = synth.poseidon_r1cs(20, inputs=(11, 12))
+    assert len(r2.constraints) == len(r1cs.constraints) and wit2 != wit
+    want = circuit.synthesize(circuit.CircomCircuit(r2, wit2, None, circuit.AUX_OFFSET, False)).var_values
+    assert (plan.assign(wit2) == want).all() and (plan.assign(wit2, native=False) == want).all()
+    # what SetupForProver keeps of its circuit: same R1CS object -> the plan; anything else -> a fresh synthesis
+    src = plonk._WitnessSource(pos, circuit.synthesize(pos))
+    other = circuit.CircomCircuit(r1cs, wit2, None, circuit.AUX_OFFSET, False)
+    assert (src.values(other) == want).all()
+    assert (src.values(circuit.CircomCircuit(r2, wit2, None, circuit.AUX_OFFSET, False)) == want).all()
+    assert src.values(circuit.CircomCircuit(r1cs, None, None, circuit.AUX_OFFSET, False)) is None
+    # the CLI's flow: set up from the witness-less circuit, then prove the one holding the witness as limbs
+    shape = circuit.CircomCircuit(r1cs, None, None, circuit.AUX_OFFSET, False)
+    asm0 = circuit.synthesize(shape)
+    assert asm0.var_values is None and (asm0.selectors == circuit.synthesize(pos).selectors).all()
+    held = circuit.CircomCircuit(r1cs, ints_to_limbs(wit2), None, circuit.AUX_OFFSET, False)
+    assert (plonk._WitnessSource(shape, asm0).values(held) == want).all()
+    # errors: a short witness, a value outside the field, a program that reads ahead
+    with pytest.raises(ValueError, match="witness holds"):
+        plan.assign(wit[:10])
+    bad = ints_to_limbs(wit)
+    bad[3] = ints_to_limbs([R_MOD])[0] + np.array([5, 0, 0, 0], dtype=np.uint64)
+    with pytest.raises(ValueError, match="variable 3"):
+        plan.assign(bad)
+    with pytest.raises(ValueError, match="before it is assigned"):
+        circuit.WitnessPlan(3, [(0, [(1, 1)]), (0, [(5, 1)])])
