@@ -602,3 +602,116 @@ def test_witness_plan_replays_synthesis_natively_and_in_python():
         plan.assign(bad)
     with pytest.raises(ValueError, match="before it is assigned"):
         circuit.WitnessPlan(3, [(0, [(1, 1)]), (0, [(5, 1)])])
+
+
+class _BoundaryRecorder:
+    """Stands where the CUDA library's context would: records what the host layer hands across the C ABI (gate tables at
+    pk_setup_create, variable values at pk_prove / pk_witness_upload) and returns an all-zero proof.  No compute."""
+
+    class _Lib:
+        def __init__(self):
+            self.values, self.uploaded, self.lagrange = None, None, None
+
+        def pk_setup_create(self, h, a_ref, out_ref):
+            a = a_ref._obj
+            n = int(a.n)
+            self.meta = (n, int(a.num_inputs), int(a.nvars))
+            self.wire_idx = np.ctypeslib.as_array((ctypes.c_uint32 * (4 * n)).from_address(a.wire_idx)).reshape(4, n).copy()
+            self.selectors = np.ctypeslib.as_array((ctypes.c_uint64 * (28 * n)).from_address(a.selectors)).reshape(7, n, 4).copy()
+            out_ref._obj.value = 77
+            return 0
+
+        def pk_setup_use_lagrange(self, h, sh, flag):
+            self.lagrange = flag
+            return 0
+
+        def pk_prove(self, h, sh, vals_ptr, nvars, pr_ref, inputs_ptr):
+            self.values = None if not vals_ptr else \
+                np.ctypeslib.as_array((ctypes.c_uint64 * (4 * nvars)).from_address(vals_ptr)).reshape(nvars, 4).copy()
+            pr_ref._obj.n, pr_ref._obj.num_inputs = self.meta[0] - 1, self.meta[1]
+            return 0
+
+        def pk_witness_upload(self, h, sh, vals_ptr, nvars):
+            self.uploaded = np.ctypeslib.as_array((ctypes.c_uint64 * (4 * nvars)).from_address(vals_ptr)).reshape(nvars, 4).copy()
+            return 0
+
+        def pk_setup_destroy(self, sh):
+            return 0
+
+        # the sharded prover's entry points take the same arguments
+        pk_dist_setup_create, pk_dist_prove, pk_dist_witness_upload, pk_dist_setup_destroy = \
+            pk_setup_create, pk_prove, pk_witness_upload, pk_setup_destroy
+
+    def __init__(self, rank=0, world=1):
+        self._lib, self._h, self._children = self._Lib(), 1, set()
+        self.srs_tag = self.lagrange_tag = None
+        self.rank, self.world, self.loaded = rank, world, None
+
+    def _check(self, rc):
+        assert rc == 0
+
+    def srs_load_g1(self, bases, tag=None):
+        self.srs_tag, self.loaded = tag, bases
+
+    def srs_load_g1_lagrange(self, bases, tag=None):
+        self.lagrange_tag = tag
+
+
+def test_host_layer_hands_the_synthesised_tables_and_values_across_the_c_abi(tmp_path, monkeypatch, simple_key):
+    """Everything between the reference-facing calls and the C ABI, without a device: `SetupForProver` and the CLI's `prove`
+    must pass pk_setup_create the gate tables of synthesize(circuit) and pk_prove the variable values of synthesize(circuit)
+    — whether the witness comes with the circuit, as another witness of the same R1CS (WitnessPlan), as an Assembly, as an
+    array, or from witness.json / .wtns files through the CLI."""
+    from plonkit_b200 import __main__ as cli
+    r1cs = reader.load_r1cs(os.path.join(SIMPLE, "circuit.r1cs.json"))
+    wit = reader.load_witness_from_file(os.path.join(SIMPLE, "witness.json"))
+    c = circuit.CircomCircuit(r1cs, wit)
+    want = circuit.synthesize(c)
+    rec = _BoundaryRecorder()
+    setup = plonk.SetupForProver.prepare_setup_for_prover(c, simple_key, None, ctx=rec)
+    assert rec._lib.meta == (want.n, want.num_inputs, want.nvars)
+    assert (rec._lib.wire_idx == want.wire_idx).all() and (rec._lib.selectors == want.selectors).all()
+    proof = setup.prove(c, "keccak")
+    assert (rec._lib.values == want.var_values).all() and proof.n == want.n - 1 and rec._lib.lagrange == 0
+    for form in (want, want.var_values, circuit.CircomCircuit(r1cs, ints_to_limbs(wit)),
+                 circuit.CircomCircuit(reader.load_r1cs(os.path.join(SIMPLE, "circuit.r1cs.json")), wit)):
+        rec._lib.values = None
+        setup.prove(form)
+        assert (rec._lib.values == want.var_values).all()
+    setup.upload_witness(c)
+    assert (rec._lib.uploaded == want.var_values).all()
+    setup.prove(None)
+    assert rec._lib.values is None                                  # the device-resident witness is used
+    with pytest.raises(_lib.SynthesisError):
+        setup.prove(circuit.CircomCircuit(r1cs, None))
+    setup.close()
+    # one rank of the sharded prover: its chunk of the key, the same tables, the same values
+    rec1 = _BoundaryRecorder(rank=1, world=2)
+    sh = plonk.ShardedSetupForProver.prepare_setup_for_prover(c, simple_key, rec1)
+    assert (rec1.loaded == simple_key.g1_bases[want.n // 2:want.n]).all() and (rec1._lib.selectors == want.selectors).all()
+    for form in (c, circuit.CircomCircuit(r1cs, ints_to_limbs(wit)), want, want.var_values):
+        rec1._lib.values = None
+        sh.prove(form)
+        assert (rec1._lib.values == want.var_values).all()
+    sh.upload_witness(want.var_values)
+    assert (rec1._lib.uploaded == want.var_values).all()
+    sh.close()
+    # the CLI, golden simple circuit (strict mode) and a Poseidon-shaped .r1cs / .wtns pair (general mode)
+    rec2 = _BoundaryRecorder()
+    monkeypatch.setattr(plonk, "default_context", lambda device=0: rec2)
+    key = os.path.join(SIMPLE, "setup_2^10.key")
+    cli.main(["prove", "-m", key, "-c", os.path.join(SIMPLE, "circuit.r1cs.json"), "-w", os.path.join(SIMPLE, "witness.json"),
+              "-p", str(tmp_path / "p.bin"), "-j", str(tmp_path / "p.json"), "-i", str(tmp_path / "i.json")])
+    assert (rec2._lib.values == want.var_values).all() and (rec2._lib.selectors == want.selectors).all()
+    pr1cs, pwit = synth.poseidon_r1cs(1)
+    synth.write_r1cs_bin(pr1cs, str(tmp_path / "c.r1cs"))
+    synth.write_wtns(pwit, str(tmp_path / "w.wtns"))
+    pwant = circuit.synthesize(circuit.CircomCircuit(pr1cs, pwit, None, circuit.AUX_OFFSET, False))
+    key = str(tmp_path / "big.key")                                  # the recorder never reads the bases: repeat the golden ones
+    with open(key, "wb") as f:
+        reader.Crs(np.tile(simple_key.g1_bases, (pwant.n // 1024, 1)), reader.CRS_42_G2).write(f)
+    cli.main(["prove", "-m", key, "-c", str(tmp_path / "c.r1cs"), "-w", str(tmp_path / "w.wtns"), "--allow-unpinned-transpilation",
+              "-p", str(tmp_path / "p2.bin"), "-j", str(tmp_path / "p2.json"), "-i", str(tmp_path / "i2.json")])
+    assert rec2._lib.meta == (pwant.n, pwant.num_inputs, pwant.nvars)
+    assert (rec2._lib.values == pwant.var_values).all() and (rec2._lib.wire_idx == pwant.wire_idx).all()
+    assert (rec2._lib.selectors == pwant.selectors).all()
