@@ -334,11 +334,18 @@ class ProverPool:
     def __init__(self, circuit, key_monomial_form: Crs, inflight: int = 3, device: int = 0):
         if inflight < 1:
             raise ValueError("inflight must be >= 1")
-        self.setups = [SetupForProver.prepare_setup_for_prover(circuit, key_monomial_form, None, ctx=Context(device))
-                       for _ in range(inflight)]
+        asm = _as_assembly(circuit)                      # one transpilation serves every prover of the pool
+        source = _WitnessSource(circuit, asm)
+        self.setups = []
+        for _ in range(inflight):
+            s_ = SetupForProver.prepare_setup_for_prover(asm, key_monomial_form, None, ctx=Context(device))
+            s_._source = source
+            self.setups.append(s_)
 
     def prove_all(self, witnesses, transcript: str = "keccak"):
-        """Proves every witness (var_values arrays or circuits); returns the proofs in input order."""
+        """Proves every witness (var_values arrays, Assemblies, or CircomCircuits holding other witnesses of the pool's
+        R1CS — those are assigned by the worker threads through the circuit's WitnessPlan, native host code that runs
+        beside the other provers' device work); returns the proofs in input order."""
         import queue
         import threading
         items = list(enumerate(witnesses))

@@ -696,6 +696,18 @@ def test_host_layer_hands_the_synthesised_tables_and_values_across_the_c_abi(tmp
     sh.upload_witness(want.var_values)
     assert (rec1._lib.uploaded == want.var_values).all()
     sh.close()
+    # a pool: ONE transpilation, every prover assigns other witnesses of the R1CS through the shared plan
+    made = []
+    monkeypatch.setattr(plonk, "Context", lambda device=0: made.append(_BoundaryRecorder()) or made[-1])
+    calls = []
+    real_transpile = circuit._transpile
+    monkeypatch.setattr(circuit, "_transpile", lambda *a, **k: calls.append(1) or real_transpile(*a, **k))
+    pool = plonk.ProverPool(c, simple_key, inflight=2)
+    pool.prove_all([circuit.CircomCircuit(r1cs, wit), circuit.CircomCircuit(r1cs, ints_to_limbs(wit)), want.var_values])
+    assert len(made) == 2 and len(calls) == 1
+    assert all(m._lib.values is None or (m._lib.values == want.var_values).all() for m in made)
+    assert any(m._lib.values is not None for m in made)
+    monkeypatch.setattr(circuit, "_transpile", real_transpile)
     # the CLI, golden simple circuit (strict mode) and a Poseidon-shaped .r1cs / .wtns pair (general mode)
     rec2 = _BoundaryRecorder()
     monkeypatch.setattr(plonk, "default_context", lambda device=0: rec2)
