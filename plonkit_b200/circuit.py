@@ -242,19 +242,20 @@ class WitnessPlan:
         self.num_direct = num_direct
         self.num_new = len(program)
         off = np.zeros(self.num_new + 1, dtype=np.uint64)
-        tv, tc, consts = [], [], []
+        distinct, tv, tc, kc = {}, [], [], []      # few distinct coefficients: each is converted to limbs once
         for k, (const, terms) in enumerate(program):
             for v, c in terms:
                 if not 0 <= v < num_direct + k:
                     raise ValueError("witness program entry %d reads variable %d before it is assigned" % (k, v))
                 tv.append(v)
-                tc.append(c % R_MOD)
-            consts.append(const % R_MOD)
+                tc.append(distinct.setdefault(c % R_MOD, len(distinct)))
+            kc.append(distinct.setdefault(const % R_MOD, len(distinct)))
             off[k + 1] = len(tv)
+        table = ints_to_limbs(list(distinct)) if distinct else np.zeros((0, 4), dtype=np.uint64)
         self.off = off
         self.term_var = np.asarray(tv, dtype=np.uint32)
-        self.term_coef = ints_to_limbs(tc) if tc else np.zeros((0, 4), dtype=np.uint64)
-        self.consts = ints_to_limbs(consts) if consts else np.zeros((0, 4), dtype=np.uint64)
+        self.term_coef = np.ascontiguousarray(table[np.asarray(tc, dtype=np.int64)]) if tc else np.zeros((0, 4), dtype=np.uint64)
+        self.consts = np.ascontiguousarray(table[np.asarray(kc, dtype=np.int64)]) if kc else np.zeros((0, 4), dtype=np.uint64)
         self._coef_mont = None      # the coefficients in Montgomery form, made once by the host library
 
     @property
@@ -341,12 +342,19 @@ def assembly_from_rows(rows, values, num_inputs) -> Assembly:
     while n < n_gates + 1:
         n *= 2
     wire_idx = np.zeros((4, n), dtype=np.uint32)
-    sel = [[0] * n for _ in range(7)]
+    # selector tables are sparse and draw on few distinct coefficients: convert each distinct value to limbs once
+    distinct, nz_s, nz_r, nz_v = {}, [], [], []
     for r, (a, b, c, d, q) in enumerate(rows):
         wire_idx[0, r], wire_idx[1, r], wire_idx[2, r], wire_idx[3, r] = a, b, c, d
         for s in range(7):
-            sel[s][r] = q[s]
-    selectors = np.stack([ints_to_limbs(s) for s in sel])
+            v = q[s]
+            if v:
+                nz_s.append(s)
+                nz_r.append(r)
+                nz_v.append(distinct.setdefault(v, len(distinct)))
+    selectors = np.zeros((7, n, 4), dtype=np.uint64)
+    if distinct:
+        selectors[np.asarray(nz_s), np.asarray(nz_r)] = ints_to_limbs(list(distinct))[np.asarray(nz_v)]
     var_values = None
     if values and values[-1] is not None and all(v is not None for v in values):
         var_values = ints_to_limbs(values)
