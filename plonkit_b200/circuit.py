@@ -25,12 +25,64 @@ SELECTOR_NAMES = ("q_a", "q_b", "q_c", "q_d", "q_m", "q_const", "q_dnext")
 LC = List[Tuple[int, int]]  # [(wire index, coefficient)]
 
 
-@dataclass
 class R1CS:  # src/circom_circuit.rs:32-38
-    num_inputs: int
-    num_aux: int
-    num_variables: int
-    constraints: List[Tuple[LC, LC, LC]]
+    """constraints: [(A, B, C)], every side a list of (wire, coefficient).  A circuit parsed from a `.r1cs` file by the host
+    library keeps them as arrays (`csr()`) and builds the Python list only if somebody asks for it."""
+
+    def __init__(self, num_inputs: int, num_aux: int, num_variables: int, constraints=None, csr=None):
+        self.num_inputs, self.num_aux, self.num_variables = num_inputs, num_aux, num_variables
+        self._constraints = constraints if constraints is not None or csr is not None else []
+        self._csr = csr          # (lc_off uint64[3 nc + 1], lc_var uint32[nt], lc_coef uint64[nt, 4] canonical)
+        self._native = None      # the host library's copy (made on first use)
+
+    @property
+    def num_constraints(self) -> int:
+        return len(self._constraints) if self._constraints is not None else (len(self._csr[0]) - 1) // 3
+
+    @property
+    def constraints(self):
+        if self._constraints is None:
+            off, var, coef = self._csr
+            off, var, ints = off.tolist(), var.tolist(), limbs_to_ints(coef)
+            self._constraints = [tuple(list(zip(var[off[3 * ci + k]:off[3 * ci + k + 1]], ints[off[3 * ci + k]:off[3 * ci + k + 1]]))
+                                       for k in range(3)) for ci in range((len(off) - 1) // 3)]
+        return self._constraints
+
+    def csr(self):
+        if self._csr is None:
+            off, var, coef = [0], [], []
+            for sides in self._constraints:
+                for lc in sides:
+                    for v, c in lc:
+                        var.append(v)
+                        coef.append(c % R_MOD)
+                    off.append(len(var))
+            self._csr = (np.asarray(off, dtype=np.uint64), np.asarray(var, dtype=np.uint32),
+                         ints_to_limbs(coef) if coef else np.zeros((0, 4), dtype=np.uint64))
+        return self._csr
+
+    def __eq__(self, other):
+        return isinstance(other, R1CS) and (self.num_inputs, self.num_aux, self.num_variables) == \
+            (other.num_inputs, other.num_aux, other.num_variables) and self.constraints == other.constraints
+
+    def __repr__(self):
+        return "R1CS(num_inputs=%d, num_aux=%d, num_variables=%d, %d constraints)" % (
+            self.num_inputs, self.num_aux, self.num_variables, self.num_constraints)
+
+
+class _NativeHandle:
+    """an object of the host library, freed with it"""
+
+    def __init__(self, ptr, free):
+        self.ptr, self._free = ptr, free
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self._free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
 
 
 @dataclass
@@ -120,9 +172,85 @@ class _Gates:
     program: list = field(default_factory=list)  # per new variable, in order: (const, [(var, coeff)]) — its value as a combination of earlier ones
     hints: int = 0
     stats: list = field(default_factory=list)
+    # the compiled transpiler hands the same content over as arrays instead of rows / values / program / stats
+    tables: Optional[tuple] = None     # (n, wire_idx (4, n), selectors (7, n, 4)) already padded to the domain
+    var_values: Optional[np.ndarray] = None
+    plan: Optional["WitnessPlan"] = None
+    stat_arrays: Optional[tuple] = None
+    native_rows: int = 0
+
+    @property
+    def n_rows(self) -> int:
+        return self.native_rows if self.tables is not None else len(self.rows)
+
+    @property
+    def n_stats(self) -> int:
+        return len(self.stat_arrays[0]) if self.stat_arrays is not None else len(self.stats)
+
+    def stat_list(self):
+        if self.stat_arrays is not None:
+            return [ConstraintStat(str(int(c)), int(k)) for c, k in zip(*self.stat_arrays)]
+        return self.stats
+
+
+NATIVE = [True]   # tests set NATIVE[0] = False to run the Python statement of the transpiler / parser instead of the compiled one
 
 
 def _transpile(circuit: CircomCircuit, strict: bool = True) -> _Gates:
+    """R1CS constraints -> width-4 gates: the host library's compiled transpiler (csrc/host/transpile.cpp) when it is built,
+    else `_transpile_py`, the readable statement of the same layout (tests hold the two equal)."""
+    lib = host_library() if NATIVE[0] else None
+    if lib is None:
+        return _transpile_py(circuit, strict)
+    import ctypes
+    r = circuit.r1cs
+    if r._native is None:
+        off, var, coef = r.csr()
+        h = ctypes.c_void_p()
+        vp = ctypes.c_void_p
+        if lib.ph_r1cs_from_csr(ctypes.c_uint64(r.num_inputs), ctypes.c_uint64(r.num_aux), ctypes.c_uint64(r.num_variables),
+                                ctypes.c_uint64(r.num_constraints), off.ctypes.data_as(vp), var.ctypes.data_as(vp),
+                                coef.ctypes.data_as(vp), ctypes.byref(h)):
+            raise ValueError(lib.ph_last_error().decode())
+        r._native = _NativeHandle(h, lib.ph_r1cs_free)
+    detail = (ctypes.c_uint64 * 7)()
+    out = ctypes.c_void_p()
+    rc = lib.ph_transpile(r._native.ptr, int(bool(strict)), ctypes.byref(out), detail)
+    if rc == 1:
+        raise UnpinnedTranspilation("constraint %d: A and B must be single-variable terms" % detail[1])
+    if rc == 2:
+        raise UnpinnedTranspilation("constraint %d: C side with %d variables is not pinned by any fixture" % (detail[1], detail[2]))
+    if rc == 3:
+        raise ValueError("constraint %d is the contradiction %d = 0" % (detail[1], sum(int(detail[3 + i]) << (64 * i) for i in range(4))))
+    if rc:
+        raise ValueError("transpilation failed (%d)" % rc)
+    gates = _NativeHandle(out, lib.ph_gates_free)
+    hdr = (ctypes.c_uint64 * 6)()
+    lib.ph_gates_header(gates.ptr, hdr)
+    rows, nvars, ndirect, hints, nstats, nterms = (int(x) for x in hdr)
+    n = 1
+    while n < rows + 1:
+        n *= 2
+    wire_idx = np.zeros((4, n), dtype=np.uint32)
+    selectors = np.zeros((7, n, 4), dtype=np.uint64)
+    prog_off = np.zeros(nvars - ndirect + 1, dtype=np.uint64)
+    prog_var = np.zeros(nterms, dtype=np.uint32)
+    prog_coef = np.zeros((nterms, 4), dtype=np.uint64)
+    prog_const = np.zeros((nvars - ndirect, 4), dtype=np.uint64)
+    stat_c, stat_g = np.zeros(nstats, dtype=np.uint32), np.zeros(nstats, dtype=np.uint32)
+    vp = ctypes.c_void_p
+    lib.ph_gates_export(gates.ptr, ctypes.c_uint64(n), wire_idx.ctypes.data_as(vp), selectors.ctypes.data_as(vp),
+                        prog_off.ctypes.data_as(vp), prog_var.ctypes.data_as(vp), prog_coef.ctypes.data_as(vp),
+                        prog_const.ctypes.data_as(vp), stat_c.ctypes.data_as(vp), stat_g.ctypes.data_as(vp))
+    g = _Gates()
+    g.tables, g.native_rows, g.hints, g.stat_arrays = (n, wire_idx, selectors), rows, hints, (stat_c, stat_g)
+    g.plan = WitnessPlan.from_arrays(ndirect, prog_off, prog_var, prog_coef, prog_const)
+    if circuit.witness is not None:
+        g.var_values = g.plan.assign(circuit.witness, circuit.wire_mapping)
+    return g
+
+
+def _transpile_py(circuit: CircomCircuit, strict: bool = True) -> _Gates:
     """R1CS constraints -> width-4 gates.
 
     strict = True accepts only the constraint shapes whose gate layout the reference's golden vectors pin
@@ -258,6 +386,13 @@ class WitnessPlan:
         self.consts = np.ascontiguousarray(table[np.asarray(kc, dtype=np.int64)]) if kc else np.zeros((0, 4), dtype=np.uint64)
         self._coef_mont = None      # the coefficients in Montgomery form, made once by the host library
 
+    @classmethod
+    def from_arrays(cls, num_direct, off, term_var, term_coef, consts):
+        self = cls.__new__(cls)
+        self.num_direct, self.num_new = int(num_direct), len(off) - 1
+        self.off, self.term_var, self.term_coef, self.consts, self._coef_mont = off, term_var, term_coef, consts, None
+        return self
+
     @property
     def nvars(self):
         return self.num_direct + self.num_new
@@ -318,6 +453,7 @@ def host_library():
         if os.path.exists(path):
             lib = ctypes.CDLL(path)
             lib.ph_assign_witness.restype = ctypes.c_int64
+            lib.ph_last_error.restype = ctypes.c_char_p
         _HOST_LIB[0] = lib
     return _HOST_LIB[0]
 
@@ -326,11 +462,15 @@ def transpile_with_gates_count(circuit: CircomCircuit, strict: Optional[bool] = 
     """src/transpile.rs:127-139 -> (gates_count, hints_count).  Counts exclude the public-input gates."""
     g = _transpile(circuit, circuit.strict if strict is None else strict)
     n_in = circuit.r1cs.num_inputs - 1
-    return len(g.rows) - n_in, g.hints
+    return g.n_rows - n_in, g.hints
 
 
 def synthesize(circuit: CircomCircuit, strict: Optional[bool] = None) -> Assembly:
     g = _transpile(circuit, circuit.strict if strict is None else strict)
+    if g.tables is not None:
+        n, wire_idx, selectors = g.tables
+        return Assembly(n=n, num_inputs=circuit.r1cs.num_inputs - 1, wire_idx=wire_idx, selectors=selectors,
+                        var_values=g.var_values, nvars=g.plan.nvars, num_gates=g.n_rows, plan=g.plan)
     asm = assembly_from_rows(g.rows, g.values, circuit.r1cs.num_inputs - 1)
     asm.plan = WitnessPlan(circuit.r1cs.num_variables, g.program)
     return asm
@@ -370,13 +510,13 @@ def analyse(circuit: CircomCircuit, strict: Optional[bool] = None) -> dict:
         "num_inputs": r.num_inputs,
         "num_aux": r.num_aux,
         "num_variables": r.num_variables,
-        "num_constraints": len(r.constraints),
-        "num_nontrivial_constraints": len(g.stats),
-        "num_gates": len(g.rows) - (r.num_inputs - 1),
+        "num_constraints": r.num_constraints,
+        "num_nontrivial_constraints": g.n_stats,
+        "num_gates": g.n_rows - (r.num_inputs - 1),
         "num_hints": g.hints,
     }
-    if g.stats:
-        res["constraint_stats"] = [{"name": s.name, "num_gates": s.num_gates} for s in g.stats]
+    if g.n_stats:
+        res["constraint_stats"] = [{"name": s.name, "num_gates": s.num_gates} for s in g.stat_list()]
     return res
 
 

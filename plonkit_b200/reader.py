@@ -334,6 +334,32 @@ def load_r1cs_from_json(cj: dict) -> R1CS:  # src/reader.rs:194-218
 
 
 def load_r1cs_from_bin(buf: bytes):  # src/r1cs_file.rs:100-154 + src/reader.rs:227-241
+    """-> (R1CS, wire_mapping).  Parsed by the host library (csrc/host/transpile.cpp: the constraints stay arrays, no Python
+    object per term) when it is built, else by `_load_r1cs_from_bin_py` — same checks, same result."""
+    from . import circuit as _circuit
+    lib = _circuit.host_library() if _circuit.NATIVE[0] else None
+    if lib is None:
+        return _load_r1cs_from_bin_py(buf)
+    import ctypes
+    h = ctypes.c_void_p()
+    if lib.ph_r1cs_parse_bin(buf, ctypes.c_uint64(len(buf)), ctypes.byref(h)):
+        raise ValueError(lib.ph_last_error().decode())
+    handle = _circuit._NativeHandle(h, lib.ph_r1cs_free)
+    hdr = (ctypes.c_uint64 * 6)()
+    lib.ph_r1cs_header(handle.ptr, hdr)
+    num_inputs, num_aux, num_variables, nc, nt, nmap = (int(x) for x in hdr)
+    off = np.zeros(3 * nc + 1, dtype=np.uint64)
+    var = np.zeros(nt, dtype=np.uint32)
+    coef = np.zeros((nt, 4), dtype=np.uint64)
+    wmap = np.zeros(nmap, dtype=np.uint64)
+    vp = ctypes.c_void_p
+    lib.ph_r1cs_export(handle.ptr, off.ctypes.data_as(vp), var.ctypes.data_as(vp), coef.ctypes.data_as(vp), wmap.ctypes.data_as(vp))
+    r1cs = R1CS(num_inputs, num_aux, num_variables, None, csr=(off, var, coef))
+    r1cs._native = handle
+    return r1cs, wmap.tolist()
+
+
+def _load_r1cs_from_bin_py(buf: bytes):
     if buf[:4] != b"r1cs":
         raise ValueError("Invalid magic number")
     version, num_sections = struct.unpack_from("<II", buf, 4)

@@ -33,7 +33,9 @@ def test_host_library_loads_and_exports_every_declared_symbol():
     assert lib is not None, "libplonkit_host.so is not built (python __graft_entry__.py)"
     hdr = open(os.path.join(ROOT, "include", "plonkit_host.h")).read()
     declared = set(re.findall(r"\b(ph_[a-z0-9_]+)\s*\(", hdr))
-    assert declared == {"ph_assign_witness", "ph_fr_to_mont", "ph_fr_mul"}
+    assert declared == {"ph_assign_witness", "ph_fr_to_mont", "ph_fr_mul", "ph_last_error", "ph_r1cs_parse_bin", "ph_r1cs_from_csr",
+                        "ph_r1cs_free", "ph_r1cs_header", "ph_r1cs_export", "ph_transpile", "ph_gates_free", "ph_gates_header",
+                        "ph_gates_export"}
     for name in declared:
         assert getattr(lib, name) is not None
     rng = np.random.default_rng(3)
@@ -727,3 +729,118 @@ def test_host_layer_hands_the_synthesised_tables_and_values_across_the_c_abi(tmp
     assert rec2._lib.meta == (pwant.n, pwant.num_inputs, pwant.nvars)
     assert (rec2._lib.values == pwant.var_values).all() and (rec2._lib.wire_idx == pwant.wire_idx).all()
     assert (rec2._lib.selectors == pwant.selectors).all()
+
+
+def _random_lc(rng, nv, kind):
+    if kind == "empty":
+        return []
+    if kind == "const":
+        return [(0, rng.choice([1, 5, R_MOD - 1, rng.randrange(R_MOD)]))]
+    k = {"one": 1, "two": 2, "few": rng.randint(1, 4), "many": rng.randint(5, 14)}[kind]
+    lc = [(rng.randrange(1, nv), rng.choice([1, 2, R_MOD - 1, rng.randrange(R_MOD), 0])) for _ in range(k)]
+    if kind in ("few", "many"):
+        if rng.random() < 0.3:
+            lc.append((0, rng.randrange(R_MOD)))
+        if rng.random() < 0.2:
+            lc.append((lc[0][0], rng.randrange(R_MOD)))                # the same variable twice
+        if rng.random() < 0.1:
+            lc.append((lc[0][0], (R_MOD - lc[0][1]) % R_MOD))          # ... cancelling
+    rng.shuffle(lc)
+    return lc
+
+
+def test_compiled_transpiler_equals_the_python_statement_on_random_circuits():
+    """csrc/host/transpile.cpp against circuit._transpile_py (the readable statement of the same layout): gate tables, variable
+    values, witness program, analyse() output, gate counts and the error raised (unpinned shape in strict mode, contradiction)
+    are identical on random R1CS — empty and constant sides, duplicate and cancelling terms, zero coefficients, long
+    combinations — in both modes; strict mode also on circuits made of pinned shapes only."""
+    import random
+    assert circuit.host_library() is not None, "libplonkit_host.so is not built (python __graft_entry__.py)"
+    outcomes = {}
+    for seed in range(500):
+        for strict in (False, True):
+            rng = random.Random(seed)
+            nv, ni = rng.randint(4, 30), rng.randint(1, 3)
+            pinned_only = strict and seed % 2 == 0
+            cons = []
+            for _ in range(rng.randint(1, 25)):
+                if pinned_only:
+                    def coef():
+                        return rng.choice([1, 2, R_MOD - 1, rng.randrange(1, R_MOD)])
+                    c_side = rng.choice(["one", "two", "two+const"])
+                    cc = [(v, coef()) for v in rng.sample(range(1, nv), 1 if c_side == "one" else 2)]
+                    if c_side == "two+const":
+                        cc.append((0, rng.randrange(R_MOD)))
+                    cons.append(([(rng.randrange(1, nv), coef())], [(rng.randrange(1, nv), coef())], cc))
+                else:
+                    kinds, w = ["empty", "const", "one", "two", "few", "many"], [8, 8, 40, 20, 25, 15]
+                    cons.append(tuple(_random_lc(rng, nv, rng.choices(kinds, w)[0]) for _ in range(3)))
+            r = circuit.R1CS(ni, nv - ni, nv, cons)
+            c = circuit.CircomCircuit(r, [1] + [rng.randrange(R_MOD) for _ in range(nv - 1)], None, circuit.AUX_OFFSET, strict)
+            res = []
+            for native in (True, False):
+                circuit.NATIVE[0] = native
+                try:
+                    a = circuit.synthesize(c)
+                    res.append(("ok", a.n, a.num_inputs, a.nvars, a.num_gates, a.wire_idx.tobytes(), a.selectors.tobytes(),
+                                a.var_values.tobytes(), a.plan.off.tobytes(), a.plan.term_var.tobytes(), a.plan.term_coef.tobytes(),
+                                a.plan.consts.tobytes(), str(circuit.analyse(c)), circuit.transpile_with_gates_count(c)))
+                except (circuit.UnpinnedTranspilation, ValueError) as e:
+                    res.append((type(e).__name__, str(e)))
+                finally:
+                    circuit.NATIVE[0] = True
+            assert res[0] == res[1], (seed, strict)
+            outcomes[(strict, res[0][0])] = outcomes.get((strict, res[0][0]), 0) + 1
+    assert outcomes.get((True, "ok"), 0) > 50 and outcomes.get((False, "ok"), 0) > 100      # both modes really transpile
+    assert outcomes.get((True, "UnpinnedTranspilation"), 0) > 50 and outcomes.get((False, "ValueError"), 0) > 10
+
+
+def test_compiled_r1cs_parser_equals_the_python_statement(tmp_path):
+    """csrc/host/transpile.cpp's `.r1cs` parser against reader._load_r1cs_from_bin_py: same R1CS, same wire map, same refusals
+    (magic, version, header size, field size, prime, coefficient outside the field, map size, wire 0, truncation)."""
+    import random
+    assert circuit.host_library() is not None
+
+    def both(buf):
+        out = []
+        for native in (True, False):
+            circuit.NATIVE[0] = native
+            try:
+                r, wmap = reader.load_r1cs_from_bin(buf)
+                out.append(("ok", r.num_inputs, r.num_aux, r.num_variables, r.num_constraints, r.constraints, wmap))
+            except ValueError as e:
+                out.append(("ValueError", str(e)))
+            except struct.error:
+                out.append(("ValueError", "r1cs file is truncated"))          # the Python statement's way of running off the end
+            finally:
+                circuit.NATIVE[0] = True
+        return out
+    rng = random.Random(7)
+    for case in range(40):
+        nv = rng.randint(3, 40)
+        cons = [tuple(_random_lc(rng, nv, rng.choice(["empty", "const", "one", "two", "few", "many"])) for _ in range(3))
+                for _ in range(rng.randint(0, 30))]
+        cons = [tuple([(v, c % R_MOD) for v, c in lc] for lc in sides) for sides in cons]
+        buf = _r1cs_bin(nv, rng.randint(0, 1), 1, nv - 3, cons)
+        a, b = both(buf)
+        assert a == b and a[0] == "ok" and a[5] == [tuple(list(lc) for lc in sides) for sides in cons]
+    r1cs, _ = synth.poseidon_r1cs(1)
+    synth.write_r1cs_bin(r1cs, str(tmp_path / "p.r1cs"))
+    good = open(tmp_path / "p.r1cs", "rb").read()
+    a, b = both(good)
+    assert a == b and a[0] == "ok" and a[4] == len(r1cs.constraints)
+    small = _r1cs_bin(4, 0, 1, 1, [([(2, 1)], [(2, 1)], [(3, 1)])])
+    broken = {
+        "magic": b"x" + small[1:],
+        "version": small[:4] + struct.pack("<I", 2) + small[8:],
+        "header size": small.replace(struct.pack("<IQ", 1, 64), struct.pack("<IQ", 1, 63), 1),
+        "field size": _r1cs_bin(4, 0, 1, 1, [], field_size=31),
+        "prime": small.replace(bytes.fromhex("010000f093f5e143"), bytes.fromhex("020000f093f5e143"), 1),
+        "coefficient": _r1cs_bin(4, 0, 1, 1, [([(2, 1)], [(2, 1)], [(3, 1)])]).replace((1).to_bytes(32, "little"), R_MOD.to_bytes(32, "little"), 1),
+    }
+    for name, buf in broken.items():
+        a, b = both(buf)
+        assert a == b and a[0] == "ValueError", (name, a, b)
+    for cut in (6, 20, 60, 100, len(small) - 3):
+        a, b = both(small[:cut])
+        assert a[0] == b[0] == "ValueError", (cut, a, b)
