@@ -844,3 +844,19 @@ def test_compiled_r1cs_parser_equals_the_python_statement(tmp_path):
     for cut in (6, 20, 60, 100, len(small) - 3):
         a, b = both(small[:cut])
         assert a[0] == b[0] == "ValueError", (cut, a, b)
+
+
+def test_general_mode_layout_is_frozen():
+    """This repository's own layout for unpinned constraint shapes (running sums through d / q_dnext) must not
+    drift between rounds: digest of the gate tables and variable values of the Poseidon(2)-shaped circuit, both transpilers."""
+    import hashlib
+    r1cs, wit = synth.poseidon_r1cs(1)
+    for native in (True, False):
+        circuit.NATIVE[0] = native
+        try:
+            a = circuit.synthesize(circuit.CircomCircuit(r1cs, wit, None, circuit.AUX_OFFSET, False))
+        finally:
+            circuit.NATIVE[0] = True
+        assert (a.n, a.num_gates, a.nvars) == (4096, 2309, 2311)
+        assert hashlib.sha256(a.wire_idx.tobytes() + a.selectors.tobytes() + a.var_values.tobytes()).hexdigest() == \
+            "9f5c195735571140fda1ccc06dc2840629fc2b106711c970fcdb7a0d55f7e056"
