@@ -167,6 +167,13 @@ def test_rehearse_golden_proof_and_vk(fake, simple_circuit, simple_key):
     device_tests.test_lagrange_srs_matches_oracle(fake, fake.orc, simple_circuit, simple_key)
 
 
+def test_rehearse_lagrange_key_fixture_and_synthetic_circuits(fake, simple_circuit, simple_key):
+    device_tests.test_prove_with_lagrange_key_gives_the_same_bytes(fake, fake.orc, simple_circuit, simple_key)
+    device_tests.test_poseidon_shaped_golden_fixture(fake, simple_key)
+    device_tests.test_proofs_equal_oracle_on_synthetic_circuits(fake, fake.orc, "random", 6)     # incl. plonk.verify on the result
+    device_tests.test_public_input_polynomial_paths(fake, fake.orc, 9)
+
+
 def test_rehearse_error_behaviour(fake, simple_circuit, simple_key):
     device_tests.test_error_behaviour_mirrors_reference(fake, fake.orc, simple_circuit, simple_key)
 
