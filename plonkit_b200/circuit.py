@@ -199,11 +199,14 @@ NATIVE = [True]   # tests set NATIVE[0] = False to run the Python statement of t
 def _transpile(circuit: CircomCircuit, strict: bool = True) -> _Gates:
     """R1CS constraints -> width-4 gates: the host library's compiled transpiler (csrc/host/transpile.cpp) when it is built,
     else `_transpile_py`, the readable statement of the same layout (tests hold the two equal)."""
+    r = circuit.r1cs
+    _, wires, _ = r.csr()
+    if len(wires) and int(wires.max()) >= r.num_variables:
+        raise ValueError("a constraint refers to wire %d but the circuit has %d variables" % (int(wires.max()), r.num_variables))
     lib = host_library() if NATIVE[0] else None
     if lib is None:
         return _transpile_py(circuit, strict)
     import ctypes
-    r = circuit.r1cs
     if r._native is None:
         off, var, coef = r.csr()
         h = ctypes.c_void_p()

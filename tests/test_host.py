@@ -846,6 +846,17 @@ def test_compiled_r1cs_parser_equals_the_python_statement(tmp_path):
         assert a[0] == b[0] == "ValueError", (cut, a, b)
 
 
+def test_constraint_with_a_wire_beyond_the_circuit_is_refused():
+    r = circuit.R1CS(2, 2, 4, [([(2, 1)], [(7, 1)], [(3, 1)])])
+    for native in (True, False):
+        circuit.NATIVE[0] = native
+        try:
+            with pytest.raises(ValueError, match="wire 7"):
+                circuit.synthesize(circuit.CircomCircuit(r, None))
+        finally:
+            circuit.NATIVE[0] = True
+
+
 def test_general_mode_layout_is_frozen():
     """This repository's own layout for unpinned constraint shapes (running sums through d / q_dnext) must not
     drift between rounds: digest of the gate tables and variable values of the Poseidon(2)-shaped circuit, both transpilers."""
