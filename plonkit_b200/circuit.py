@@ -207,7 +207,8 @@ def _transpile(circuit: CircomCircuit, strict: bool = True) -> _Gates:
     if lib is None:
         return _transpile_py(circuit, strict)
     import ctypes
-    if r._native is None:
+    native = r._native           # held locally: ranks of a sharded prover transpile the same R1CS from several threads
+    if native is None:
         off, var, coef = r.csr()
         h = ctypes.c_void_p()
         vp = ctypes.c_void_p
@@ -215,10 +216,10 @@ def _transpile(circuit: CircomCircuit, strict: bool = True) -> _Gates:
                                 ctypes.c_uint64(r.num_constraints), off.ctypes.data_as(vp), var.ctypes.data_as(vp),
                                 coef.ctypes.data_as(vp), ctypes.byref(h)):
             raise ValueError(lib.ph_last_error().decode())
-        r._native = _NativeHandle(h, lib.ph_r1cs_free)
+        native = r._native = _NativeHandle(h, lib.ph_r1cs_free)
     detail = (ctypes.c_uint64 * 7)()
     out = ctypes.c_void_p()
-    rc = lib.ph_transpile(r._native.ptr, int(bool(strict)), ctypes.byref(out), detail)
+    rc = lib.ph_transpile(native.ptr, int(bool(strict)), ctypes.byref(out), detail)
     if rc == 1:
         raise UnpinnedTranspilation("constraint %d: A and B must be single-variable terms" % detail[1])
     if rc == 2:
@@ -420,13 +421,16 @@ class WitnessPlan:
             import ctypes
             import os
             vp = ctypes.c_void_p
-            if self._coef_mont is None:
-                self._coef_mont = np.zeros_like(self.term_coef)
-                lib.ph_fr_to_mont(self.term_coef.ctypes.data_as(vp), self._coef_mont.ctypes.data_as(vp), ctypes.c_uint64(len(self.term_coef)))
+            coef_mont = self._coef_mont
+            if coef_mont is None:
+                # filled before it is published: provers of a pool / ranks of a sharded prover assign concurrently
+                coef_mont = np.zeros_like(self.term_coef)
+                lib.ph_fr_to_mont(self.term_coef.ctypes.data_as(vp), coef_mont.ctypes.data_as(vp), ctypes.c_uint64(len(self.term_coef)))
+                self._coef_mont = coef_mont
             if threads is None:
                 threads = min(16, os.cpu_count() or 1)
             rc = lib.ph_assign_witness(ctypes.c_uint64(self.num_direct), ctypes.c_uint64(self.num_new), self.off.ctypes.data_as(vp),
-                                       self.term_var.ctypes.data_as(vp), self._coef_mont.ctypes.data_as(vp), 1,
+                                       self.term_var.ctypes.data_as(vp), coef_mont.ctypes.data_as(vp), 1,
                                        self.consts.ctypes.data_as(vp), values.ctypes.data_as(vp), int(threads))
             if rc:
                 raise ValueError("witness assignment failed at variable %d (value not in the field, or a malformed program)" % (rc - 1))

@@ -871,3 +871,47 @@ def test_general_mode_layout_is_frozen():
         assert (a.n, a.num_gates, a.nvars) == (4096, 2309, 2311)
         assert hashlib.sha256(a.wire_idx.tobytes() + a.selectors.tobytes() + a.var_values.tobytes()).hexdigest() == \
             "9f5c195735571140fda1ccc06dc2840629fc2b106711c970fcdb7a0d55f7e056"
+
+
+def test_concurrent_synthesis_and_assignment_on_shared_objects():
+    """The ranks of a sharded prover (threads) transpile the same R1CS object at once, and the provers of a pool assign witnesses
+    through one shared plan at once: lazily made state (the library's copy of the R1CS, the Montgomery coefficients of the
+    plan) must be complete before another thread can see it."""
+    import threading
+    for trial in range(5):
+        r1cs, wit = synth.poseidon_r1cs(6)
+        want = None
+        circuit.NATIVE[0] = False
+        try:
+            want = circuit.synthesize(circuit.CircomCircuit(r1cs, wit, None, circuit.AUX_OFFSET, False))
+        finally:
+            circuit.NATIVE[0] = True
+        fresh = circuit.R1CS(r1cs.num_inputs, r1cs.num_aux, r1cs.num_variables, r1cs.constraints)
+        out, errs = [None] * 8, []
+
+        def run(i):
+            try:
+                a = circuit.synthesize(circuit.CircomCircuit(fresh, None, None, circuit.AUX_OFFSET, False))
+                out[i] = (a, a.plan.assign(wit))
+            except Exception as e:   # noqa: BLE001
+                errs.append(e)
+        th = [threading.Thread(target=run, args=(i,)) for i in range(8)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        assert not errs
+        for a, v in out:
+            assert (a.selectors == want.selectors).all() and (a.wire_idx == want.wire_idx).all() and (v == want.var_values).all()
+        shared = out[0][0].plan
+        shared._coef_mont = None
+        res = [None] * 8
+
+        def assign(i):
+            res[i] = shared.assign(wit, threads=2)
+        th = [threading.Thread(target=assign, args=(i,)) for i in range(8)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        assert all((v == want.var_values).all() for v in res)
