@@ -13,6 +13,7 @@ import numpy as np
 import pytest
 
 import test_gpu_prove as device_tests
+import test_gpu_shard as shard_tests
 from plonkit_b200 import _lib, circuit, plonk, reader
 from plonkit_b200.bn254 import ints_to_limbs
 
@@ -119,11 +120,48 @@ class OracleBackedContext:
                 _view(inputs_ptr, np.uint64, 4 * p.num_inputs)[:] = ints_to_limbs(p.input_values).reshape(-1)
             return 0
 
+        # ---- the sharded prover's entry points: every rank holds its chunk of the key; the stand-in puts them together
+        def pk_dist_setup_create(self, h, a_ref, out_ref):
+            n, world = int(a_ref._obj.n), self.ctx.world
+            if n % world or n < world * world:
+                self.err = b"domain too small for this many ranks"
+                return 6
+            full, self.ctx.bases = self.ctx.bases, np.zeros((n, 8), dtype=np.uint64)     # size check of the 1-GPU path does not apply
+            try:
+                return self.pk_setup_create(h, a_ref, out_ref)
+            finally:
+                self.ctx.bases = full
+
+        def _with_full_key(self, fn, *args):
+            mine = self.ctx.bases
+            self.ctx.bases = np.concatenate([m.bases for m in self.ctx.group.members])
+            try:
+                return fn(*args)
+            finally:
+                self.ctx.bases = mine
+
+        def pk_dist_setup_commitments(self, h, sh, out_ptr):
+            return self._with_full_key(self.pk_setup_commitments, h, sh, out_ptr)
+
+        def pk_dist_prove(self, h, sh, ptr, nvars, pr_ref, inputs_ptr):
+            return self._with_full_key(self.pk_prove, h, sh, ptr, nvars, pr_ref, inputs_ptr)
+
+        def pk_dist_witness_upload(self, h, sh, ptr, nvars):
+            return self.pk_witness_upload(h, sh, ptr, nvars)
+
+        def pk_dist_setup_destroy(self, sh):
+            return self.pk_setup_destroy(sh)
+
     def __init__(self, orc):
         self._lib, self._h, self._children = self._Lib(self, orc), 1, set()
         self.orc = orc
         self.srs_tag = self.lagrange_tag = None
         self.bases = self.lagrange = None
+        self.rank, self.world, self.group = 0, 1, None
+
+    def attach_group(self, group, rank):
+        self.rank, self.world, self.group = rank, group.world, group
+        group.members[rank] = self
 
     def _check(self, rc):
         if rc:
@@ -145,6 +183,22 @@ class OracleBackedContext:
 
     def close(self):
         pass
+
+
+class _Group:
+    def __init__(self, world):
+        self.world, self.members = world, [None] * world
+
+    def close(self):
+        pass
+
+
+@pytest.fixture()
+def fake_ranks(orc, monkeypatch):
+    """ShardedProver builds its own contexts and communicator: hand it stand-ins"""
+    monkeypatch.setattr(plonk, "Context", lambda device=0: OracleBackedContext(orc))
+    monkeypatch.setattr(_lib, "CommGroup", _Group)
+    return orc
 
 
 @pytest.fixture()
@@ -201,3 +255,11 @@ def test_rehearse_both_transpilers(fake, tmp_path, simple_circuit, simple_key):
         device_tests.test_cli_prove_and_export_vk_write_the_golden_files(tmp_path)
     finally:
         circuit.NATIVE[0] = True
+
+
+def test_rehearse_sharded_prover_threads(fake_ranks, simple_circuit, simple_key):
+    """the ranks-as-threads flows of tests/test_gpu_shard.py: every rank synthesises the SAME circuit object concurrently"""
+    for _ in range(3):
+        shard_tests.test_sharded_prover_reproduces_reference_proof_bin(simple_circuit, simple_key)
+    shard_tests.test_sharded_proof_bytes_equal_oracle(fake_ranks, 4, "poseidon", 6)
+    shard_tests.test_sharded_prover_errors_reach_every_rank_and_do_not_stick(fake_ranks)
