@@ -191,6 +191,18 @@ def load_proof(filename: str) -> Proof:  # src/reader.rs:23-25
         return Proof.read(f)
 
 
+def load_proofs_from_list(list_file: str) -> List[Proof]:  # src/reader.rs:27-47
+    """one proof file name per line (the input of `recursive-prove`); all proofs must have the same number of inputs"""
+    with open(list_file) as f:
+        names = [line.rstrip("\n") for line in f]
+    proofs = [load_proof(name) for name in names]
+    if not proofs:
+        raise ValueError("no proof file found!")
+    if any(p.num_inputs != proofs[0].num_inputs for p in proofs):
+        raise ValueError("proofs num_inputs mismatch!")
+    return proofs
+
+
 # ---------------------------------------------------------------- VerificationKey (App. B.3)
 @dataclass
 class VerificationKey:
@@ -243,6 +255,16 @@ def load_witness_from_file(filename: str) -> List[int]:  # src/reader.rs:92-98
     if filename.endswith("json"):
         with open(filename) as f:
             return [int(x) % R_MOD for x in json.load(f)]
+    with open(filename, "rb") as f:
+        return load_witness_from_array(f.read())
+
+
+def load_witness_from_json_file(filename: str) -> List[int]:  # src/reader.rs:101-104
+    with open(filename) as f:
+        return [int(x) % R_MOD for x in json.load(f)]
+
+
+def load_witness_from_bin_file(filename: str) -> List[int]:  # src/reader.rs:113-116
     with open(filename, "rb") as f:
         return load_witness_from_array(f.read())
 

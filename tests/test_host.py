@@ -121,6 +121,27 @@ def test_wtns_parser_and_its_error_paths():
         reader.load_witness_from_array(_wtns([R_MOD]))
 
 
+def test_proof_list_and_witness_file_loaders(tmp_path):
+    """src/reader.rs:27-47 (load_proofs_from_list), :101-116 (the per-format witness loaders)"""
+    golden = os.path.join(SIMPLE, "proof.bin")
+    (tmp_path / "list.txt").write_text(golden + "\n" + golden + "\n")
+    proofs = reader.load_proofs_from_list(str(tmp_path / "list.txt"))
+    assert len(proofs) == 2 and proofs[0].to_bytes() == proofs[1].to_bytes() == open(golden, "rb").read()
+    (tmp_path / "empty.txt").write_text("")
+    with pytest.raises(ValueError, match="no proof file found"):
+        reader.load_proofs_from_list(str(tmp_path / "empty.txt"))
+    other = reader.load_proof(golden)
+    other.num_inputs, other.input_values = 2, other.input_values * 2
+    (tmp_path / "other.bin").write_bytes(other.to_bytes())
+    (tmp_path / "mixed.txt").write_text(golden + "\n" + str(tmp_path / "other.bin") + "\n")
+    with pytest.raises(ValueError, match="num_inputs mismatch"):
+        reader.load_proofs_from_list(str(tmp_path / "mixed.txt"))
+    wj = os.path.join(SIMPLE, "witness.json")
+    assert reader.load_witness_from_json_file(wj) == reader.load_witness_from_file(wj)
+    (tmp_path / "w.wtns").write_bytes(_wtns([1, 35, 3, 9]))
+    assert reader.load_witness_from_bin_file(str(tmp_path / "w.wtns")) == [1, 35, 3, 9]
+
+
 def test_witness_as_limbs_equals_witness_as_integers(tmp_path):
     """reader.load_witness_limbs: the same values as load_witness_from_file, as the (len, 4) limb array the prover consumes
     (.wtns elements taken as they lie in the file), same field check; a CircomCircuit holding it behaves the same."""
