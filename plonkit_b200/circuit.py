@@ -227,7 +227,7 @@ def _transpile(circuit: CircomCircuit, strict: bool = True) -> _Gates:
     if rc == 3:
         raise ValueError("constraint %d is the contradiction %d = 0" % (detail[1], sum(int(detail[3 + i]) << (64 * i) for i in range(4))))
     if rc:
-        raise ValueError("transpilation failed (%d)" % rc)
+        raise ValueError(lib.ph_last_error().decode() or "transpilation failed (%d)" % rc)
     gates = _NativeHandle(out, lib.ph_gates_free)
     hdr = (ctypes.c_uint64 * 6)()
     lib.ph_gates_header(gates.ptr, hdr)

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <utility>
 #include <vector>
@@ -86,7 +87,8 @@ bool parse_bin(const uint8_t* buf, uint64_t len, R1cs& r) {
     uint64_t p = sec_off[2];
     const uint64_t end = len;
     r.off.assign(1, 0);
-    r.off.reserve(3 * (uint64_t)n_constraints + 1);
+    // the count comes from the file: never reserve more than the bytes that are left could hold (4 per linear combination)
+    r.off.reserve(std::min<uint64_t>(3 * (uint64_t)n_constraints, (p <= len ? len - p : 0) / 4) + 1);
     for (uint64_t c = 0; c < 3 * (uint64_t)n_constraints; ++c) {
         if (p + 4 > end) return fail("r1cs file is truncated");
         const uint32_t k = rd32(buf + p);
@@ -108,6 +110,7 @@ bool parse_bin(const uint8_t* buf, uint64_t len, R1cs& r) {
     for (uint32_t i = 0; i < n_wires; ++i) r.wire_map[i] = rd64(buf + sec_off[3] + 8 * (uint64_t)i);
     if (n_wires && r.wire_map[0] != 0) return fail("Wire 0 should always be mapped to 0");
     r.num_inputs = 1 + (uint64_t)n_pub_in + n_pub_out;
+    if (r.num_inputs > n_wires) return fail("more public inputs and outputs than wires");
     r.num_aux = (uint64_t)n_wires - r.num_inputs;
     r.num_variables = n_wires;
     return true;
@@ -292,9 +295,16 @@ const char* ph_last_error(void) { return g_error.c_str(); }
 
 // parse an iden3 .r1cs image (src/r1cs_file.rs:100-154); 0 on success, else ph_last_error() says why
 int ph_r1cs_parse_bin(const uint8_t* buf, uint64_t len, ph_r1cs** out) {
-    R1cs* r = new R1cs();
-    if (!parse_bin(buf, len, *r)) {
+    R1cs* r = nullptr;
+    try {
+        r = new R1cs();
+        if (!parse_bin(buf, len, *r)) {
+            delete r;
+            return 1;
+        }
+    } catch (const std::exception& e) {  // nothing unwinds across the C boundary
         delete r;
+        g_error = std::string("r1cs parser: ") + e.what();
         return 1;
     }
     *out = reinterpret_cast<ph_r1cs*>(r);
@@ -303,19 +313,26 @@ int ph_r1cs_parse_bin(const uint8_t* buf, uint64_t len, ph_r1cs** out) {
 // the same object from arrays: lc_off has 3 * num_constraints + 1 entries (A, B, C of every constraint), coefficients canonical
 int ph_r1cs_from_csr(uint64_t num_inputs, uint64_t num_aux, uint64_t num_variables, uint64_t num_constraints, const uint64_t* lc_off,
                      const uint32_t* lc_var, const uint64_t* lc_coef, ph_r1cs** out) {
-    R1cs* r = new R1cs();
-    r->num_inputs = num_inputs; r->num_aux = num_aux; r->num_variables = num_variables;
-    r->off.assign(lc_off, lc_off + 3 * num_constraints + 1);
-    const uint64_t nt = r->off.back();
-    r->var.assign(lc_var, lc_var + nt);
-    r->coef.resize(nt);
-    for (uint64_t i = 0; i < nt; ++i) {
-        memcpy(r->coef[i].v, lc_coef + 4 * i, 32);
-        if (!canonical(r->coef[i].v)) {
-            delete r;
-            g_error = "coefficient is not in the field";
-            return 1;
+    R1cs* r = nullptr;
+    try {
+        r = new R1cs();
+        r->num_inputs = num_inputs; r->num_aux = num_aux; r->num_variables = num_variables;
+        r->off.assign(lc_off, lc_off + 3 * num_constraints + 1);
+        const uint64_t nt = r->off.back();
+        r->var.assign(lc_var, lc_var + nt);
+        r->coef.resize(nt);
+        for (uint64_t i = 0; i < nt; ++i) {
+            memcpy(r->coef[i].v, lc_coef + 4 * i, 32);
+            if (!canonical(r->coef[i].v)) {
+                delete r;
+                g_error = "coefficient is not in the field";
+                return 1;
+            }
         }
+    } catch (const std::exception& e) {
+        delete r;
+        g_error = std::string("r1cs from arrays: ") + e.what();
+        return 1;
     }
     *out = reinterpret_cast<ph_r1cs*>(r);
     return 0;
@@ -340,8 +357,16 @@ void ph_r1cs_export(const ph_r1cs* h, uint64_t* lc_off, uint32_t* lc_var, uint64
 // R1CS -> width-4 gates.  0 on success; 1 / 2 = a constraint shape strict mode does not accept, 3 = a contradiction:
 // detail = {code, constraint index, number of C-side variables, constant limbs 0..3}
 int ph_transpile(const ph_r1cs* h, int strict, ph_gates** out, uint64_t detail[7]) {
-    Gates* g = new Gates();
-    const int rc = transpile(*reinterpret_cast<const R1cs*>(h), strict != 0, *g);
+    Gates* g = nullptr;
+    int rc;
+    try {
+        g = new Gates();
+        rc = transpile(*reinterpret_cast<const R1cs*>(h), strict != 0, *g);
+    } catch (const std::exception& e) {
+        delete g;
+        g_error = std::string("transpiler: ") + e.what();
+        return 4;
+    }
     if (rc) {
         detail[0] = g->detail[0]; detail[1] = g->detail[1]; detail[2] = g->detail[2];
         memcpy(detail + 3, g->err_const.v, 32);

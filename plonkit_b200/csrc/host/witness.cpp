@@ -9,6 +9,7 @@
 // that this file evaluates per proof: 254-bit Montgomery arithmetic on 4 x 64-bit limbs.
 #include <cstdint>
 #include <cstring>
+#include <exception>
 #include <thread>
 #include <vector>
 
@@ -59,24 +60,36 @@ int64_t ph_assign_witness(uint64_t num_direct, uint64_t num_new, const uint64_t*
     if (threads < 1) threads = 1;
     if (threads == 1 || num_new < 4096)
         return run_range(0, num_new, num_direct, off, term_var, term_coef, coef_is_mont, consts, values);
-    // sufmin[k] = the oldest introduced variable (as a program index) read by any entry >= k
-    std::vector<uint64_t> sufmin(num_new + 1, UINT64_MAX);
-    for (uint64_t k = num_new; k-- > 0;) {
-        uint64_t m = sufmin[k + 1];
-        for (uint64_t j = off[k]; j < off[k + 1]; ++j)
-            if (term_var[j] >= num_direct && term_var[j] - num_direct < m) m = term_var[j] - num_direct;
-        sufmin[k] = m;
-    }
-    std::vector<uint64_t> cuts(1, 0);
-    const uint64_t total = off[num_new], target = total / (uint64_t)threads + 1;
-    for (uint64_t k = 1; k < num_new && (int)cuts.size() < threads; ++k)
-        if (off[k] >= target * cuts.size() && sufmin[k] >= k) cuts.push_back(k);
-    cuts.push_back(num_new);
-    const size_t pieces = cuts.size() - 1;
-    std::vector<int64_t> rc(pieces, 0);
+    std::vector<uint64_t> cuts;
+    std::vector<int64_t> rc;
     std::vector<std::thread> pool;
-    for (size_t t = 1; t < pieces; ++t)
-        pool.emplace_back([&, t] { rc[t] = run_range(cuts[t], cuts[t + 1], num_direct, off, term_var, term_coef, coef_is_mont, consts, values); });
+    try {
+        // sufmin[k] = the oldest introduced variable (as a program index) read by any entry >= k
+        std::vector<uint64_t> sufmin(num_new + 1, UINT64_MAX);
+        for (uint64_t k = num_new; k-- > 0;) {
+            uint64_t m = sufmin[k + 1];
+            for (uint64_t j = off[k]; j < off[k + 1]; ++j)
+                if (term_var[j] >= num_direct && term_var[j] - num_direct < m) m = term_var[j] - num_direct;
+            sufmin[k] = m;
+        }
+        cuts.push_back(0);
+        const uint64_t total = off[num_new], target = total / (uint64_t)threads + 1;
+        for (uint64_t k = 1; k < num_new && (int)cuts.size() < threads; ++k)
+            if (off[k] >= target * cuts.size() && sufmin[k] >= k) cuts.push_back(k);
+        cuts.push_back(num_new);
+        rc.assign(cuts.size() - 1, 0);
+        pool.reserve(cuts.size());
+    } catch (const std::exception&) {  // no memory for the plan of the split: nothing unwinds across the C boundary
+        return run_range(0, num_new, num_direct, off, term_var, term_coef, coef_is_mont, consts, values);
+    }
+    const size_t pieces = cuts.size() - 1;
+    for (size_t t = 1; t < pieces; ++t) {
+        try {
+            pool.emplace_back([&, t] { rc[t] = run_range(cuts[t], cuts[t + 1], num_direct, off, term_var, term_coef, coef_is_mont, consts, values); });
+        } catch (const std::exception&) {  // no thread to be had: this piece runs here
+            rc[t] = run_range(cuts[t], cuts[t + 1], num_direct, off, term_var, term_coef, coef_is_mont, consts, values);
+        }
+    }
     rc[0] = run_range(cuts[0], cuts[1], num_direct, off, term_var, term_coef, coef_is_mont, consts, values);
     for (auto& th : pool) th.join();
     for (size_t t = 0; t < pieces; ++t)

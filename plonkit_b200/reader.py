@@ -431,4 +431,6 @@ def _load_r1cs_from_bin_py(buf: bytes):
     if wire_mapping and wire_mapping[0] != 0:
         raise ValueError("Wire 0 should always be mapped to 0")
     num_inputs = 1 + n_pub_in + n_pub_out
+    if num_inputs > n_wires:
+        raise ValueError("more public inputs and outputs than wires")
     return R1CS(num_inputs, n_wires - num_inputs, n_wires, constraints), wire_mapping
