@@ -61,6 +61,15 @@ _crs_tokens = itertools.count(1)
 
 
 def _read_exact(f, n: int, what: str) -> bytes:
+    # n may come straight from the file: compare it with what is left before asking for that many bytes
+    try:
+        pos = f.tell()
+        left = f.seek(0, 2) - pos
+        f.seek(pos)
+    except (OSError, AttributeError, ValueError):
+        left = None
+    if n < 0 or n > (1 << 48) or (left is not None and n > left):
+        raise ValueError("truncated file: %s needs %d bytes%s" % (what, n, "" if left is None else ", %d are left" % left))
     b = f.read(n)
     if len(b) != n:
         raise ValueError("truncated file: %s needs %d bytes, got %d" % (what, n, len(b)))
@@ -156,31 +165,40 @@ class Proof:
 
     @staticmethod
     def read(f, gated: bool = False) -> "Proof":
+        """bellman `Proof::read`; a malformed file is a ValueError (short reads, counts other than the protocol's, a number of
+        inputs no file could hold), never a partial object."""
         def u64():
-            return struct.unpack(">Q", f.read(8))[0]
+            return struct.unpack(">Q", _read_exact(f, 8, "a count of the proof"))[0]
+
+        def count(want, what):
+            got = u64()
+            if got != want:
+                raise ValueError("proof file: %d %s, expected %d" % (got, what, want))
 
         def frs(k):
-            return limbs_to_ints(be_bytes_to_limbs(f.read(32 * k), k))
+            return limbs_to_ints(be_bytes_to_limbs(_read_exact(f, 32 * k, "field elements of the proof"), k))
 
         def g1s(k):
-            return g1_from_bytes(f.read(64 * k), k)
+            return g1_from_bytes(_read_exact(f, 64 * k, "points of the proof"), k)
         n, ni = u64(), u64()
+        if ni > 1 << 28:
+            raise ValueError("proof file: %d public inputs" % ni)
         inputs = frs(ni)
-        assert u64() == 4
+        count(4, "wire commitments")
         wc = g1s(4)
         gp = g1s(1)[0]
-        assert u64() == 4
+        count(4, "quotient commitments")
         qc = g1s(4)
-        assert u64() == 4
+        count(4, "wire values at z")
         wz = frs(4)
-        assert u64() == 1
+        count(1, "wire values at z omega")
         wzo = frs(1)
         gpz, tz, rz = frs(3)
-        assert u64() == 3
+        count(3, "permutation polynomials at z")
         pz = frs(3)
         gsel = None
         if gated:
-            assert u64() == 2
+            count(2, "gate selectors at z")
             gsel = frs(2)
         o1, o2 = g1s(1)[0], g1s(1)[0]
         return Proof(n, ni, inputs, wc, gp, qc, wz, wzo, gpz, tz, rz, pz, o1, o2, gsel)
@@ -231,16 +249,21 @@ class VerificationKey:
     @staticmethod
     def read(f) -> "VerificationKey":
         def u64():
-            return struct.unpack(">Q", f.read(8))[0]
+            return struct.unpack(">Q", _read_exact(f, 8, "a count of the verification key"))[0]
+
+        def count(want, what):
+            got = u64()
+            if got != want:
+                raise ValueError("verification key file: %d %s, expected %d" % (got, what, want))
         n, ni = u64(), u64()
-        assert u64() == 6
-        sel = g1_from_bytes(f.read(64 * 6), 6)
-        assert u64() == 1
-        nxt = g1_from_bytes(f.read(64), 1)
-        assert u64() == 4
-        perm = g1_from_bytes(f.read(64 * 4), 4)
-        assert u64() == 3
-        nr = limbs_to_ints(be_bytes_to_limbs(f.read(96), 3))
+        count(6, "selector commitments")
+        sel = g1_from_bytes(_read_exact(f, 64 * 6, "selector commitments"), 6)
+        count(1, "next-step selector commitments")
+        nxt = g1_from_bytes(_read_exact(f, 64, "next-step selector commitment"), 1)
+        count(4, "permutation commitments")
+        perm = g1_from_bytes(_read_exact(f, 64 * 4, "permutation commitments"), 4)
+        count(3, "non-residues")
+        nr = limbs_to_ints(be_bytes_to_limbs(_read_exact(f, 96, "non-residues"), 3))
         g2 = _read_exact(f, 256, "G2 elements of the verification key")
         return VerificationKey(n, ni, sel, nxt, perm, nr, g2)
 

@@ -978,3 +978,34 @@ def test_compiled_r1cs_parser_survives_hostile_files():
         except (ValueError, circuit.UnpinnedTranspilation):
             pass
     assert accepted > 100 and refused > 100
+
+
+def test_key_proof_and_vk_readers_refuse_malformed_files_cleanly():
+    """Mutated golden setup_2^10.key / proof.bin / vk.bin (flipped bytes, truncations, huge counts): every read returns an object
+    or raises ValueError — never another exception type, a partial object, or a read sized by a number from the file."""
+    import random
+    files = {"key": (os.path.join(SIMPLE, "setup_2^10.key"), lambda b: reader.Crs.read(io.BytesIO(b))),
+             "proof": (os.path.join(SIMPLE, "proof.bin"), lambda b: reader.Proof.read(io.BytesIO(b))),
+             "vk": (os.path.join(SIMPLE, "vk.bin"), lambda b: reader.VerificationKey.read(io.BytesIO(b)))}
+    blobs = {k: open(p, "rb").read() for k, (p, _) in files.items()}
+    rng = random.Random(3)
+    refused = 0
+    for it in range(900):
+        name = rng.choice(sorted(files))
+        b = bytearray(blobs[name])
+        kind = rng.randrange(3)
+        if kind == 0:
+            for _ in range(rng.randint(1, 4)):
+                b[rng.randrange(min(len(b), 400))] = rng.randrange(256)
+        elif kind == 1:
+            b = b[:rng.randrange(len(b))]
+        else:
+            pos = rng.randrange(0, min(len(b) - 8, 64))
+            b[pos:pos + 8] = struct.pack(">Q", rng.choice([0, 1, 2 ** 32 - 1, 2 ** 63, 2 ** 64 - 1, rng.randrange(2 ** 40)]))
+        try:
+            files[name][1](bytes(b))
+        except ValueError:
+            refused += 1
+    assert refused > 200
+    with pytest.raises(ValueError, match="expected 4"):
+        reader.Proof.read(io.BytesIO(blobs["proof"][:48] + struct.pack(">Q", 5) + blobs["proof"][56:]))
