@@ -323,6 +323,13 @@ def load_witness_from_array(buffer: bytes) -> List[int]:  # src/reader.rs:119-17
 
 def _wtns_body(buffer: bytes):
     """header checks of src/reader.rs:119-175 -> (offset of the first element, number of elements)"""
+    try:
+        return _wtns_body_checked(buffer)
+    except struct.error:
+        raise ValueError("witness file is truncated") from None
+
+
+def _wtns_body_checked(buffer: bytes):
     if buffer[:4] != b"wtns":
         raise ValueError("invalid file header")
     version, num_sections = struct.unpack_from("<II", buffer, 4)
@@ -405,6 +412,13 @@ def load_r1cs_from_bin(buf: bytes):  # src/r1cs_file.rs:100-154 + src/reader.rs:
 
 
 def _load_r1cs_from_bin_py(buf: bytes):
+    try:
+        return _load_r1cs_from_bin_checked(buf)
+    except (struct.error, KeyError):
+        raise ValueError("r1cs file is truncated or lacks a section") from None
+
+
+def _load_r1cs_from_bin_checked(buf: bytes):
     if buf[:4] != b"r1cs":
         raise ValueError("Invalid magic number")
     version, num_sections = struct.unpack_from("<II", buf, 4)
