@@ -184,6 +184,9 @@ class OracleBackedContext:
     def close(self):
         pass
 
+    def profile(self):
+        return {"kernel_launches": 1}
+
 
 class _Group:
     def __init__(self, world):
@@ -263,3 +266,11 @@ def test_rehearse_sharded_prover_threads(fake_ranks, simple_circuit, simple_key)
         shard_tests.test_sharded_prover_reproduces_reference_proof_bin(simple_circuit, simple_key)
     shard_tests.test_sharded_proof_bytes_equal_oracle(fake_ranks, 4, "poseidon", 6)
     shard_tests.test_sharded_prover_errors_reach_every_rank_and_do_not_stick(fake_ranks)
+
+
+def test_rehearse_smoke(fake_ranks, monkeypatch, capsys):
+    """__graft_entry__.smoke()'s host flow (what the driver runs on the B200 before the bench)"""
+    import __graft_entry__ as entry
+    monkeypatch.setattr(_lib, "Context", lambda device=0: OracleBackedContext(fake_ranks))
+    entry.smoke()
+    assert "smoke ok" in capsys.readouterr().out
