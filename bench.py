@@ -411,7 +411,8 @@ def bench_ours(args):
         "prep_s": prep_s,
     }
     if shard is not None:
-        shard["speedup_vs_one_gpu"] = (ms_single / args.steps) / shard["ms_per_proof"]
+        if "ms_per_proof" in shard:
+            shard["speedup_vs_one_gpu"] = (ms_single / args.steps) / shard["ms_per_proof"]
         out["sharded_single_proof"] = shard
     # BASELINE.json's secondary metrics on the same GPU: single-set MSM (uniform scalars) and NTT at the bench size
     try:
